@@ -1,0 +1,122 @@
+"""ctypes binding of the C ABI declared in include/aps.h.
+
+The structures here are the Python spelling of `aps_params` / `aps_batch`; the oracle's test
+binding (oracle/oracle.py) re-uses them so that both sides are driven with the same descriptor.
+The product library is `csrc/libaps_b200.so`, built in-tree by `build.py`.  There is no CPU
+fallback: if the library is missing, `load()` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "csrc", "libaps_b200.so")
+
+APS_OK = 0
+APS_ERR_INVALID, APS_ERR_NO_DEVICE, APS_ERR_CUDA, APS_ERR_CAPACITY = 1, 2, 3, 4
+APS_RUN_DONE, APS_RUN_EMPTY, APS_RUN_DRAWS_EXHAUSTED, APS_RUN_MAX_EVENTS = 0, 1, 2, 3
+APS_FLAG_CROWDING = 1
+APS_REC_COUNTS, APS_REC_POS, APS_REC_MLOCAL = 1, 2, 4
+APS_EV_DIFF_LEFT, APS_EV_DIFF_RIGHT, APS_EV_ACTIVE, APS_EV_FLIP = 0, 1, 2, 3
+
+
+class ApsParams(C.Structure):
+    _fields_ = [
+        ("L", C.c_int32),
+        ("K", C.c_int32),
+        ("radius", C.c_int32),
+        ("flags", C.c_uint32),
+        ("rate_diffusion", C.c_double),
+        ("rate_active", C.c_double),
+        ("T", C.c_double),
+    ]
+
+
+class ApsBatch(C.Structure):
+    _fields_ = [
+        ("n_replicas", C.c_int32),
+        ("n_max", C.c_int32),
+        ("M", C.c_int32),
+        ("record", C.c_uint32),
+        ("max_events", C.c_int64),
+        ("trace_cap", C.c_int64),
+        ("times_obs", C.c_void_p),
+        ("weights", C.c_void_p),
+        ("beta", C.c_void_p),
+        ("n", C.c_void_p),
+        ("pos0", C.c_void_p),
+        ("sigma0", C.c_void_p),
+        ("draws", C.c_void_p),
+        ("draw_off", C.c_void_p),
+        ("seeds", C.c_void_p),
+        ("t_start", C.c_void_p),
+        ("obs_start", C.c_void_p),
+        ("ev_start", C.c_void_p),
+        ("obs_cp", C.c_void_p),
+        ("obs_cm", C.c_void_p),
+        ("obs_pos", C.c_void_p),
+        ("obs_sigma_sum", C.c_void_p),
+        ("obs_m_local", C.c_void_p),
+        ("n_obs", C.c_void_p),
+        ("n_events", C.c_void_p),
+        ("t_end", C.c_void_p),
+        ("status", C.c_void_p),
+        ("n_guard", C.c_void_p),
+        ("draws_used", C.c_void_p),
+        ("pos_end", C.c_void_p),
+        ("sigma_end", C.c_void_p),
+        ("trace", C.c_void_p),
+    ]
+
+
+# every symbol include/aps.h declares: name -> (restype, argtypes)
+_P = C.POINTER
+SYMBOLS = {
+    "aps_abi_version": (C.c_int, []),
+    "aps_last_error": (C.c_char_p, []),
+    "aps_device_count": (C.c_int, []),
+    "aps_set_device": (C.c_int, [C.c_int]),
+    "aps_run_replay_device": (C.c_int, [_P(ApsParams), _P(ApsBatch), C.c_void_p]),
+    "aps_run_philox_device": (C.c_int, [_P(ApsParams), _P(ApsBatch), C.c_void_p]),
+    "aps_run_replay_host": (C.c_int, [_P(ApsParams), _P(ApsBatch)]),
+    "aps_run_philox_host": (C.c_int, [_P(ApsParams), _P(ApsBatch)]),
+    "aps_launch_count": (C.c_int64, []),
+    "aps_replica_smem_bytes": (C.c_int64, [_P(ApsParams), C.c_int32]),
+}
+
+_lib = None
+
+
+class ApsError(RuntimeError):
+    """Raised when a C-ABI call returns a non-zero aps_status."""
+
+
+def load(path: str | None = None):
+    """Load libaps_b200.so and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ApsError(
+            f"{p} is missing: build it with `python __graft_entry__.py build` "
+            "(this package has no CPU fallback)"
+        )
+    lib = C.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.aps_abi_version() != 1:
+        raise ApsError("libaps_b200.so ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "aps call"):
+    if rc != APS_OK:
+        msg = load().aps_last_error()
+        raise ApsError(f"{what} failed (status {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,149 @@
+/* aps.h — C ABI of the B200-native active-exclusion-process stepper.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference
+ * (StandeHaas/Hydrodynamic-Limits-of-Active-Particle-Systems-with-Mean-Field-Interactions):
+ * the Gillespie time-stepping loop of `ParticleSystem`
+ *     run()                     PARTICLE_solver_CLASS.py:450-558
+ *     step_gillespie()          PARTICLE_solver_CLASS.py:254-448
+ *     compute_local_m_field()   PARTICLE_solver_CLASS.py:216-246
+ *     init_particles()          PARTICLE_solver_CLASS.py:141-195
+ *     empirical_densities_from_particles()   PARTICLE_solver_CLASS.py:198-214
+ * and the ensemble loops / per-run reducers of the sweep drivers
+ *     sweep_beta_ensemble()     PARTICLE_solver_BIOLOGY_EXCLUSION_sweep_beta.py:56-117
+ *     compute_v_eff_and_window / compute_blocking_probability / compute_mean_magnetizatoin /
+ *     compute_rho_eff / compute_D_eff_active     ...sweep_beta.py:123-229,316-319,500-525
+ *
+ * The reference is pure Python, so there is no existing FFI to mirror; a maintainer binds this
+ * library with ctypes.  Conventions:
+ *   - plain C types, caller-allocated buffers, no exceptions; every entry point returns an
+ *     `aps_status` (0 = OK) and leaves a message retrievable with aps_last_error();
+ *   - `*_device` entry points take DEVICE pointers and a cudaStream_t (as void*), enqueue
+ *     kernels and return without synchronising;
+ *   - `*_host` entry points take HOST pointers, stage through device memory, synchronise and
+ *     copy results back (this is the path the end-to-end benchmark times);
+ *   - the library never falls back to the CPU: with no usable sm_100 device every compute call
+ *     fails with APS_ERR_NO_DEVICE.
+ */
+#ifndef APS_H
+#define APS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define APS_ABI_VERSION 1
+
+typedef enum aps_status {
+    APS_OK = 0,
+    APS_ERR_INVALID = 1,      /* bad argument / unsupported configuration            */
+    APS_ERR_NO_DEVICE = 2,    /* no CUDA device (the product has no CPU path)         */
+    APS_ERR_CUDA = 3,         /* CUDA runtime error, text in aps_last_error()         */
+    APS_ERR_CAPACITY = 4      /* replica does not fit the kernel's shared-memory plan */
+} aps_status;
+
+/* per-replica completion codes written to aps_batch.status[] */
+#define APS_RUN_DONE 0          /* loop ended as the reference's does (t>=T or all M rows filled) */
+#define APS_RUN_EMPTY 1         /* n == 0 or R <= 0: the reference raises here (CLASS.py:257,355) */
+#define APS_RUN_DRAWS_EXHAUSTED 2 /* replay log ran out before the loop ended                     */
+#define APS_RUN_MAX_EVENTS 3    /* stopped by aps_batch.max_events                                */
+
+/* aps_params.flags */
+#define APS_FLAG_CROWDING 1u    /* crowding_suppresses_rates=True (CLASS.py:322-336)              */
+
+/* aps_batch.record */
+#define APS_REC_COUNTS 1u       /* obs_cp / obs_cm                                                */
+#define APS_REC_POS 2u          /* obs_pos                                                        */
+#define APS_REC_MLOCAL 4u       /* obs_m_local (pre-event field, CLASS.py:512,525)                */
+
+/* event kinds in the optional trace */
+#define APS_EV_DIFF_LEFT 0
+#define APS_EV_DIFF_RIGHT 1
+#define APS_EV_ACTIVE 2
+#define APS_EV_FLIP 3
+
+/* Model parameters shared by every replica of one launch (constructor arguments of
+ * ParticleSystem after the optional dx-rescaling, CLASS.py:41-50,84). */
+typedef struct aps_params {
+    int32_t L;              /* lattice sites                                                      */
+    int32_t K;              /* site_capacity                                                      */
+    int32_t radius;         /* Gaussian filter radius lw = int(4*sigma/dx + 0.5); -1 selects the  */
+                            /* global mean field (local_kernel_sigma <= 0, CLASS.py:219-221)      */
+    uint32_t flags;
+    double rate_diffusion;  /* D                                                                  */
+    double rate_active;     /* lambda (sigma=+1 particles hop right only, CLASS.py:276,317-319)   */
+    double T;               /* run(T=...)                                                         */
+} aps_params;
+
+/* One launch = n_replicas independent ParticleSystem.run() calls.  Optional pointers may be NULL. */
+typedef struct aps_batch {
+    int32_t n_replicas;
+    int32_t n_max;              /* row stride of the per-particle arrays                          */
+    int32_t M;                  /* len(np.arange(0, T, obs_dt))                                   */
+    uint32_t record;            /* APS_REC_* mask                                                 */
+    int64_t max_events;         /* 0 = unlimited; otherwise stop each replica after this many     */
+    int64_t trace_cap;          /* events per replica the trace can hold (0 = no trace)           */
+
+    const double* times_obs;    /* [M]  exactly np.arange(0, T, obs_dt)                           */
+    const double* weights;      /* [2*radius+1] normalised Gaussian taps (scipy _gaussian_kernel1d)*/
+    const double* beta;         /* [n_replicas]                                                   */
+    const int32_t* n;           /* [n_replicas] particle count of each replica (<= n_max)         */
+    const int32_t* pos0;        /* [n_replicas][n_max] initial sites, reference particle order    */
+    const int8_t* sigma0;       /* [n_replicas][n_max] +1 / -1                                    */
+
+    /* replay mode: the variates the reference's rng returned, in call order:
+     * per event  e (standard exponential), u_choice, u_event [, u_dir if the event is diffusive] */
+    const double* draws;        /* flat log                                                       */
+    const int64_t* draw_off;    /* [n_replicas+1] offsets into draws                              */
+    /* native mode */
+    const uint64_t* seeds;      /* [n_replicas] Philox keys                                       */
+    /* optional resume point (all NULL = fresh run: t=0, observation row 0 recorded at start)    */
+    const double* t_start;      /* [n_replicas] simulation clock to resume from                   */
+    const int32_t* obs_start;   /* [n_replicas] next observation row; 0 = record row 0 first      */
+    const int64_t* ev_start;    /* [n_replicas] events already executed (Philox counter base)     */
+
+    /* observation outputs (row m of replica r is written when observation m is reached) */
+    int8_t* obs_cp;             /* [n_replicas][M][L] + particles per site                        */
+    int8_t* obs_cm;             /* [n_replicas][M][L] - particles per site                        */
+    int32_t* obs_pos;           /* [n_replicas][M][n_max]                                         */
+    int32_t* obs_sigma_sum;     /* [n_replicas][M]  sum(sigma)  (m_global = sum/n, CLASS.py:526)   */
+    double* obs_m_local;        /* [n_replicas][M][L]                                             */
+
+    /* per-replica results */
+    int32_t* n_obs;             /* [n_replicas] rows written                                      */
+    int64_t* n_events;          /* [n_replicas] ev_start + events executed (incl. the one past T) */
+    double* t_end;              /* [n_replicas] simulation clock after the last event             */
+    int32_t* status;            /* [n_replicas] APS_RUN_*                                         */
+    int64_t* n_guard;           /* [n_replicas] selections resolved by the exact slow path        */
+    int64_t* draws_used;        /* [n_replicas] replay variates consumed by completed events      */
+    int32_t* pos_end;           /* [n_replicas][n_max] optional final state                       */
+    int8_t* sigma_end;          /* [n_replicas][n_max]                                            */
+    int32_t* trace;             /* [n_replicas][trace_cap][3] = (particle, kind, new_site)        */
+} aps_batch;
+
+int aps_abi_version(void);
+const char* aps_last_error(void);
+
+/* Number of visible CUDA devices with compute capability 10.x; 0 means every compute call fails. */
+int aps_device_count(void);
+/* Bind the calling thread to a device (one process per GPU: call once with LOCAL_RANK). */
+int aps_set_device(int device);
+
+/* ---- K1: replica-batched exact Gillespie kernel ------------------------------------------- */
+/* Replaces ParticleSystem.run (CLASS.py:450) for a batch of replicas, replaying injected draws. */
+int aps_run_replay_device(const aps_params* p, const aps_batch* b, void* stream);
+/* Same loop with the counter-based Philox stream of aps_philox.h. */
+int aps_run_philox_device(const aps_params* p, const aps_batch* b, void* stream);
+/* Host-buffer variants: allocate, copy in, run, copy out, free. */
+int aps_run_replay_host(const aps_params* p, const aps_batch* b);
+int aps_run_philox_host(const aps_params* p, const aps_batch* b);
+/* Number of kernels the library has launched since load (for gpu_launches accounting). */
+int64_t aps_launch_count(void);
+/* Shared-memory bytes and threads the K1 plan uses for (L, n_max, radius); <0 if it cannot fit. */
+int64_t aps_replica_smem_bytes(const aps_params* p, int32_t n_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APS_H */

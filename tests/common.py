@@ -1,0 +1,134 @@
+"""Shared helpers for the parity tests: fixture loading, oracle driver, comparison."""
+from __future__ import annotations
+
+import glob
+import json
+import os
+
+import numpy as np
+
+from aps_b200 import capi
+from aps_b200.batch import make_batch, make_params
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def case_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_case(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = {k: z[k] for k in z.files}
+    d["meta"] = json.loads(str(d["meta"]))
+    return d
+
+
+def params_from_case(c, T=None):
+    m = c["meta"]
+    flags = capi.APS_FLAG_CROWDING if m["ps"].get("crowding_suppresses_rates") else 0
+    return make_params(m["L"], m["K"], m["radius"], m["rate_diffusion"], m["rate_active"],
+                       m["run"]["T"] if T is None else T, flags)
+
+
+class HostRun:
+    """Host-side buffers for one batch; `.batch` is the aps_batch pointing at them."""
+
+    def __init__(self, L, n_max, M, n, pos0, sigma0, beta, times_obs, weights, draws=None, draw_off=None,
+                 seeds=None, record=7, trace_cap=0, max_events=0, t_start=None, obs_start=None, ev_start=None):
+        R = len(n)
+        self.R, self.L, self.n_max, self.M = R, L, n_max, M
+        self.n = np.ascontiguousarray(n, dtype=np.int32)
+        self.pos0 = np.ascontiguousarray(pos0, dtype=np.int32).reshape(R, n_max)
+        self.sigma0 = np.ascontiguousarray(sigma0, dtype=np.int8).reshape(R, n_max)
+        self.beta = np.ascontiguousarray(beta, dtype=np.float64)
+        self.times_obs = np.ascontiguousarray(times_obs, dtype=np.float64)
+        self.weights = np.ascontiguousarray(weights, dtype=np.float64) if weights is not None and len(weights) else None
+        self.draws = None if draws is None else np.ascontiguousarray(draws, dtype=np.float64)
+        self.draw_off = None if draw_off is None else np.ascontiguousarray(draw_off, dtype=np.int64)
+        self.seeds = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        self.t_start = None if t_start is None else np.ascontiguousarray(t_start, dtype=np.float64)
+        self.obs_start = None if obs_start is None else np.ascontiguousarray(obs_start, dtype=np.int32)
+        self.ev_start = None if ev_start is None else np.ascontiguousarray(ev_start, dtype=np.int64)
+        Mr = max(M, 1)
+        self.obs_cp = np.full((R, Mr, L), -7, np.int8)
+        self.obs_cm = np.full((R, Mr, L), -7, np.int8)
+        self.obs_pos = np.full((R, Mr, n_max), -1, np.int32)
+        self.obs_sigma_sum = np.full((R, Mr), -99999, np.int32)
+        self.obs_m_local = np.full((R, Mr, L), np.nan, np.float64)
+        self.n_obs = np.zeros(R, np.int32)
+        self.n_events = np.zeros(R, np.int64)
+        self.t_end = np.zeros(R, np.float64)
+        self.status = np.full(R, -1, np.int32)
+        self.n_guard = np.zeros(R, np.int64)
+        self.draws_used = np.zeros(R, np.int64)
+        self.pos_end = np.full((R, n_max), -1, np.int32)
+        self.sigma_end = np.zeros((R, n_max), np.int8)
+        self.trace = np.full((R, max(trace_cap, 1), 3), -5, np.int32) if trace_cap else None
+        self.batch, self._keep = make_batch(
+            R, n_max, M, record=record, max_events=max_events, trace_cap=trace_cap,
+            times_obs=self.times_obs, weights=self.weights, beta=self.beta, n=self.n, pos0=self.pos0,
+            sigma0=self.sigma0, draws=self.draws, draw_off=self.draw_off, seeds=self.seeds,
+            t_start=self.t_start, obs_start=self.obs_start, ev_start=self.ev_start,
+            obs_cp=self.obs_cp, obs_cm=self.obs_cm, obs_pos=self.obs_pos, obs_sigma_sum=self.obs_sigma_sum,
+            obs_m_local=self.obs_m_local, n_obs=self.n_obs, n_events=self.n_events, t_end=self.t_end,
+            status=self.status, n_guard=self.n_guard, draws_used=self.draws_used, pos_end=self.pos_end,
+            sigma_end=self.sigma_end, trace=self.trace)
+
+    OUT_FIELDS = ["obs_cp", "obs_cm", "obs_pos", "obs_sigma_sum", "obs_m_local", "n_obs", "n_events", "t_end",
+                  "status", "draws_used", "pos_end", "sigma_end", "trace"]
+
+
+def hostrun_from_case(c, trace=True, **kw):
+    m = c["meta"]
+    n = m["n"]
+    return HostRun(m["L"], max(n, 1), len(c["times_obs"]), [n], c["pos0"], c["sigma0"], [m["ps"]["beta"]],
+                   c["times_obs"], c["weights"], draws=c["draws"], draw_off=[0, len(c["draws"])],
+                   trace_cap=(len(c["trace"]) + 4) if trace else 0, **kw)
+
+
+def run_oracle(params, hr, mode=0, threads=1):
+    from oracle import oracle
+
+    rc = oracle.load().aps_oracle_run(params, hr.batch, mode, threads)
+    assert rc == 0
+    return hr
+
+
+def assert_same_outputs(a: HostRun, b: HostRun, bitwise_time=True):
+    """GPU vs oracle: every output field identical (m_local and t_end compared as bit patterns)."""
+    for f in HostRun.OUT_FIELDS:
+        x, y = getattr(a, f), getattr(b, f)
+        if x is None and y is None:
+            continue
+        if f == "t_end" and not bitwise_time:
+            np.testing.assert_allclose(x, y, rtol=1e-12)
+            continue
+        if x.dtype == np.float64:
+            assert np.array_equal(x.view(np.uint64), y.view(np.uint64)), f"field {f} differs"
+        else:
+            assert np.array_equal(x, y), f"field {f} differs"
+
+
+def assert_matches_reference(c, hr: HostRun, rep=0):
+    """Outputs of a run (oracle or GPU) against what the unmodified reference returned."""
+    m = c["meta"]
+    n, L, n_obs, n_ev = m["n"], m["L"], m["n_obs"], m["n_events"]
+    assert hr.status[rep] == capi.APS_RUN_DONE
+    assert hr.n_obs[rep] == n_obs
+    assert hr.n_events[rep] == n_ev
+    assert hr.draws_used[rep] == len(c["draws"])
+    if hr.trace is not None:
+        assert np.array_equal(hr.trace[rep, :n_ev], c["trace"]), "event trace differs from the reference"
+    denom = float(max(1, n)) * m["dx"]
+    rho_p = hr.obs_cp[rep, :n_obs].astype(np.int64) / denom      # CLASS.py:205-213
+    rho_m = hr.obs_cm[rep, :n_obs].astype(np.int64) / denom
+    assert np.array_equal(rho_p, c["rho_p_list"][:n_obs])
+    assert np.array_equal(rho_m, c["rho_m_list"][:n_obs])
+    assert np.array_equal(rho_p + rho_m, c["total_list"][:n_obs])
+    assert np.array_equal(hr.obs_pos[rep, :n_obs, :n], c["pos_obs"][:n_obs])
+    assert np.array_equal(hr.obs_sigma_sum[rep, :n_obs] / float(n), c["m_global"][:n_obs])
+    got, want = hr.obs_m_local[rep, :n_obs], c["m_local_list"][:n_obs]
+    assert np.array_equal(got, want), f"m_local differs: max abs {np.abs(got - want).max()}"
+    # rows never reached stay zero in the reference (CLASS.py:466-472)
+    assert not c["rho_p_list"][n_obs:].any()

@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ by executing the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference).  The reference has no tests or
+golden vectors of its own, so parity is pinned on what its code does here:
+`ParticleSystem` is imported from /root/reference with matplotlib/vispy stubbed (they are
+plot-only imports, PARTICLE_solver_CLASS.py:4-7) and driven through its public API with a
+recording wrapper around a seeded numpy Generator passed via the constructor's `rng=` seam
+(PARTICLE_solver_CLASS.py:26,75-78).
+
+For each case we store: constructor/run parameters, Gaussian taps (scipy's), initial state,
+the variate log (standard exponential + uniforms in call order), the per-event trace
+(particle, kind, new site) and the returned `out` arrays.  Every case is also run a second
+time with a plain, unwrapped `np.random.default_rng(seed)` to prove that the wrapper does not
+change the reference's behaviour.
+
+Also stores outputs of the sweep drivers' per-run reducers (extracted by AST from the driver
+file, because the drivers execute their sweep at import time).
+
+Usage: python tools/gen_golden.py [case ...]
+"""
+from __future__ import annotations
+
+import ast
+import json
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+
+REF = "/root/reference"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def import_reference():
+    for m in ["matplotlib", "matplotlib.pyplot", "matplotlib.cm", "vispy", "vispy.app", "vispy.scene", "vispy.io"]:
+        sys.modules.setdefault(m, MagicMock())
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from PARTICLE_solver_CLASS import ParticleSystem  # type: ignore
+
+    return ParticleSystem
+
+
+def extract_functions(path, names):
+    """exec selected top-level function definitions of a driver script (no sweep is run)."""
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"np": np}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+            exec(code, ns)
+    return ns
+
+
+class RecordingRNG:
+    """Duck-typed rng for ParticleSystem: forwards to a numpy Generator and logs the variates of
+    the three per-event calls (exponential, choice(n, p=...), random)."""
+
+    def __init__(self, gen):
+        self.gen = gen
+        self.log = []
+
+    def exponential(self, scale=1.0):
+        e = self.gen.standard_exponential()
+        self.log.append(e)
+        return scale * e
+
+    def choice(self, a, size=None, replace=True, p=None):
+        if p is not None and size is None:
+            u = self.gen.random()
+            self.log.append(u)
+            cdf = np.asarray(p).cumsum()
+            cdf /= cdf[-1]
+            return int(cdf.searchsorted(u, side="right"))
+        return self.gen.choice(a, size=size, replace=replace, p=p)
+
+    def random(self):
+        u = self.gen.random()
+        self.log.append(u)
+        return u
+
+    def poisson(self, lam):
+        return self.gen.poisson(lam)
+
+
+def exp_gradient(L, N, frac_plus, decay_length):
+    xs = np.arange(L) / float(L)
+    plus = np.exp(-xs / decay_length)
+    minus = 0.05 * np.ones_like(xs)
+    rho_plus = N * frac_plus * (plus / plus.sum())
+    rho_minus = N * (1 - frac_plus) * (minus / minus.sum())
+    return rho_plus, rho_minus
+
+
+def profile_callables(rho_plus, rho_minus):
+    L = len(rho_plus)
+
+    def fp(x):
+        return float(rho_plus[int(np.clip(np.round(x * L), 0, L - 1))])
+
+    def fm(x):
+        return float(rho_minus[int(np.clip(np.round(x * L), 0, L - 1))])
+
+    return fp, fm
+
+
+BASE = dict(flip_rate_fn=None, minus_anchor=True, periodic=False, immobilize_when_anchored=True,
+            anchor_radius=0.003, anchor_positions=None, crowding_suppresses_rates=False, k_on=0, k_off=0, k_exit=0)
+
+
+def cases():
+    c = {}
+    c["c1_exclusion"] = dict(ps=dict(L=1000, xlim=1, rate_diffusion=0, rate_active=5, beta=0.7, init="fixed", N=750,
+                                     scale_rates=False, local_kernel_sigma=0.002, site_capacity=3),
+                             run=dict(T=1.0, obs_dt=0.25, record_fft=True, record_var=True), seed=101)
+    sw = dict(L=1000, xlim=1, rate_diffusion=0.02, rate_active=5, init="poisson", N=500, scale_rates=False,
+              local_kernel_sigma=0.005, site_capacity=1)
+    for b, name in [(0.0, "c2_sweep_b0"), (3.0, "c2_sweep_b3")]:
+        c[name] = dict(ps=dict(sw, beta=b), profile=dict(L=1000, N=500, frac_plus=0.75, decay_plus=0.35),
+                       run=dict(T=1.5, obs_dt=0.1, record_fft=True, record_var=True), seed=202 + int(b))
+    c["c3_local"] = dict(ps=dict(L=1000, xlim=1, rate_diffusion=0.05, rate_active=5, beta=1.5, init="fixed", N=900,
+                                 scale_rates=False, local_kernel_sigma=0.005, site_capacity=1),
+                         run=dict(T=2.0, obs_dt=0.5, record_fft=True, record_var=True), seed=303)
+    c["c4_double"] = dict(ps=dict(L=1000, xlim=1, rate_diffusion=0.005, rate_active=10, beta=1.5, init="poisson", N=500,
+                                  scale_rates=False, local_kernel_sigma=0.02, site_capacity=1),
+                          profile=dict(L=1000, N=500, frac_plus=0.75, decay_plus=0.2),
+                          run=dict(T=1.0, obs_dt=0.1, record_fft=False, record_var=False), seed=404)
+    c["global_sigma0"] = dict(ps=dict(L=1000, xlim=1, rate_diffusion=0.002, rate_active=5, beta=2.0, init="poisson", N=500,
+                                      scale_rates=False, local_kernel_sigma=0.0, site_capacity=1),
+                              profile=dict(L=1000, N=500, frac_plus=0.75, decay_plus=0.35),
+                              run=dict(T=1.5, obs_dt=0.1, record_fft=False, record_var=True), seed=505)
+    c["huge_sigma"] = dict(ps=dict(L=100, xlim=1, rate_diffusion=0.5, rate_active=2, beta=1.0, init="fixed", N=40,
+                                   scale_rates=False, local_kernel_sigma=0.3, site_capacity=1),
+                           run=dict(T=2.0, obs_dt=0.25, record_fft=False, record_var=False), seed=606)
+    c["tiny_diffusive"] = dict(ps=dict(L=16, xlim=1, rate_diffusion=3.0, rate_active=1, beta=0.5, init="fixed", N=8,
+                                       scale_rates=False, local_kernel_sigma=0.1, site_capacity=2),
+                               run=dict(T=3.0, obs_dt=0.2, record_fft=True, record_var=True), seed=707)
+    c["k1_dense"] = dict(ps=dict(L=64, xlim=1, rate_diffusion=1.0, rate_active=3, beta=2.5, init="fixed", N=60,
+                                 scale_rates=False, local_kernel_sigma=0.03, site_capacity=1),
+                         run=dict(T=3.0, obs_dt=0.25, record_fft=False, record_var=False), seed=808)
+    c["r0_local"] = dict(ps=dict(L=50, xlim=1, rate_diffusion=0.7, rate_active=2, beta=1.2, init="fixed", N=30,
+                                 scale_rates=False, local_kernel_sigma=0.001, site_capacity=2),
+                         run=dict(T=3.0, obs_dt=0.5, record_fft=False, record_var=False), seed=909)
+    c["crowding"] = dict(ps=dict(L=64, xlim=1, rate_diffusion=0.8, rate_active=3, beta=1.0, init="fixed", N=100,
+                                 scale_rates=False, local_kernel_sigma=0.04, site_capacity=3,
+                                 crowding_suppresses_rates=True),
+                         run=dict(T=2.0, obs_dt=0.25, record_fft=False, record_var=False), seed=1010)
+    c["scale_rates"] = dict(ps=dict(L=32, xlim=1, rate_diffusion=0.0005, rate_active=0.05, beta=0.8, init="fixed", N=20,
+                                    scale_rates=True, local_kernel_sigma=0.05, site_capacity=1),
+                            run=dict(T=4.0, obs_dt=0.5, record_fft=False, record_var=False), seed=1111)
+    c["multi_obs_per_event"] = dict(ps=dict(L=16, xlim=1, rate_diffusion=0.05, rate_active=0.1, beta=0.3, init="fixed", N=3,
+                                            scale_rates=False, local_kernel_sigma=0.1, site_capacity=1),
+                                    run=dict(T=5.0, obs_dt=0.01, record_fft=False, record_var=False), seed=1212)
+    for k, seed in enumerate([1313, 1314, 1315, 1316]):
+        c[f"sparse_events_{k}"] = dict(ps=dict(L=8, xlim=1, rate_diffusion=0.1, rate_active=0.1, beta=0.0, init="fixed", N=2,
+                                               scale_rates=False, local_kernel_sigma=0.2, site_capacity=1),
+                                       run=dict(T=1.0, obs_dt=0.9, record_fft=False, record_var=False), seed=seed)
+    c["poisson_k2"] = dict(ps=dict(L=200, xlim=1, rate_diffusion=0.3, rate_active=4, beta=1.8, init="poisson", N=260,
+                                   scale_rates=False, local_kernel_sigma=0.01, site_capacity=2),
+                           profile=dict(L=200, N=260, frac_plus=0.6, decay_plus=0.5),
+                           run=dict(T=1.0, obs_dt=0.125, record_fft=True, record_var=True), seed=1414)
+    return c
+
+
+def build_ps(PS, spec, rng):
+    kw = dict(BASE)
+    kw.update(spec["ps"])
+    if "profile" in spec:
+        p = spec["profile"]
+        rp, rm = exp_gradient(p["L"], p["N"], p["frac_plus"], p["decay_plus"])
+        fp, fm = profile_callables(rp, rm)
+        kw.update(rho0_plus=fp, rho0_minus=fm)
+    return PS(rng=rng, **kw)
+
+
+def run_case(PS, name, spec):
+    from scipy.ndimage import _filters  # scipy's own tap generator
+
+    seed = spec["seed"]
+    # (1) plain reference run, unwrapped numpy Generator
+    ps_plain = build_ps(PS, spec, np.random.default_rng(seed))
+    out_plain = ps_plain.run(**spec["run"])
+
+    # (2) recorded run: capture initial state, draws and per-event trace
+    rec = RecordingRNG(np.random.default_rng(seed))
+    ps = build_ps(PS, spec, rec)
+    captured = {}
+    orig_init = ps.init_particles
+
+    def init_hook():
+        pos, sigma = orig_init()
+        captured["pos0"] = pos.copy()
+        captured["sigma0"] = sigma.copy()
+        return pos, sigma
+
+    ps.init_particles = init_hook
+    trace = []
+    orig_step = ps.step_gillespie
+
+    def step_hook(pos, sigma, bound, *a):
+        p0, s0, nlog = pos.copy(), sigma.copy(), len(rec.log)
+        res = orig_step(pos, sigma, bound, *a)
+        used = len(rec.log) - nlog
+        dp = np.nonzero(res[0] != p0)[0]
+        dsg = np.nonzero(res[1] != s0)[0]
+        if dsg.size == 1 and dp.size == 0:
+            trace.append((int(dsg[0]), 3, -1))
+        elif dp.size == 1 and dsg.size == 0:
+            i = int(dp[0])
+            step = int(res[0][i] - p0[i])
+            kind = (0 if step < 0 else 1) if used == 4 else 2
+            trace.append((i, kind, int(res[0][i])))
+        else:
+            raise RuntimeError("event did not change exactly one particle")
+        return res
+
+    ps.step_gillespie = step_hook
+    out = ps.run(**spec["run"])
+
+    # the wrapper must be behaviour-neutral
+    for k in ["rho_p_list", "rho_m_list", "total_list", "m_local_list", "m_global"]:
+        assert np.array_equal(out[k], out_plain[k]), (name, k)
+    n_obs = sum(p is not None for p in out["pos_list"])
+    for a, b in zip(out["pos_list"][:n_obs], out_plain["pos_list"][:n_obs]):
+        assert np.array_equal(a, b)
+
+    n = captured["pos0"].size
+    pos_obs = np.full((len(out["pos_list"]), n), -1, dtype=np.int32)
+    for m in range(n_obs):
+        pos_obs[m] = out["pos_list"][m]
+    radius = -1
+    weights = np.zeros(0)
+    if ps.local_kernel_sigma > 0:
+        sd = float(ps._sigma_grid)
+        radius = int(4.0 * sd + 0.5)
+        weights = _filters._gaussian_kernel1d(sd, 0, radius)[::-1].copy()
+    meta = dict(name=name, ps=spec["ps"], run=spec["run"], seed=seed, profile=spec.get("profile"),
+                dx=ps.dx, rate_diffusion=ps.rate_diffusion, rate_active=ps.rate_active, K=ps.K, L=ps.L,
+                radius=radius, n=int(n), n_obs=int(n_obs), n_events=len(trace),
+                numpy=np.__version__, scipy=__import__("scipy").__version__)
+    save = dict(
+        meta=np.array(json.dumps(meta)),
+        weights=weights,
+        times_obs=out["times_obs"],
+        pos0=captured["pos0"].astype(np.int32),
+        sigma0=captured["sigma0"].astype(np.int8),
+        draws=np.asarray(rec.log, dtype=np.float64),
+        trace=np.asarray(trace, dtype=np.int32).reshape(-1, 3),
+        rho_p_list=out["rho_p_list"], rho_m_list=out["rho_m_list"], total_list=out["total_list"],
+        m_local_list=out["m_local_list"], m_global=out["m_global"], pos_obs=pos_obs,
+    )
+    if out["var_list"] is not None:
+        save["var_list"] = out["var_list"]
+    if out["fft_amp_list"] is not None:
+        save["fft_amp_head"] = out["fft_amp_list"][:, :32].copy()
+        save["rho_hat_head"] = out["rho_hat_complex"][:, :32].copy()
+    if "profile" in spec:
+        p = spec["profile"]
+        rp, rm = exp_gradient(p["L"], p["N"], p["frac_plus"], p["decay_plus"])
+        save["rho0_plus"], save["rho0_minus"] = rp, rm
+        assert np.array_equal(ps.rho0_plus, rp) and np.array_equal(ps.rho0_minus, rm)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **save)
+    print(f"{name}: n={n} events={len(trace)} draws={len(rec.log)} n_obs={n_obs}/{len(out['pos_list'])}")
+    return ps, out
+
+
+def reducer_golden(PS):
+    """Golden outputs of the sweep driver's per-run reducers on a short sweep_beta-like run."""
+    names = ["compute_v_eff_and_window", "compute_rho_eff", "compute_blocking_probability",
+             "compute_mean_magnetizatoin", "compute_D_eff_active", "make_exp_gradient"]
+    ns = extract_functions(os.path.join(REF, "PARTICLE_solver_BIOLOGY_EXCLUSION_sweep_beta.py"), names)
+    # our exp_gradient must match the driver's make_exp_gradient
+    r = ns["make_exp_gradient"](L=1000, N=500, frac_plus=0.75, decay_length=0.35, anchor_positions=None)
+    rp, rm = exp_gradient(1000, 500, 0.75, 0.35)
+    assert np.array_equal(r[2], rp) and np.array_equal(r[3], rm)
+    assert all(r[0](i / 1000) == rp[i] and r[1](i / 1000) == rm[i] for i in range(1000))
+    res = {}
+    for tag, beta, seed in [("b0", 0.5, 77), ("b2", 2.0, 78)]:
+        spec = dict(ps=dict(L=1000, xlim=1, rate_diffusion=0.02, rate_active=5, beta=beta, init="poisson", N=500,
+                            scale_rates=False, local_kernel_sigma=0.005, site_capacity=1),
+                    profile=dict(L=1000, N=500, frac_plus=0.75, decay_plus=0.35),
+                    run=dict(T=3.0, obs_dt=0.1, record_fft=True, record_var=True), seed=seed)
+        ps, out = run_case(PS, f"reducers_{tag}", spec)
+        mean_v, v_eff, times, si, ei, frac_b = ns["compute_v_eff_and_window"](
+            out, ps, boundary_xmin=0.99, max_buondary_fraction=0.06, min_window_fraction=0.10)
+        res[tag] = dict(mean_v=mean_v, si=int(si), ei=int(ei),
+                        D_eff=float(ns["compute_D_eff_active"](out, ps, start_idx=si, end_idx=ei)),
+                        m_mean=ns["compute_mean_magnetizatoin"](out, si, ei),
+                        rho_eff=ns["compute_rho_eff"](out, si, ei),
+                        block=float(ns["compute_blocking_probability"](out, si, ei)),
+                        v_eff=v_eff.tolist(), frac_boundary=frac_b.tolist())
+    json.dump(res, open(os.path.join(OUT, "reducers.json"), "w"), indent=1)
+    print("reducers:", {k: {kk: vv for kk, vv in v.items() if not isinstance(vv, list)} for k, v in res.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    PS = import_reference()
+    want = sys.argv[1:]
+    for name, spec in cases().items():
+        if want and name not in want:
+            continue
+        run_case(PS, name, spec)
+    if not want or "reducers" in want:
+        reducer_golden(PS)
+
+
+if __name__ == "__main__":
+    main()
