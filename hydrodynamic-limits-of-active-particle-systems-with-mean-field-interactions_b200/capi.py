@@ -84,6 +84,8 @@ SYMBOLS = {
     "aps_run_philox_host": (C.c_int, [_P(ApsParams), _P(ApsBatch)]),
     "aps_launch_count": (C.c_int64, []),
     "aps_replica_smem_bytes": (C.c_int64, [_P(ApsParams), C.c_int32]),
+    "aps_debug_set_guard_scale": (None, [C.c_double]),
+    "aps_debug_set_k1_threads": (None, [C.c_int]),
 }
 
 _lib = None

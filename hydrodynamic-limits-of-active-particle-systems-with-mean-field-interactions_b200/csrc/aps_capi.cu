@@ -1,0 +1,228 @@
+// aps_capi.cu — implementation of the C ABI in include/aps.h (host side of the kernels).
+// No torch types, no CPU compute path: without an sm_100 device every compute entry fails.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "aps_k1.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+double g_guard_scale = 1.0;
+int g_k1_threads = 0;  // 0 = heuristic
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return APS_ERR_CUDA;
+}
+#define CU(call)                                         \
+    do {                                                 \
+        cudaError_t e__ = (call);                        \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+int count_sm100() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int tree_nodes(int n) {  // nodes of numpy's pairwise-sum recursion for n elements
+    if (n <= 128) return 1;
+    int n2 = n / 2; n2 -= n2 % 8;
+    return tree_nodes(n2) + tree_nodes(n - n2) + 1;
+}
+int max_tree_nodes(int n_max) {
+    int best = 1;
+    for (int n = 1; n <= n_max; ++n) { int t = tree_nodes(n); if (t > best) best = t; }
+    return best;
+}
+
+int validate(const aps_params* p, const aps_batch* b, bool philox) {
+    if (!p || !b) return fail(APS_ERR_INVALID, "null params/batch");
+    if (p->L < 1 || p->L > 65535) return fail(APS_ERR_INVALID, "K1 needs 1 <= L <= 65535 (shared-memory resident lattice)");
+    if (p->K < 1 || p->K > 63) return fail(APS_ERR_INVALID, "site capacity K must be in [1, 63]");
+    if (b->n_replicas < 0 || b->n_max < 1 || b->n_max > 8192) return fail(APS_ERR_INVALID, "need 1 <= n_max <= 8192");
+    if (b->M < 1) return fail(APS_ERR_INVALID, "need at least one observation time (M >= 1)");
+    if (!b->times_obs || !b->beta || !b->n || !b->pos0 || !b->sigma0) return fail(APS_ERR_INVALID, "missing required input pointer");
+    if (p->radius >= 0 && !b->weights) return fail(APS_ERR_INVALID, "weights required when radius >= 0");
+    if (philox && !b->seeds) return fail(APS_ERR_INVALID, "seeds required in native (Philox) mode");
+    if (!philox && (!b->draws || !b->draw_off)) return fail(APS_ERR_INVALID, "draws/draw_off required in replay mode");
+    return APS_OK;
+}
+
+template <int NT>
+int launch_nt(const aps::K1Args& a, bool philox, size_t smem, cudaStream_t st) {
+    auto kr = aps::k1_kernel<NT, false>;
+    auto kp = aps::k1_kernel<NT, true>;
+    if (philox) {
+        CU(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kp<<<a.b.n_replicas, NT, smem, st>>>(a);
+    } else {
+        CU(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kr<<<a.b.n_replicas, NT, smem, st>>>(a);
+    }
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+int pick_threads(int n_max) {
+    if (g_k1_threads) return g_k1_threads;
+    const char* e = getenv("APS_K1_THREADS");
+    if (e) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) return v; }
+    return n_max > 1536 ? 256 : 128;
+}
+
+int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philox) {
+    int rc = validate(p, b, philox);
+    if (rc) return rc;
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (b->n_replicas == 0) return APS_OK;
+    aps::K1Args a;
+    a.p = *p; a.b = *b;
+    a.guard_scale = g_guard_scale;
+    a.max_nodes = max_tree_nodes(b->n_max);
+    a.pad = p->radius > 0 ? p->radius : 0;
+    const int nt = pick_threads(b->n_max);
+    const size_t smem = aps::k1_smem_bytes(p->L, b->n_max, p->radius, a.max_nodes, nt / 32);
+    if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "replica does not fit in 227 KB of shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nt) {
+        case 64: return launch_nt<64>(a, philox, smem, st);
+        case 256: return launch_nt<256>(a, philox, smem, st);
+        default: return launch_nt<128>(a, philox, smem, st);
+    }
+}
+
+// ---- host-buffer staging -------------------------------------------------------------------
+struct DevBuf {
+    void* d = nullptr;
+    ~DevBuf() { if (d) cudaFree(d); }
+};
+
+struct Stager {
+    std::vector<DevBuf*> bufs;
+    struct Out { void* host; void* dev; size_t bytes; };
+    std::vector<Out> outs;
+    cudaStream_t st = nullptr;
+    ~Stager() { for (auto* b : bufs) delete b; }
+    // copy a host input to the device (returns nullptr for nullptr)
+    int in(const void* h, size_t bytes, const void** dptr) {
+        *dptr = nullptr;
+        if (!h || bytes == 0) return APS_OK;
+        auto* b = new DevBuf(); bufs.push_back(b);
+        CU(cudaMalloc(&b->d, bytes));
+        CU(cudaMemcpyAsync(b->d, h, bytes, cudaMemcpyHostToDevice, st));
+        *dptr = b->d;
+        return APS_OK;
+    }
+    // allocate a device output mirrored back to `h` at the end
+    int out(void* h, size_t bytes, void** dptr, bool copy_in_first = true) {
+        *dptr = nullptr;
+        if (!h || bytes == 0) return APS_OK;
+        auto* b = new DevBuf(); bufs.push_back(b);
+        CU(cudaMalloc(&b->d, bytes));
+        if (copy_in_first) CU(cudaMemcpyAsync(b->d, h, bytes, cudaMemcpyHostToDevice, st));
+        outs.push_back({h, b->d, bytes});
+        *dptr = b->d;
+        return APS_OK;
+    }
+    int finish() {
+        for (auto& o : outs) CU(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return APS_OK;
+    }
+};
+
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+int run_host(const aps_params* p, const aps_batch* hb, bool philox) {
+    int rc = validate(p, hb, philox);
+    if (rc) return rc;
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    const size_t R = (size_t)hb->n_replicas, NM = (size_t)hb->n_max, M = (size_t)hb->M, L = (size_t)p->L;
+    if (R == 0) return APS_OK;
+    Stager s;
+    aps_batch d = *hb;
+    TRY(s.in(hb->times_obs, M * 8, (const void**)&d.times_obs));
+    TRY(s.in(hb->weights, p->radius >= 0 ? (size_t)(2 * p->radius + 1) * 8 : 0, (const void**)&d.weights));
+    TRY(s.in(hb->beta, R * 8, (const void**)&d.beta));
+    TRY(s.in(hb->n, R * 4, (const void**)&d.n));
+    TRY(s.in(hb->pos0, R * NM * 4, (const void**)&d.pos0));
+    TRY(s.in(hb->sigma0, R * NM, (const void**)&d.sigma0));
+    if (!philox) {
+        TRY(s.in(hb->draw_off, (R + 1) * 8, (const void**)&d.draw_off));
+        TRY(s.in(hb->draws, (size_t)hb->draw_off[R] * 8, (const void**)&d.draws));
+    } else {
+        TRY(s.in(hb->seeds, R * 8, (const void**)&d.seeds));
+    }
+    TRY(s.in(hb->t_start, R * 8, (const void**)&d.t_start));
+    TRY(s.in(hb->obs_start, R * 4, (const void**)&d.obs_start));
+    TRY(s.in(hb->ev_start, R * 8, (const void**)&d.ev_start));
+    // observation rows not reached keep whatever the caller put there (the reference leaves zeros)
+    TRY(s.out((hb->record & APS_REC_COUNTS) ? hb->obs_cp : nullptr, R * M * L, (void**)&d.obs_cp));
+    TRY(s.out((hb->record & APS_REC_COUNTS) ? hb->obs_cm : nullptr, R * M * L, (void**)&d.obs_cm));
+    TRY(s.out((hb->record & APS_REC_POS) ? hb->obs_pos : nullptr, R * M * NM * 4, (void**)&d.obs_pos));
+    TRY(s.out(hb->obs_sigma_sum, R * M * 4, (void**)&d.obs_sigma_sum));
+    TRY(s.out((hb->record & APS_REC_MLOCAL) ? hb->obs_m_local : nullptr, R * M * L * 8, (void**)&d.obs_m_local));
+    TRY(s.out(hb->n_obs, R * 4, (void**)&d.n_obs, false));
+    TRY(s.out(hb->n_events, R * 8, (void**)&d.n_events, false));
+    TRY(s.out(hb->t_end, R * 8, (void**)&d.t_end, false));
+    TRY(s.out(hb->status, R * 4, (void**)&d.status, false));
+    TRY(s.out(hb->n_guard, R * 8, (void**)&d.n_guard, false));
+    TRY(s.out(hb->draws_used, R * 8, (void**)&d.draws_used, false));
+    TRY(s.out(hb->pos_end, R * NM * 4, (void**)&d.pos_end));
+    TRY(s.out(hb->sigma_end, R * NM, (void**)&d.sigma_end));
+    TRY(s.out(hb->trace_cap > 0 ? hb->trace : nullptr, R * (size_t)hb->trace_cap * 12, (void**)&d.trace));
+    if (hb->trace_cap <= 0) d.trace = nullptr;
+    TRY(run_device(p, &d, nullptr, philox));
+    return s.finish();
+}
+
+}  // namespace
+
+extern "C" {
+
+int aps_abi_version(void) { return APS_ABI_VERSION; }
+const char* aps_last_error(void) { return g_err.c_str(); }
+int aps_device_count(void) { return count_sm100(); }
+int aps_set_device(int device) {
+    CU(cudaSetDevice(device));
+    return APS_OK;
+}
+int64_t aps_launch_count(void) { return g_launches.load(); }
+
+int64_t aps_replica_smem_bytes(const aps_params* p, int32_t n_max) {
+    if (!p || n_max < 1 || n_max > 8192) return -1;
+    int nt = pick_threads(n_max);
+    size_t b = aps::k1_smem_bytes(p->L, n_max, p->radius, max_tree_nodes(n_max), nt / 32);
+    return b > 227 * 1024 ? -1 : (int64_t)b;
+}
+
+int aps_run_replay_device(const aps_params* p, const aps_batch* b, void* stream) { return run_device(p, b, stream, false); }
+int aps_run_philox_device(const aps_params* p, const aps_batch* b, void* stream) { return run_device(p, b, stream, true); }
+int aps_run_replay_host(const aps_params* p, const aps_batch* b) { return run_host(p, b, false); }
+int aps_run_philox_host(const aps_params* p, const aps_batch* b) { return run_host(p, b, true); }
+
+// Test / tuning hooks (declared in include/aps.h).
+void aps_debug_set_guard_scale(double s) { g_guard_scale = s; }
+void aps_debug_set_k1_threads(int nt) { g_k1_threads = (nt == 64 || nt == 128 || nt == 256) ? nt : 0; }
+
+}  // extern "C"

@@ -1,0 +1,530 @@
+// aps_k1.cuh — K1: replica-batched exact Gillespie kernel (one CTA per replica).
+//
+// What it replaces: one launch == n_replicas calls of ParticleSystem.run()
+// (PARTICLE_solver_CLASS.py:450-558), each event being one step_gillespie()
+// (:254-448) preceded by compute_local_m_field() (:216-246).
+//
+// B200-first design (not a translation of the numpy code):
+//   * the reference recomputes the whole field (2 Gaussian filters over L sites) and all n
+//     rates for every single-particle event: O(L*taps + n).  Here the lattice lives in shared
+//     memory as one packed uint16 per site (c_plus | c_minus<<8) with the reflect halo
+//     materialised, the per-particle total rates live in shared memory, and an event only
+//     re-evaluates the rates of the particles inside the window its <=2 changed sites can
+//     influence (filter radius r): O(rho*r*r) work, all of it on-chip.
+//   * the filter value at a particle's site is re-evaluated from scratch in the reference's
+//     exact tap order (outermost pair first, separate mul and add, no FMA), so every rate is
+//     bit-identical to the oracle's full recomputation.
+//   * particle selection: the reference does searchsorted(cumsum(rates/R)/last, u).  A serial
+//     cumsum is a 100s-of-adds dependent chain, so the kernel selects with a two-level parallel
+//     prefix sum (per-thread chunk + warp shuffle scan) and proves the decision equal to the
+//     serial one with a rounding-error guard band; if u lies within the band of a bin edge
+//     (probability ~1e-10 per event) one thread redoes that selection in the exact serial order.
+//   * R = rates.sum() is numpy's pairwise summation; it is reproduced exactly and in parallel
+//     (8 strided accumulators per <=128-element leaf == 8 lanes, butterfly combine, then the
+//     recursion tree), so the event clock t is bit-identical as well.
+//   * HBM is touched only for the observation rows (M per run) and, in replay mode, for the
+//     variate log.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aps.h"
+#include "../../include/aps_math.h"
+#include "../../include/aps_philox.h"
+
+namespace aps {
+
+constexpr int kMaxNodes = 512;  // nodes of the pairwise-sum tree (n_max <= 8192)
+
+struct K1Args {
+    aps_params p;
+    aps_batch b;
+    double guard_scale;   // multiplies the selection guard band (test hook; 1.0 in production)
+    int32_t max_nodes;    // tree nodes the shared-memory plan reserves
+    int32_t pad;          // halo width = max(radius, 0)
+};
+
+// Shared-memory plan (bytes) — keep in sync with carve() below.
+__host__ __device__ inline size_t k1_smem_bytes(int L, int n_max, int radius, int max_nodes, int nwarps) {
+    int pad = radius > 0 ? radius : 0;
+    size_t d = 0;
+    d += (size_t)n_max;                  // rates
+    d += (size_t)(pad + 1);              // taps w[0..r]
+    d += (size_t)max_nodes;              // tree node values
+    d += (size_t)nwarps;                 // warp totals
+    d += 8;                              // draws[4], t_new, R, spare
+    size_t bytes = d * 8;
+    bytes += (size_t)max_nodes * 3 * 4;  // node_a, node_b (children or leaf start/len), kind
+    bytes += 16 * 4;                     // desc + flags
+    bytes += (((size_t)(L + 2 * pad) + 1) / 2) * 4;  // packed lattice (uint16, 4-byte granules)
+    bytes += (((size_t)n_max + 1) / 2) * 4;          // pos (uint16)
+    bytes += (((size_t)n_max + 3) / 4) * 4;          // sigma (int8)
+    return bytes;
+}
+
+struct Smem {
+    double* rates; double* w; double* node_val; double* wtot; double* misc;
+    int32_t* node_a; int32_t* node_b; int32_t* node_kind; int32_t* desc;
+    uint16_t* pk; uint16_t* pos; int8_t* sigma;
+};
+
+__device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int pad, int max_nodes, int nwarps) {
+    Smem s;
+    double* d = reinterpret_cast<double*>(base);
+    s.rates = d; d += n_max;
+    s.w = d; d += pad + 1;
+    s.node_val = d; d += max_nodes;
+    s.wtot = d; d += nwarps;
+    s.misc = d; d += 8;
+    int32_t* q = reinterpret_cast<int32_t*>(d);
+    s.node_a = q; q += max_nodes;
+    s.node_b = q; q += max_nodes;
+    s.node_kind = q; q += max_nodes;
+    s.desc = q; q += 16;
+    s.pk = reinterpret_cast<uint16_t*>(q); q += ((L + 2 * pad) + 1) / 2;
+    s.pos = reinterpret_cast<uint16_t*>(q); q += (n_max + 1) / 2;
+    s.sigma = reinterpret_cast<int8_t*>(q);
+    return s;
+}
+
+// desc[] slots
+enum { D_SEQ = 0, D_PART, D_KIND, D_OLD, D_NEW, D_STOP, D_EXACT, D_NCROSS, D_END, D_AVAIL, D_NNODES, D_BADR };
+// misc[] slots
+enum { X_E = 0, X_UC, X_UE, X_UD, X_TNEW, X_R };
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// Add `delta` to the packed cell of site x and to every reflect image inside the halo.
+__device__ __forceinline__ void pk_add(uint16_t* pk, int L, int pad, int x, int delta) {
+    if (pad < L) {
+        pk[pad + x] = (uint16_t)(pk[pad + x] + delta);
+        if (x < pad) pk[pad - 1 - x] = (uint16_t)(pk[pad - 1 - x] + delta);
+        if (x >= L - pad) pk[pad + 2 * L - 1 - x] = (uint16_t)(pk[pad + 2 * L - 1 - x] + delta);
+    } else {
+        const int twoL = 2 * L;
+        const int kmax = (pad + L) / twoL + 1;
+        for (int k = -kmax; k <= kmax; ++k) {
+            int i1 = k * twoL + x, i2 = k * twoL - 1 - x;
+            if (i1 >= -pad && i1 < L + pad) pk[pad + i1] = (uint16_t)(pk[pad + i1] + delta);
+            if (i2 >= -pad && i2 < L + pad) pk[pad + i2] = (uint16_t)(pk[pad + i2] + delta);
+        }
+    }
+}
+
+__device__ __forceinline__ int occ_of(uint16_t v) { return (v & 0xff) + (v >> 8); }
+
+// Hop rates of one particle, CLASS.py:276-336 (anchors absent).
+__device__ __forceinline__ void hop_rates(const uint16_t* pk, int pad, int L, int K, double D, double lam, bool crowd,
+                                          int p, int sg, double& rl, double& rr, double& ra) {
+    int fwd = clampi(p + (sg == 1), 0, L - 1), lt = clampi(p - 1, 0, L - 1), rt = clampi(p + 1, 0, L - 1);
+    int occ_l = occ_of(pk[pad + lt]), occ_r = occ_of(pk[pad + rt]);
+    int occ_f = (fwd == rt) ? occ_r : occ_of(pk[pad + fwd]);
+    bool f_free = (occ_f < K) && (fwd != p);
+    bool l_free = (occ_l < K) && (lt != p);
+    bool r_free = (occ_r < K) && (rt != p);
+    rl = l_free ? D : APS_MUL(D, 0.0);
+    rr = r_free ? D : APS_MUL(D, 0.0);
+    ra = (sg == 1 && f_free) ? lam : 0.0;
+    if (crowd) {
+        double kd = (double)K;
+        double ff = APS_SUB(1.0, APS_DIV((double)occ_f, kd));
+        ff = ff < 0.0 ? 0.0 : (ff > 1.0 ? 1.0 : ff);
+        ra = APS_MUL(ra, ff);
+        double lf = APS_SUB(1.0, APS_DIV((double)occ_l, kd)), rf = APS_SUB(1.0, APS_DIV((double)occ_r, kd));
+        lf = lf < 0.0 ? 0.0 : (lf > 1.0 ? 1.0 : lf);
+        rf = rf < 0.0 ? 0.0 : (rf > 1.0 ? 1.0 : rf);
+        rl = APS_MUL(rl, lf);
+        rr = APS_MUL(rr, rf);
+    }
+}
+
+// Local magnetisation at site p: the two Gaussian filters of CLASS.py:229-245 evaluated at one
+// output in scipy's symmetric-correlate order.
+__device__ __forceinline__ double local_m(const uint16_t* pk, const double* w, int pad, int r, int p) {
+    const uint16_t* c = pk + pad + p;
+    uint32_t v0 = c[0];
+    double sc = APS_MUL((double)((int)(v0 & 0xff) - (int)(v0 >> 8)), w[r]);
+    double tc = APS_MUL((double)((int)(v0 & 0xff) + (int)(v0 >> 8)), w[r]);
+    for (int jj = -r; jj < 0; ++jj) {
+        uint32_t a = (uint32_t)c[jj] + (uint32_t)c[-jj];
+        int acp = (int)(a & 0xff), acm = (int)(a >> 8);
+        double wj = w[r + jj];
+        sc = APS_ADD(sc, APS_MUL((double)(acp - acm), wj));
+        tc = APS_ADD(tc, APS_MUL((double)(acp + acm), wj));
+    }
+    double m = 0.0;
+    if (tc > 0.0) m = APS_DIV(sc, tc);
+    m = m < -1.0 ? -1.0 : (m > 1.0 ? 1.0 : m);
+    return m;
+}
+
+// rates[i] of CLASS.py:351 for one particle (bind/unbind/exit terms are +0.0).
+__device__ __forceinline__ double particle_rate(const Smem& s, const aps_params& P, int pad, bool crowd, double beta,
+                                                double m_global, int p, int sg) {
+    double rl, rr, ra;
+    hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, rl, rr, ra);
+    double m = (P.radius < 0) ? m_global : local_m(s.pk, s.w, pad, P.radius, p);
+    double arg = APS_MUL(APS_MUL(-beta, (double)sg), m);
+    double cv = aps_exp(arg);
+    return APS_ADD(APS_ADD(APS_ADD(rl, rr), ra), cv);
+}
+
+// numpy pairwise-sum tree for n elements, built once per replica by one thread.
+// Nodes are stored children-before-parents; kind 0 = leaf (a=start, b=len), 1 = add(a, b).
+__device__ inline int build_sum_tree(int n, int32_t* na, int32_t* nb, int32_t* nk, int cap) {
+    // explicit stack of (start, len, state, left_node)
+    int st_start[32], st_len[32], st_state[32], st_left[32];
+    int sp = 0, nn = 0, ret = -1;
+    st_start[0] = 0; st_len[0] = n; st_state[0] = 0; st_left[0] = -1; sp = 1;
+    while (sp > 0) {
+        int top = sp - 1;
+        int start = st_start[top], len = st_len[top];
+        if (len <= 128) {
+            if (nn >= cap) return -1;
+            na[nn] = start; nb[nn] = len; nk[nn] = 0; ret = nn++; --sp;
+            continue;
+        }
+        int n2 = len / 2; n2 -= n2 % 8;
+        if (st_state[top] == 0) {
+            st_state[top] = 1;
+            st_start[sp] = start; st_len[sp] = n2; st_state[sp] = 0; st_left[sp] = -1; ++sp;
+        } else if (st_state[top] == 1) {
+            st_left[top] = ret; st_state[top] = 2;
+            st_start[sp] = start + n2; st_len[sp] = len - n2; st_state[sp] = 0; st_left[sp] = -1; ++sp;
+        } else {
+            if (nn >= cap) return -1;
+            na[nn] = st_left[top]; nb[nn] = ret; nk[nn] = 1; ret = nn++; --sp;
+        }
+    }
+    return nn;
+}
+
+// Apply one event to the shared-memory state.
+__device__ __forceinline__ void apply_event(const Smem& s, int L, int pad, int i, int kind, int oldp, int newp, int sg) {
+    if (kind == APS_EV_FLIP) {
+        s.sigma[i] = (int8_t)(-sg);
+        pk_add(s.pk, L, pad, oldp, sg == 1 ? 255 : -255);   // c_plus-1,c_minus+1  or the reverse
+    } else {
+        s.pos[i] = (uint16_t)newp;
+        int d = sg == 1 ? 1 : 256;
+        pk_add(s.pk, L, pad, oldp, -d);
+        pk_add(s.pk, L, pad, newp, d);
+    }
+}
+
+// Decide the event of particle `sel` from u_event/u_dir (CLASS.py:362-446) and apply it.
+// Returns false (nothing applied) if a direction draw is needed but not available.
+__device__ __forceinline__ bool decode_and_apply(const Smem& s, const aps_params& P, int pad, bool crowd, int sel,
+                                                 double ue, double ud, int avail, int seq) {
+    int p = s.pos[sel], sg = s.sigma[sel];
+    double rl, rr, ra;
+    hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, rl, rr, ra);
+    double v = APS_MUL(ue, s.rates[sel]);
+    double diff_thresh = APS_ADD(rl, rr);
+    double act_thresh = APS_ADD(diff_thresh, ra);
+    int kind, newp = p;
+    if (v < diff_thresh) {
+        if (avail < 4) { s.desc[D_STOP] = 1; s.desc[D_SEQ] = seq; return false; }
+        if (ud < APS_DIV(rl, APS_ADD(rl, rr))) { kind = APS_EV_DIFF_LEFT; newp = clampi(p - 1, 0, P.L - 1); }
+        else { kind = APS_EV_DIFF_RIGHT; newp = clampi(p + 1, 0, P.L - 1); }
+    } else if (v < act_thresh) {
+        kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, P.L - 1);
+    } else kind = APS_EV_FLIP;
+    apply_event(s, P.L, pad, sel, kind, p, newp, sg);
+    s.desc[D_PART] = sel; s.desc[D_KIND] = kind; s.desc[D_OLD] = p; s.desc[D_NEW] = newp;
+    s.desc[D_STOP] = 0; s.desc[D_SEQ] = seq;
+    return true;
+}
+
+template <int NT, bool PHILOX>
+__global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = NT / 32;
+    const aps_params& P = A.p;
+    const aps_batch& B = A.b;
+    const int rep = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int L = P.L, pad = A.pad, r = P.radius, n_max = B.n_max, M = B.M;
+    const bool crowd = (P.flags & APS_FLAG_CROWDING) != 0;
+    const bool global_m = r < 0;
+    const int n = B.n[rep];
+    const double beta = B.beta[rep], T = P.T;
+    Smem s = carve(smem_raw, L, n_max, pad, A.max_nodes, NW);
+
+    // ---------------- prologue: stage the replica into shared memory ----------------
+    {
+        uint32_t* pk32 = reinterpret_cast<uint32_t*>(s.pk);
+        for (int i = tid; i < (L + 2 * pad + 1) / 2; i += NT) pk32[i] = 0u;
+        if (r >= 0) for (int i = tid; i <= r; i += NT) s.w[i] = B.weights[i];
+        if (tid < 16) s.desc[tid] = 0;
+    }
+    __syncthreads();
+    int S = 0;  // sum(sigma), replicated in every thread
+    {
+        const int32_t* gp = B.pos0 + (size_t)rep * n_max;
+        const int8_t* gs = B.sigma0 + (size_t)rep * n_max;
+        uint32_t* pk32 = reinterpret_cast<uint32_t*>(s.pk);
+        int part = 0;
+        for (int i = tid; i < n; i += NT) {
+            int p = gp[i], sg = gs[i];
+            s.pos[i] = (uint16_t)p; s.sigma[i] = (int8_t)sg;
+            part += sg;
+            uint32_t d = sg == 1 ? 1u : 256u;
+            // every reflect image of p inside the halo (atomic: several particles may share a word)
+            const int twoL = 2 * L, kmax = (pad + L) / twoL + 1;
+            for (int k = -kmax; k <= kmax; ++k) {
+                int i1 = k * twoL + p, i2 = k * twoL - 1 - p;
+                if (i1 >= -pad && i1 < L + pad) { int q = pad + i1; atomicAdd(&pk32[q >> 1], d << (16 * (q & 1))); }
+                if (i2 >= -pad && i2 < L + pad) { int q = pad + i2; atomicAdd(&pk32[q >> 1], d << (16 * (q & 1))); }
+            }
+        }
+        // block-wide sum of sigma
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) s.node_a[wid] = part;   // node arrays are free until the tree is built
+        __syncthreads();
+        for (int w2 = 0; w2 < NW; ++w2) S += s.node_a[w2];
+        __syncthreads();
+        if (tid == 0) s.desc[D_NNODES] = (n > 0) ? build_sum_tree(n, s.node_a, s.node_b, s.node_kind, A.max_nodes) : 0;
+    }
+    __syncthreads();
+    const int nnodes = s.desc[D_NNODES];
+
+    int64_t n_done = 0;
+    const int64_t ev_base = B.ev_start ? B.ev_start[rep] : 0;
+    int64_t cursor = 0, n_guard = 0;
+    const int64_t draws_len = PHILOX ? 0 : (B.draw_off[rep + 1] - B.draw_off[rep]);
+    const double* gdraws = PHILOX ? nullptr : (B.draws + B.draw_off[rep]);
+    const uint32_t k0 = PHILOX ? (uint32_t)B.seeds[rep] : 0u, k1 = PHILOX ? (uint32_t)(B.seeds[rep] >> 32) : 0u;
+    double t = B.t_start ? B.t_start[rep] : 0.0;
+    int obs_idx = B.obs_start ? B.obs_start[rep] : 0;
+    int status = APS_RUN_DONE;
+    double m_glob = (global_m && n > 0) ? APS_DIV((double)S, (double)n) : 0.0;
+
+    // fetch the variates of the next event into shared memory (one thread)
+    auto fetch_draws = [&](int64_t ev_local, int64_t cur) {
+        if (PHILOX) {
+            uint64_t ev = (uint64_t)(ev_base + ev_local);
+            aps_u32x4 a = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_A, 0u, k0, k1);
+            aps_u32x4 b = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_B, 0u, k0, k1);
+            double neg = aps_log(APS_SUB(1.0, aps_u53(a.v[0], a.v[1])));
+            s.misc[X_E] = -neg;
+            s.misc[X_UC] = aps_u53(a.v[2], a.v[3]);
+            s.misc[X_UE] = aps_u53(b.v[0], b.v[1]);
+            s.misc[X_UD] = aps_u53(b.v[2], b.v[3]);
+            s.desc[D_AVAIL] = 4;
+        } else {
+            int64_t left = draws_len - cur;
+            int av = left >= 4 ? 4 : (int)(left < 0 ? 0 : left);
+            for (int k = 0; k < av; ++k) s.misc[X_E + k] = __ldg(gdraws + cur + k);
+            s.desc[D_AVAIL] = av;
+        }
+    };
+
+    // observation row writer (post-event state; field written separately)
+    auto write_rows = [&](int first, int count) {
+        for (int m = first; m < first + count; ++m) {
+            size_t row = (size_t)rep * (size_t)M + (size_t)m;
+            if ((B.record & APS_REC_COUNTS) && B.obs_cp && B.obs_cm) {
+                int8_t* ocp = B.obs_cp + row * (size_t)L; int8_t* ocm = B.obs_cm + row * (size_t)L;
+                for (int l = tid; l < L; l += NT) { uint16_t v = s.pk[pad + l]; ocp[l] = (int8_t)(v & 0xff); ocm[l] = (int8_t)(v >> 8); }
+            }
+            if ((B.record & APS_REC_POS) && B.obs_pos) {
+                int32_t* op = B.obs_pos + row * (size_t)n_max;
+                for (int i = tid; i < n; i += NT) op[i] = (int32_t)s.pos[i];
+            }
+            if (B.obs_sigma_sum && tid == 0) B.obs_sigma_sum[row] = S;
+        }
+    };
+    auto write_field = [&](int first, int count) {
+        if (!((B.record & APS_REC_MLOCAL) && B.obs_m_local)) return;
+        for (int l = tid; l < L; l += NT) {
+            double m = global_m ? m_glob : local_m(s.pk, s.w, pad, r, l);
+            for (int mm = first; mm < first + count; ++mm)
+                B.obs_m_local[((size_t)rep * (size_t)M + (size_t)mm) * (size_t)L + l] = m;
+        }
+    };
+
+    if (n == 0 || nnodes <= 0) {
+        status = APS_RUN_EMPTY;
+    } else {
+        // initial rates (every particle), observation row 0, first variates
+        for (int i = tid; i < n; i += NT) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, s.pos[i], s.sigma[i]);
+        if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
+        if (tid == NT - 1) fetch_draws(0, 0);
+        __syncthreads();
+        double next_obs = (obs_idx < M) ? B.times_obs[obs_idx] : 0.0;
+        const double guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
+        const int chunk = (n + NT - 1) / NT;
+
+        while (true) {
+            if (!(t < T)) { status = APS_RUN_DONE; break; }
+            if (B.max_events > 0 && n_done >= B.max_events) { status = APS_RUN_MAX_EVENTS; break; }
+            const int avail = s.desc[D_AVAIL];
+            if (avail < 3) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+            const double uc = s.misc[X_UC], ue = s.misc[X_UE], ud = s.misc[X_UD];
+            const int seq = (int)(n_done & 0x3fffffff) + 1;
+
+            // ---- A1: chunked prefix sums (approximate order) + exact pairwise leaves ----
+            const int c0 = tid * chunk;
+            double cs = 0.0;
+            for (int j = 0; j < chunk; ++j) { int i = c0 + j; if (i < n) cs = APS_ADD(cs, s.rates[i]); }
+            double incl = cs;
+            for (int o = 1; o < 32; o <<= 1) {
+                double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = APS_ADD(incl, up);
+            }
+            double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) prev = 0.0;
+            if (lane == 31) s.wtot[wid] = incl;
+            // exact leaves: 8 lanes per leaf == numpy's 8 strided accumulators
+            for (int g = tid >> 3; g < nnodes; g += NT / 8) {
+                const unsigned gmask = 0xffu << (lane & 24);
+                if (s.node_kind[g] != 0) continue;   // uniform within the 8-lane group
+                const int k = tid & 7, start = s.node_a[g], len = s.node_b[g];
+                double res;
+                if (len < 8) {
+                    res = 0.0;
+                    for (int i = 0; i < len; ++i) res = APS_ADD(res, s.rates[start + i]);
+                } else {
+                    const int body = len - (len % 8);
+                    double acc = s.rates[start + k];
+                    for (int i = 8; i < body; i += 8) acc = APS_ADD(acc, s.rates[start + i + k]);
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 1));
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 2));
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 4));
+                    res = acc;
+                    for (int i = body; i < len; ++i) res = APS_ADD(res, s.rates[start + i]);
+                }
+                if (k == 0) s.node_val[g] = res;
+            }
+            __syncthreads();  // BAR1
+
+            // ---- A2: locate the selected particle; one thread forms R, tau and the clock ----
+            double base = 0.0, atot = 0.0;
+            for (int w2 = 0; w2 < NW; ++w2) { if (w2 == wid) base = atot; atot = APS_ADD(atot, s.wtot[w2]); }
+            const double target = APS_MUL(uc, atot);
+            const double excl = APS_ADD(base, prev), inc2 = APS_ADD(base, incl);
+            if (excl <= target && target < inc2 && c0 < n) {
+                // walk the chunk; interior edges use the same association as the scan inputs and the
+                // last edge is pinned to inc2 so that neighbouring threads share their boundary exactly
+                double run = 0.0, lo = excl, hi = excl; int sel = -1;
+                for (int j = 0; j < chunk; ++j) {
+                    int i = c0 + j; if (i >= n) break;
+                    run = APS_ADD(run, s.rates[i]);
+                    const bool last = (j == chunk - 1) || (i == n - 1);
+                    hi = last ? inc2 : APS_ADD(base, APS_ADD(prev, run));
+                    if (target < hi) { sel = i; break; }
+                    lo = hi;
+                }
+                const double band = APS_MUL(guard, atot);
+                if (sel < 0 || (target - lo) < band || (hi - target) < band) {
+                    s.desc[D_EXACT] = 1;
+                } else {
+                    decode_and_apply(s, P, pad, crowd, sel, ue, ud, avail, seq);
+                }
+            }
+            if (tid == NT - 1) {
+                for (int g = 0; g < nnodes; ++g)
+                    if (s.node_kind[g] != 0) s.node_val[g] = APS_ADD(s.node_val[s.node_a[g]], s.node_val[s.node_b[g]]);
+                const double R = s.node_val[nnodes - 1];
+                const double tau = APS_MUL(APS_DIV(1.0, R), s.misc[X_E]);
+                const double tn = APS_ADD(t, tau);
+                s.misc[X_R] = R; s.misc[X_TNEW] = tn;
+                s.desc[D_BADR] = !(R > 0.0);
+                s.desc[D_END] = tn > T;
+                int nc = 0;
+                if (!(tn > T) && obs_idx < M && next_obs <= tn) {
+                    nc = 1;
+                    while (obs_idx + nc < M && B.times_obs[obs_idx + nc] <= tn) ++nc;
+                }
+                s.desc[D_NCROSS] = nc;
+            }
+            __syncthreads();  // BAR2
+
+            if (s.desc[D_BADR]) { status = APS_RUN_EMPTY; break; }
+            if (s.desc[D_EXACT] || s.desc[D_SEQ] != seq) {
+                // exact serial selection (CLASS.py:359-360 literally); rare
+                __syncthreads();
+                if (tid == 0) {
+                    const double R = s.misc[X_R];
+                    double acc = 0.0;
+                    for (int i = 0; i < n; ++i) acc = APS_ADD(acc, APS_DIV(s.rates[i], R));
+                    const double last = acc;
+                    int sel = n - 1; acc = 0.0;
+                    for (int i = 0; i < n; ++i) { acc = APS_ADD(acc, APS_DIV(s.rates[i], R)); if (APS_DIV(acc, last) > uc) { sel = i; break; } }
+                    decode_and_apply(s, P, pad, crowd, sel, ue, ud, avail, seq);
+                    s.desc[D_EXACT] = 0;
+                }
+                ++n_guard;
+                __syncthreads();
+            }
+            if (s.desc[D_STOP]) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+            const int kind = s.desc[D_KIND], part = s.desc[D_PART], oldp = s.desc[D_OLD], newp = s.desc[D_NEW];
+            const int ncross = s.desc[D_NCROSS], endflag = s.desc[D_END];
+            const double tnew = s.misc[X_TNEW];
+            if (B.trace && tid == 0 && n_done < B.trace_cap) {
+                int32_t* tr = B.trace + ((size_t)rep * (size_t)B.trace_cap + (size_t)n_done) * 3;
+                tr[0] = part; tr[1] = kind; tr[2] = (kind == APS_EV_FLIP) ? -1 : newp;
+            }
+            ++n_done;
+            cursor += 3 + (kind < 2 ? 1 : 0);
+            int sg_new = 0;
+            if (kind == APS_EV_FLIP) { sg_new = s.sigma[part]; S += 2 * sg_new; }
+            t = tnew;
+            if (endflag) { status = APS_RUN_DONE; break; }
+            if (ncross > 0) {
+                // rows get the field computed BEFORE this event (CLASS.py:512,525) and the state after it
+                if ((B.record & APS_REC_MLOCAL) && B.obs_m_local) {
+                    __syncthreads();
+                    if (tid == 0) {  // undo
+                        if (kind == APS_EV_FLIP) pk_add(s.pk, L, pad, oldp, sg_new == 1 ? 255 : -255);
+                        else { int d = s.sigma[part] == 1 ? 1 : 256; pk_add(s.pk, L, pad, newp, -d); pk_add(s.pk, L, pad, oldp, d); }
+                    }
+                    __syncthreads();
+                    write_field(obs_idx, ncross);   // m_glob still holds the pre-event value
+                    __syncthreads();
+                    if (tid == 0) {  // redo
+                        if (kind == APS_EV_FLIP) pk_add(s.pk, L, pad, oldp, sg_new == 1 ? -255 : 255);
+                        else { int d = s.sigma[part] == 1 ? 1 : 256; pk_add(s.pk, L, pad, newp, d); pk_add(s.pk, L, pad, oldp, -d); }
+                    }
+                    __syncthreads();
+                }
+                write_rows(obs_idx, ncross);
+                obs_idx += ncross;
+                if (obs_idx < M) next_obs = B.times_obs[obs_idx];
+            }
+            if (obs_idx >= M) { status = APS_RUN_DONE; break; }
+
+            // ---- B: refresh the rates the event can have changed; prefetch the next variates ----
+            if (tid == NT - 1) fetch_draws(n_done, cursor);
+            int wlo, whi;
+            if (global_m) {
+                if (kind == APS_EV_FLIP) { m_glob = APS_DIV((double)S, (double)n); wlo = 0; whi = L - 1; }
+                else { wlo = (oldp < newp ? oldp : newp) - 1; whi = (oldp < newp ? newp : oldp) + 1; }
+            } else {
+                const int reach = r > 1 ? r : 1;
+                wlo = (oldp < newp ? oldp : newp) - reach; whi = (oldp < newp ? newp : oldp) + reach;
+            }
+            for (int i = tid; i < n; i += NT) {
+                int p = s.pos[i];
+                if (p >= wlo && p <= whi) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, p, s.sigma[i]);
+            }
+            __syncthreads();  // BAR3
+        }
+    }
+
+    // ---------------- epilogue ----------------
+    if (tid == 0) {
+        if (B.n_obs) B.n_obs[rep] = obs_idx;
+        if (B.n_events) B.n_events[rep] = ev_base + n_done;
+        if (B.t_end) B.t_end[rep] = t;
+        if (B.status) B.status[rep] = status;
+        if (B.n_guard) B.n_guard[rep] = n_guard;
+        if (B.draws_used) B.draws_used[rep] = PHILOX ? 0 : cursor;
+    }
+    __syncthreads();
+    if (B.pos_end) for (int i = tid; i < n; i += NT) B.pos_end[(size_t)rep * n_max + i] = (int32_t)s.pos[i];
+    if (B.sigma_end) for (int i = tid; i < n; i += NT) B.sigma_end[(size_t)rep * n_max + i] = s.sigma[i];
+}
+
+}  // namespace aps

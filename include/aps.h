@@ -143,6 +143,11 @@ int64_t aps_launch_count(void);
 /* Shared-memory bytes and threads the K1 plan uses for (L, n_max, radius); <0 if it cannot fit. */
 int64_t aps_replica_smem_bytes(const aps_params* p, int32_t n_max);
 
+/* Test / tuning hooks: widen the selection guard band (forces the exact serial slow path) and
+ * override the K1 block size (64, 128, 256; 0 = heuristic). Not needed in production. */
+void aps_debug_set_guard_scale(double scale);
+void aps_debug_set_k1_threads(int threads);
+
 #ifdef __cplusplus
 }
 #endif
