@@ -86,6 +86,7 @@ SYMBOLS = {
     "aps_replica_smem_bytes": (C.c_int64, [_P(ApsParams), C.c_int32]),
     "aps_debug_set_guard_scale": (None, [C.c_double]),
     "aps_debug_set_k1_threads": (None, [C.c_int]),
+    "aps_debug_set_use_lut": (None, [C.c_int]),
 }
 
 _lib = None

@@ -17,6 +17,7 @@ thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
 double g_guard_scale = 1.0;
 int g_k1_threads = 0;  // 0 = heuristic
+int g_use_lut = 1;
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -86,8 +87,8 @@ int launch_nt(const aps::K1Args& a, bool philox, size_t smem, cudaStream_t st) {
 int pick_threads(int n_max) {
     if (g_k1_threads) return g_k1_threads;
     const char* e = getenv("APS_K1_THREADS");
-    if (e) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) return v; }
-    return n_max > 1536 ? 256 : 128;
+    if (e) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) return v; }
+    return n_max > 2048 ? 128 : 64;
 }
 
 int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philox) {
@@ -101,10 +102,13 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     a.max_nodes = max_tree_nodes(b->n_max);
     a.pad = p->radius > 0 ? p->radius : 0;
     const int nt = pick_threads(b->n_max);
-    const size_t smem = aps::k1_smem_bytes(p->L, b->n_max, p->radius, a.max_nodes, nt / 32);
+    a.bcode = 2 * p->K + 1;
+    a.use_lut = (g_use_lut && p->radius >= 0 && aps::k1_lut_bytes(p->K, p->radius) <= aps::kLutMaxBytes) ? 1 : 0;
+    const size_t smem = aps::k1_smem_bytes(p->L, b->n_max, p->radius, a.max_nodes, nt / 32, a.use_lut, p->K);
     if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "replica does not fit in 227 KB of shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     switch (nt) {
+        case 32: return launch_nt<32>(a, philox, smem, st);
         case 64: return launch_nt<64>(a, philox, smem, st);
         case 256: return launch_nt<256>(a, philox, smem, st);
         default: return launch_nt<128>(a, philox, smem, st);
@@ -212,7 +216,8 @@ int64_t aps_launch_count(void) { return g_launches.load(); }
 int64_t aps_replica_smem_bytes(const aps_params* p, int32_t n_max) {
     if (!p || n_max < 1 || n_max > 8192) return -1;
     int nt = pick_threads(n_max);
-    size_t b = aps::k1_smem_bytes(p->L, n_max, p->radius, max_tree_nodes(n_max), nt / 32);
+    int use_lut = (g_use_lut && p->radius >= 0 && aps::k1_lut_bytes(p->K, p->radius) <= aps::kLutMaxBytes) ? 1 : 0;
+    size_t b = aps::k1_smem_bytes(p->L, n_max, p->radius, max_tree_nodes(n_max), nt / 32, use_lut, p->K);
     return b > 227 * 1024 ? -1 : (int64_t)b;
 }
 
@@ -223,6 +228,7 @@ int aps_run_philox_host(const aps_params* p, const aps_batch* b) { return run_ho
 
 // Test / tuning hooks (declared in include/aps.h).
 void aps_debug_set_guard_scale(double s) { g_guard_scale = s; }
-void aps_debug_set_k1_threads(int nt) { g_k1_threads = (nt == 64 || nt == 128 || nt == 256) ? nt : 0; }
+void aps_debug_set_k1_threads(int nt) { g_k1_threads = (nt == 32 || nt == 64 || nt == 128 || nt == 256) ? nt : 0; }
+void aps_debug_set_use_lut(int on) { g_use_lut = on ? 1 : 0; }
 
 }  // extern "C"

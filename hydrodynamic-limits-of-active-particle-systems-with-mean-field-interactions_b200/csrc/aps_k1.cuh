@@ -42,12 +42,24 @@ struct K1Args {
     double guard_scale;   // multiplies the selection guard band (test hook; 1.0 in production)
     int32_t max_nodes;    // tree nodes the shared-memory plan reserves
     int32_t pad;          // halo width = max(radius, 0)
+    int32_t use_lut;      // 1: filter taps come from the product table (see local_m_lut)
+    int32_t bcode;        // 2K+1: radix of the per-site code c_plus + bcode*c_minus
 };
 
+constexpr int kRing = 128;      // doubles of variate look-ahead kept in shared memory
+constexpr size_t kLutMaxBytes = 24 * 1024;
+
 // Shared-memory plan (bytes) — keep in sync with carve() below.
-__host__ __device__ inline size_t k1_smem_bytes(int L, int n_max, int radius, int max_nodes, int nwarps) {
+__host__ __device__ inline size_t k1_lut_bytes(int K, int radius) {
+    if (radius < 0) return 0;
+    size_t b = (size_t)(2 * K + 1);
+    return (size_t)(radius + 1) * b * b * 16;
+}
+__host__ __device__ inline size_t k1_smem_bytes(int L, int n_max, int radius, int max_nodes, int nwarps, int use_lut, int K) {
     int pad = radius > 0 ? radius : 0;
     size_t d = 0;
+    if (use_lut) d += k1_lut_bytes(K, radius) / 8;  // product table (16-byte aligned: first)
+    d += (size_t)kRing;                  // variate ring
     d += (size_t)n_max;                  // rates
     d += (size_t)(pad + 1);              // taps w[0..r]
     d += (size_t)max_nodes;              // tree node values
@@ -57,20 +69,26 @@ __host__ __device__ inline size_t k1_smem_bytes(int L, int n_max, int radius, in
     bytes += (size_t)max_nodes * 3 * 4;  // node_a, node_b (children or leaf start/len), kind
     bytes += 16 * 4;                     // desc + flags
     bytes += (((size_t)(L + 2 * pad) + 1) / 2) * 4;  // packed lattice (uint16, 4-byte granules)
+    if (use_lut) bytes += (((size_t)(L + 2 * pad) + 1) / 2) * 4;  // per-site codes
     bytes += (((size_t)n_max + 1) / 2) * 4;          // pos (uint16)
     bytes += (((size_t)n_max + 3) / 4) * 4;          // sigma (int8)
     return bytes;
 }
 
 struct Smem {
+    double2* lut; double* ring;
     double* rates; double* w; double* node_val; double* wtot; double* misc;
     int32_t* node_a; int32_t* node_b; int32_t* node_kind; int32_t* desc;
-    uint16_t* pk; uint16_t* pos; int8_t* sigma;
+    uint16_t* pk; uint16_t* code; uint16_t* pos; int8_t* sigma;
 };
 
-__device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int pad, int max_nodes, int nwarps) {
+__device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int pad, int max_nodes, int nwarps,
+                                      int use_lut, int K, int radius) {
     Smem s;
     double* d = reinterpret_cast<double*>(base);
+    s.lut = reinterpret_cast<double2*>(d);
+    if (use_lut) d += k1_lut_bytes(K, radius) / 8;
+    s.ring = d; d += kRing;
     s.rates = d; d += n_max;
     s.w = d; d += pad + 1;
     s.node_val = d; d += max_nodes;
@@ -82,6 +100,7 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int
     s.node_kind = q; q += max_nodes;
     s.desc = q; q += 16;
     s.pk = reinterpret_cast<uint16_t*>(q); q += ((L + 2 * pad) + 1) / 2;
+    s.code = reinterpret_cast<uint16_t*>(q); if (use_lut) q += ((L + 2 * pad) + 1) / 2;
     s.pos = reinterpret_cast<uint16_t*>(q); q += (n_max + 1) / 2;
     s.sigma = reinterpret_cast<int8_t*>(q);
     return s;
@@ -90,12 +109,12 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int
 // desc[] slots
 enum { D_SEQ = 0, D_PART, D_KIND, D_OLD, D_NEW, D_STOP, D_EXACT, D_NCROSS, D_END, D_AVAIL, D_NNODES, D_BADR };
 // misc[] slots
-enum { X_E = 0, X_UC, X_UE, X_UD, X_TNEW, X_R };
+enum { X_TNEW = 0, X_R };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// Add `delta` to the packed cell of site x and to every reflect image inside the halo.
-__device__ __forceinline__ void pk_add(uint16_t* pk, int L, int pad, int x, int delta) {
+// Add `delta` to the cell of site x and to every reflect image inside the halo.
+__device__ __forceinline__ void cell_add(uint16_t* pk, int L, int pad, int x, int delta) {
     if (pad < L) {
         pk[pad + x] = (uint16_t)(pk[pad + x] + delta);
         if (x < pad) pk[pad - 1 - x] = (uint16_t)(pk[pad - 1 - x] + delta);
@@ -109,6 +128,12 @@ __device__ __forceinline__ void pk_add(uint16_t* pk, int L, int pad, int x, int 
             if (i2 >= -pad && i2 < L + pad) pk[pad + i2] = (uint16_t)(pk[pad + i2] + delta);
         }
     }
+}
+
+// packed counts (c_plus | c_minus<<8) and, when the product table is in use, the radix code
+__device__ __forceinline__ void pk_add(const Smem& s, int L, int pad, int x, int dplus, int dminus, int bcode, bool lut) {
+    cell_add(s.pk, L, pad, x, dplus + 256 * dminus);
+    if (lut) cell_add(s.code, L, pad, x, dplus + bcode * dminus);
 }
 
 __device__ __forceinline__ int occ_of(uint16_t v) { return (v & 0xff) + (v >> 8); }
@@ -158,12 +183,38 @@ __device__ __forceinline__ double local_m(const uint16_t* pk, const double* w, i
     return m;
 }
 
+// Same value, fewer instructions: per tap the pair (x[l+j]+x[l-j]) is a small integer pair
+// (a_plus, a_minus) in [0,2K]^2, so both products (a_plus-a_minus)*w_j and (a_plus+a_minus)*w_j
+// are looked up from a table built once per CTA with the same __dmul_rn; the radix codes of the
+// two sites add up to the table index.  Adds stay in the reference order.
+__device__ __forceinline__ double local_m_lut(const uint16_t* code, const double2* lut, int pad, int r, int b2, int p) {
+    const uint16_t* c = code + pad + p;
+    double2 v = lut[r * b2 + c[0]];
+    double sc = v.x, tc = v.y;
+    const double2* row = lut;
+#pragma unroll 4
+    for (int jj = -r; jj < 0; ++jj) {
+        int idx = (int)c[jj] + (int)c[-jj];
+        double2 t2 = row[idx];
+        row += b2;
+        sc = APS_ADD(sc, t2.x);
+        tc = APS_ADD(tc, t2.y);
+    }
+    double m = 0.0;
+    if (tc > 0.0) m = APS_DIV(sc, tc);
+    m = m < -1.0 ? -1.0 : (m > 1.0 ? 1.0 : m);
+    return m;
+}
+
 // rates[i] of CLASS.py:351 for one particle (bind/unbind/exit terms are +0.0).
+__device__ __forceinline__ double site_m(const Smem& s, const aps_params& P, int pad, bool lut, int b2, int p) {
+    return lut ? local_m_lut(s.code, s.lut, pad, P.radius, b2, p) : local_m(s.pk, s.w, pad, P.radius, p);
+}
 __device__ __forceinline__ double particle_rate(const Smem& s, const aps_params& P, int pad, bool crowd, double beta,
-                                                double m_global, int p, int sg) {
+                                                double m_global, int p, int sg, bool lut, int b2) {
     double rl, rr, ra;
     hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, rl, rr, ra);
-    double m = (P.radius < 0) ? m_global : local_m(s.pk, s.w, pad, P.radius, p);
+    double m = (P.radius < 0) ? m_global : site_m(s, P, pad, lut, b2, p);
     double arg = APS_MUL(APS_MUL(-beta, (double)sg), m);
     double cv = aps_exp(arg);
     return APS_ADD(APS_ADD(APS_ADD(rl, rr), ra), cv);
@@ -200,22 +251,34 @@ __device__ inline int build_sum_tree(int n, int32_t* na, int32_t* nb, int32_t* n
 }
 
 // Apply one event to the shared-memory state.
-__device__ __forceinline__ void apply_event(const Smem& s, int L, int pad, int i, int kind, int oldp, int newp, int sg) {
+__device__ __forceinline__ void apply_event(const Smem& s, int L, int pad, int i, int kind, int oldp, int newp, int sg,
+                                            int bcode, bool lut) {
     if (kind == APS_EV_FLIP) {
         s.sigma[i] = (int8_t)(-sg);
-        pk_add(s.pk, L, pad, oldp, sg == 1 ? 255 : -255);   // c_plus-1,c_minus+1  or the reverse
+        pk_add(s, L, pad, oldp, -sg, sg, bcode, lut);   // c_plus-1,c_minus+1  or the reverse
     } else {
         s.pos[i] = (uint16_t)newp;
-        int d = sg == 1 ? 1 : 256;
-        pk_add(s.pk, L, pad, oldp, -d);
-        pk_add(s.pk, L, pad, newp, d);
+        const int dp = sg == 1 ? 1 : 0, dm = 1 - dp;
+        pk_add(s, L, pad, oldp, -dp, -dm, bcode, lut);
+        pk_add(s, L, pad, newp, dp, dm, bcode, lut);
+    }
+}
+// Exact inverse of apply_event on the lattice arrays only (used to expose the pre-event field).
+__device__ __forceinline__ void lattice_delta(const Smem& s, int L, int pad, int kind, int oldp, int newp, int sg_old,
+                                              int sign, int bcode, bool lut) {
+    if (kind == APS_EV_FLIP) {
+        pk_add(s, L, pad, oldp, -sign * sg_old, sign * sg_old, bcode, lut);
+    } else {
+        const int dp = sg_old == 1 ? 1 : 0, dm = 1 - dp;
+        pk_add(s, L, pad, oldp, -sign * dp, -sign * dm, bcode, lut);
+        pk_add(s, L, pad, newp, sign * dp, sign * dm, bcode, lut);
     }
 }
 
 // Decide the event of particle `sel` from u_event/u_dir (CLASS.py:362-446) and apply it.
 // Returns false (nothing applied) if a direction draw is needed but not available.
 __device__ __forceinline__ bool decode_and_apply(const Smem& s, const aps_params& P, int pad, bool crowd, int sel,
-                                                 double ue, double ud, int avail, int seq) {
+                                                 double ue, double ud, int avail, int seq, int bcode, bool lut) {
     int p = s.pos[sel], sg = s.sigma[sel];
     double rl, rr, ra;
     hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, rl, rr, ra);
@@ -230,14 +293,19 @@ __device__ __forceinline__ bool decode_and_apply(const Smem& s, const aps_params
     } else if (v < act_thresh) {
         kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, P.L - 1);
     } else kind = APS_EV_FLIP;
-    apply_event(s, P.L, pad, sel, kind, p, newp, sg);
+    apply_event(s, P.L, pad, sel, kind, p, newp, sg, bcode, lut);
     s.desc[D_PART] = sel; s.desc[D_KIND] = kind; s.desc[D_OLD] = p; s.desc[D_NEW] = newp;
     s.desc[D_STOP] = 0; s.desc[D_SEQ] = seq;
     return true;
 }
 
+template <int NT>
+__device__ __forceinline__ void bsync() {
+    if (NT == 32) __syncwarp(); else __syncthreads();
+}
+
 template <int NT, bool PHILOX>
-__global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A) {
+__global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant__ K1Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = NT / 32;
     const aps_params& P = A.p;
@@ -247,51 +315,76 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
     const int L = P.L, pad = A.pad, r = P.radius, n_max = B.n_max, M = B.M;
     const bool crowd = (P.flags & APS_FLAG_CROWDING) != 0;
     const bool global_m = r < 0;
+    bool lut = A.use_lut != 0;
+    const int bcode = A.bcode, b2 = A.bcode * A.bcode;
     const int n = B.n[rep];
     const double beta = B.beta[rep], T = P.T;
-    Smem s = carve(smem_raw, L, n_max, pad, A.max_nodes, NW);
+    Smem s = carve(smem_raw, L, n_max, pad, A.max_nodes, NW, A.use_lut, P.K, r);
 
     // ---------------- prologue: stage the replica into shared memory ----------------
     {
         uint32_t* pk32 = reinterpret_cast<uint32_t*>(s.pk);
-        for (int i = tid; i < (L + 2 * pad + 1) / 2; i += NT) pk32[i] = 0u;
+        uint32_t* cd32 = reinterpret_cast<uint32_t*>(s.code);
+        for (int i = tid; i < (L + 2 * pad + 1) / 2; i += NT) { pk32[i] = 0u; if (lut) cd32[i] = 0u; }
         if (r >= 0) for (int i = tid; i <= r; i += NT) s.w[i] = B.weights[i];
+        if (lut) {
+            // table[j][a_minus*bcode + a_plus] = ((a_plus-a_minus)*w_j, (a_plus+a_minus)*w_j)
+            for (int e = tid; e < (r + 1) * b2; e += NT) {
+                int j = e / b2, idx = e - j * b2, am = idx / bcode, ap = idx - am * bcode;
+                double wj = B.weights[j];
+                s.lut[e] = make_double2(APS_MUL((double)(ap - am), wj), APS_MUL((double)(ap + am), wj));
+            }
+        }
         if (tid < 16) s.desc[tid] = 0;
     }
-    __syncthreads();
+    bsync<NT>();
     int S = 0;  // sum(sigma), replicated in every thread
     {
         const int32_t* gp = B.pos0 + (size_t)rep * n_max;
         const int8_t* gs = B.sigma0 + (size_t)rep * n_max;
         uint32_t* pk32 = reinterpret_cast<uint32_t*>(s.pk);
+        uint32_t* cd32 = reinterpret_cast<uint32_t*>(s.code);
         int part = 0;
         for (int i = tid; i < n; i += NT) {
             int p = gp[i], sg = gs[i];
             s.pos[i] = (uint16_t)p; s.sigma[i] = (int8_t)sg;
             part += sg;
-            uint32_t d = sg == 1 ? 1u : 256u;
+            const uint32_t d = sg == 1 ? 1u : 256u, dc = sg == 1 ? 1u : (uint32_t)bcode;
             // every reflect image of p inside the halo (atomic: several particles may share a word)
             const int twoL = 2 * L, kmax = (pad + L) / twoL + 1;
             for (int k = -kmax; k <= kmax; ++k) {
                 int i1 = k * twoL + p, i2 = k * twoL - 1 - p;
-                if (i1 >= -pad && i1 < L + pad) { int q = pad + i1; atomicAdd(&pk32[q >> 1], d << (16 * (q & 1))); }
-                if (i2 >= -pad && i2 < L + pad) { int q = pad + i2; atomicAdd(&pk32[q >> 1], d << (16 * (q & 1))); }
+                if (i1 >= -pad && i1 < L + pad) {
+                    int q = pad + i1; atomicAdd(&pk32[q >> 1], d << (16 * (q & 1)));
+                    if (lut) atomicAdd(&cd32[q >> 1], dc << (16 * (q & 1)));
+                }
+                if (i2 >= -pad && i2 < L + pad) {
+                    int q = pad + i2; atomicAdd(&pk32[q >> 1], d << (16 * (q & 1)));
+                    if (lut) atomicAdd(&cd32[q >> 1], dc << (16 * (q & 1)));
+                }
             }
         }
-        // block-wide sum of sigma
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        if (lane == 0) s.node_a[wid] = part;   // node arrays are free until the tree is built
-        __syncthreads();
-        for (int w2 = 0; w2 < NW; ++w2) S += s.node_a[w2];
-        __syncthreads();
+        if (lane == 0) s.ring[wid] = (double)part;   // the variate ring is free until the loop starts
+        bsync<NT>();
+        for (int w2 = 0; w2 < NW; ++w2) S += (int)s.ring[w2];
+        // The product table indexes pair sums up to 2K per species; an over-capacity initial state
+        // (the reference accepts one) makes this replica fall back to the arithmetic taps.
+        if (lut) {
+            int bad = 0;
+            for (int l = tid; l < L; l += NT) { uint16_t v = s.pk[pad + l]; bad |= ((v & 0xff) > P.K) | ((v >> 8) > P.K); }
+            bad = (NT == 32) ? __any_sync(0xffffffffu, bad) : __syncthreads_or(bad);
+            if (bad) lut = false;
+        }
+        bsync<NT>();
         if (tid == 0) s.desc[D_NNODES] = (n > 0) ? build_sum_tree(n, s.node_a, s.node_b, s.node_kind, A.max_nodes) : 0;
     }
-    __syncthreads();
+    bsync<NT>();
     const int nnodes = s.desc[D_NNODES];
 
     int64_t n_done = 0;
     const int64_t ev_base = B.ev_start ? B.ev_start[rep] : 0;
-    int64_t cursor = 0, n_guard = 0;
+    int64_t cursor = 0, n_guard = 0, rbase = -(int64_t)kRing - 8;
     const int64_t draws_len = PHILOX ? 0 : (B.draw_off[rep + 1] - B.draw_off[rep]);
     const double* gdraws = PHILOX ? nullptr : (B.draws + B.draw_off[rep]);
     const uint32_t k0 = PHILOX ? (uint32_t)B.seeds[rep] : 0u, k1 = PHILOX ? (uint32_t)(B.seeds[rep] >> 32) : 0u;
@@ -299,26 +392,6 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
     int obs_idx = B.obs_start ? B.obs_start[rep] : 0;
     int status = APS_RUN_DONE;
     double m_glob = (global_m && n > 0) ? APS_DIV((double)S, (double)n) : 0.0;
-
-    // fetch the variates of the next event into shared memory (one thread)
-    auto fetch_draws = [&](int64_t ev_local, int64_t cur) {
-        if (PHILOX) {
-            uint64_t ev = (uint64_t)(ev_base + ev_local);
-            aps_u32x4 a = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_A, 0u, k0, k1);
-            aps_u32x4 b = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_B, 0u, k0, k1);
-            double neg = aps_log(APS_SUB(1.0, aps_u53(a.v[0], a.v[1])));
-            s.misc[X_E] = -neg;
-            s.misc[X_UC] = aps_u53(a.v[2], a.v[3]);
-            s.misc[X_UE] = aps_u53(b.v[0], b.v[1]);
-            s.misc[X_UD] = aps_u53(b.v[2], b.v[3]);
-            s.desc[D_AVAIL] = 4;
-        } else {
-            int64_t left = draws_len - cur;
-            int av = left >= 4 ? 4 : (int)(left < 0 ? 0 : left);
-            for (int k = 0; k < av; ++k) s.misc[X_E + k] = __ldg(gdraws + cur + k);
-            s.desc[D_AVAIL] = av;
-        }
-    };
 
     // observation row writer (post-event state; field written separately)
     auto write_rows = [&](int first, int count) {
@@ -338,7 +411,7 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
     auto write_field = [&](int first, int count) {
         if (!((B.record & APS_REC_MLOCAL) && B.obs_m_local)) return;
         for (int l = tid; l < L; l += NT) {
-            double m = global_m ? m_glob : local_m(s.pk, s.w, pad, r, l);
+            double m = global_m ? m_glob : site_m(s, P, pad, lut, b2, l);
             for (int mm = first; mm < first + count; ++mm)
                 B.obs_m_local[((size_t)rep * (size_t)M + (size_t)mm) * (size_t)L + l] = m;
         }
@@ -347,11 +420,11 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
     if (n == 0 || nnodes <= 0) {
         status = APS_RUN_EMPTY;
     } else {
-        // initial rates (every particle), observation row 0, first variates
-        for (int i = tid; i < n; i += NT) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, s.pos[i], s.sigma[i]);
+        // initial rates (every particle) and observation row 0
+        for (int i = tid; i < n; i += NT)
+            s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, s.pos[i], s.sigma[i], lut, b2);
         if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
-        if (tid == NT - 1) fetch_draws(0, 0);
-        __syncthreads();
+        bsync<NT>();
         double next_obs = (obs_idx < M) ? B.times_obs[obs_idx] : 0.0;
         const double guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
         const int chunk = (n + NT - 1) / NT;
@@ -359,9 +432,38 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
         while (true) {
             if (!(t < T)) { status = APS_RUN_DONE; break; }
             if (B.max_events > 0 && n_done >= B.max_events) { status = APS_RUN_MAX_EVENTS; break; }
-            const int avail = s.desc[D_AVAIL];
+
+            // ---- variates of this event from the shared-memory ring (refilled by a whole warp) ----
+            int avail; double e, uc, ue, ud;
+            if (PHILOX) {
+                const int slot = (int)(n_done & 31);
+                if (slot == 0) {
+                    if (tid < 32) {   // 32 events ahead, one per lane
+                        uint64_t ev = (uint64_t)(ev_base + n_done + tid);
+                        aps_u32x4 a = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_A, 0u, k0, k1);
+                        aps_u32x4 b = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_B, 0u, k0, k1);
+                        s.ring[4 * tid + 0] = -aps_log(APS_SUB(1.0, aps_u53(a.v[0], a.v[1])));
+                        s.ring[4 * tid + 1] = aps_u53(a.v[2], a.v[3]);
+                        s.ring[4 * tid + 2] = aps_u53(b.v[0], b.v[1]);
+                        s.ring[4 * tid + 3] = aps_u53(b.v[2], b.v[3]);
+                    }
+                    bsync<NT>();
+                }
+                avail = 4;
+                e = s.ring[4 * slot]; uc = s.ring[4 * slot + 1]; ue = s.ring[4 * slot + 2]; ud = s.ring[4 * slot + 3];
+            } else {
+                if (cursor + 4 > rbase + kRing) {
+                    bsync<NT>();
+                    rbase = cursor;
+                    for (int i = tid; i < kRing; i += NT) s.ring[i] = (rbase + i < draws_len) ? __ldg(gdraws + rbase + i) : 0.0;
+                    bsync<NT>();
+                }
+                const int64_t left = draws_len - cursor;
+                avail = left >= 4 ? 4 : (int)(left < 0 ? 0 : left);
+                const int o = (int)(cursor - rbase);
+                e = s.ring[o]; uc = s.ring[o + 1]; ue = s.ring[o + 2]; ud = s.ring[o + 3];
+            }
             if (avail < 3) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
-            const double uc = s.misc[X_UC], ue = s.misc[X_UE], ud = s.misc[X_UD];
             const int seq = (int)(n_done & 0x3fffffff) + 1;
 
             // ---- A1: chunked prefix sums (approximate order) + exact pairwise leaves ----
@@ -397,7 +499,7 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
                 }
                 if (k == 0) s.node_val[g] = res;
             }
-            __syncthreads();  // BAR1
+            bsync<NT>();  // BAR1
 
             // ---- A2: locate the selected particle; one thread forms R, tau and the clock ----
             double base = 0.0, atot = 0.0;
@@ -420,14 +522,14 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
                 if (sel < 0 || (target - lo) < band || (hi - target) < band) {
                     s.desc[D_EXACT] = 1;
                 } else {
-                    decode_and_apply(s, P, pad, crowd, sel, ue, ud, avail, seq);
+                    decode_and_apply(s, P, pad, crowd, sel, ue, ud, avail, seq, bcode, lut);
                 }
             }
             if (tid == NT - 1) {
                 for (int g = 0; g < nnodes; ++g)
                     if (s.node_kind[g] != 0) s.node_val[g] = APS_ADD(s.node_val[s.node_a[g]], s.node_val[s.node_b[g]]);
                 const double R = s.node_val[nnodes - 1];
-                const double tau = APS_MUL(APS_DIV(1.0, R), s.misc[X_E]);
+                const double tau = APS_MUL(APS_DIV(1.0, R), e);
                 const double tn = APS_ADD(t, tau);
                 s.misc[X_R] = R; s.misc[X_TNEW] = tn;
                 s.desc[D_BADR] = !(R > 0.0);
@@ -439,12 +541,12 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
                 }
                 s.desc[D_NCROSS] = nc;
             }
-            __syncthreads();  // BAR2
+            bsync<NT>();  // BAR2
 
             if (s.desc[D_BADR]) { status = APS_RUN_EMPTY; break; }
             if (s.desc[D_EXACT] || s.desc[D_SEQ] != seq) {
                 // exact serial selection (CLASS.py:359-360 literally); rare
-                __syncthreads();
+                bsync<NT>();
                 if (tid == 0) {
                     const double R = s.misc[X_R];
                     double acc = 0.0;
@@ -452,11 +554,11 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
                     const double last = acc;
                     int sel = n - 1; acc = 0.0;
                     for (int i = 0; i < n; ++i) { acc = APS_ADD(acc, APS_DIV(s.rates[i], R)); if (APS_DIV(acc, last) > uc) { sel = i; break; } }
-                    decode_and_apply(s, P, pad, crowd, sel, ue, ud, avail, seq);
+                    decode_and_apply(s, P, pad, crowd, sel, ue, ud, avail, seq, bcode, lut);
                     s.desc[D_EXACT] = 0;
                 }
                 ++n_guard;
-                __syncthreads();
+                bsync<NT>();
             }
             if (s.desc[D_STOP]) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
             const int kind = s.desc[D_KIND], part = s.desc[D_PART], oldp = s.desc[D_OLD], newp = s.desc[D_NEW];
@@ -468,26 +570,20 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
             }
             ++n_done;
             cursor += 3 + (kind < 2 ? 1 : 0);
-            int sg_new = 0;
-            if (kind == APS_EV_FLIP) { sg_new = s.sigma[part]; S += 2 * sg_new; }
+            int sg_old = s.sigma[part];
+            if (kind == APS_EV_FLIP) { S += 2 * sg_old; sg_old = -sg_old; }   // sigma[] already holds the new sign
             t = tnew;
             if (endflag) { status = APS_RUN_DONE; break; }
             if (ncross > 0) {
                 // rows get the field computed BEFORE this event (CLASS.py:512,525) and the state after it
                 if ((B.record & APS_REC_MLOCAL) && B.obs_m_local) {
-                    __syncthreads();
-                    if (tid == 0) {  // undo
-                        if (kind == APS_EV_FLIP) pk_add(s.pk, L, pad, oldp, sg_new == 1 ? 255 : -255);
-                        else { int d = s.sigma[part] == 1 ? 1 : 256; pk_add(s.pk, L, pad, newp, -d); pk_add(s.pk, L, pad, oldp, d); }
-                    }
-                    __syncthreads();
+                    bsync<NT>();
+                    if (tid == 0) lattice_delta(s, L, pad, kind, oldp, newp, sg_old, -1, bcode, lut);   // undo
+                    bsync<NT>();
                     write_field(obs_idx, ncross);   // m_glob still holds the pre-event value
-                    __syncthreads();
-                    if (tid == 0) {  // redo
-                        if (kind == APS_EV_FLIP) pk_add(s.pk, L, pad, oldp, sg_new == 1 ? -255 : 255);
-                        else { int d = s.sigma[part] == 1 ? 1 : 256; pk_add(s.pk, L, pad, newp, d); pk_add(s.pk, L, pad, oldp, -d); }
-                    }
-                    __syncthreads();
+                    bsync<NT>();
+                    if (tid == 0) lattice_delta(s, L, pad, kind, oldp, newp, sg_old, +1, bcode, lut);   // redo
+                    bsync<NT>();
                 }
                 write_rows(obs_idx, ncross);
                 obs_idx += ncross;
@@ -495,8 +591,7 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
             }
             if (obs_idx >= M) { status = APS_RUN_DONE; break; }
 
-            // ---- B: refresh the rates the event can have changed; prefetch the next variates ----
-            if (tid == NT - 1) fetch_draws(n_done, cursor);
+            // ---- B: refresh the rates the event can have changed ----
             int wlo, whi;
             if (global_m) {
                 if (kind == APS_EV_FLIP) { m_glob = APS_DIV((double)S, (double)n); wlo = 0; whi = L - 1; }
@@ -507,9 +602,9 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
             }
             for (int i = tid; i < n; i += NT) {
                 int p = s.pos[i];
-                if (p >= wlo && p <= whi) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, p, s.sigma[i]);
+                if (p >= wlo && p <= whi) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, p, s.sigma[i], lut, b2);
             }
-            __syncthreads();  // BAR3
+            bsync<NT>();  // BAR3
         }
     }
 
@@ -522,7 +617,7 @@ __global__ void __launch_bounds__(NT) k1_kernel(const __grid_constant__ K1Args A
         if (B.n_guard) B.n_guard[rep] = n_guard;
         if (B.draws_used) B.draws_used[rep] = PHILOX ? 0 : cursor;
     }
-    __syncthreads();
+    bsync<NT>();
     if (B.pos_end) for (int i = tid; i < n; i += NT) B.pos_end[(size_t)rep * n_max + i] = (int32_t)s.pos[i];
     if (B.sigma_end) for (int i = tid; i < n; i += NT) B.sigma_end[(size_t)rep * n_max + i] = s.sigma[i];
 }

@@ -144,9 +144,10 @@ int64_t aps_launch_count(void);
 int64_t aps_replica_smem_bytes(const aps_params* p, int32_t n_max);
 
 /* Test / tuning hooks: widen the selection guard band (forces the exact serial slow path) and
- * override the K1 block size (64, 128, 256; 0 = heuristic). Not needed in production. */
+ * override the K1 block size (32, 64, 128, 256; 0 = heuristic). Not needed in production. */
 void aps_debug_set_guard_scale(double scale);
 void aps_debug_set_k1_threads(int threads);
+void aps_debug_set_use_lut(int on); /* 0: evaluate filter taps arithmetically instead of by table */
 
 #ifdef __cplusplus
 }

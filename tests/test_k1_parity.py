@@ -25,15 +25,18 @@ def run_gpu(lib, params, hr, philox=False):
     return hr
 
 
-@pytest.mark.parametrize("threads", [128, 64, 256])
+@pytest.mark.parametrize("threads,use_lut", [(0, 1), (32, 1), (64, 0), (128, 1), (256, 0), (32, 0)])
 @pytest.mark.parametrize("name", case_names())
-def test_replay_matches_reference_and_oracle(lib, name, threads):
+def test_replay_matches_reference_and_oracle(lib, name, threads, use_lut):
+    """Every block-size variant and both filter-tap paths (product table / arithmetic)."""
     c = load_case(name)
     lib.aps_debug_set_k1_threads(threads)
+    lib.aps_debug_set_use_lut(use_lut)
     try:
         g = run_gpu(lib, params_from_case(c), hostrun_from_case(c))
     finally:
         lib.aps_debug_set_k1_threads(0)
+        lib.aps_debug_set_use_lut(1)
     assert_matches_reference(c, g)
     o = run_oracle(params_from_case(c), hostrun_from_case(c))
     assert_same_outputs(g, o)
@@ -94,7 +97,10 @@ def test_batched_replicas_with_ragged_sizes(lib):
         for r in range(R):
             pos0[r, :ns[r]] = c["pos0"][:ns[r]]; sg0[r, :ns[r]] = c["sigma0"][:ns[r]]
         betas = np.linspace(0.0, 3.0, R); betas[0] = m["ps"]["beta"]
-        draws = np.tile(c["draws"], R); off = np.arange(R + 1) * len(c["draws"])
+        # replica 0 replays the recorded log; the others follow different trajectories, so their log
+        # must be valid in every role: values in [0,1) serve as uniforms and as exponential variates
+        nd = len(c["draws"])
+        draws = np.concatenate([c["draws"]] + [rng.random(nd) for _ in range(R - 1)]); off = np.arange(R + 1) * nd
         mk = lambda: HostRun(m["L"], nmax, len(c["times_obs"]), ns, pos0, sg0, betas, c["times_obs"], c["weights"],
                              draws=draws, draw_off=off)
         g = run_gpu(lib, params_from_case(c), mk())
@@ -117,6 +123,23 @@ def test_philox_mode_matches_oracle(lib):
         assert_same_outputs(g, o)
         assert (g.status == capi.APS_RUN_DONE).all() and (g.n_events > 0).all()
         assert len(set(g.n_events.tolist())) > 1   # different seeds / betas -> different runs
+
+
+def test_over_capacity_initial_state_still_matches_oracle(lib):
+    """The reference accepts initial states with more than K particles on a site; the product-table
+    path cannot index them, so such a replica must take the arithmetic path and still agree."""
+    c = load_case("k1_dense")
+    m = c["meta"]
+    n = m["n"]
+    pos0 = c["pos0"].copy(); pos0[:6] = pos0[6]          # seven particles on one site, K = 1
+    rng = np.random.default_rng(9)
+    draws = rng.random(4000)
+    mk = lambda: HostRun(m["L"], n, len(c["times_obs"]), [n], pos0, c["sigma0"], [1.3], c["times_obs"], c["weights"],
+                         draws=draws, draw_off=[0, len(draws)], trace_cap=1200)
+    g = run_gpu(lib, params_from_case(c), mk())
+    o = run_oracle(params_from_case(c), mk())
+    assert_same_outputs(g, o)
+    assert g.n_events[0] > 50
 
 
 def test_empty_replica_reports_the_reference_failure(lib):
