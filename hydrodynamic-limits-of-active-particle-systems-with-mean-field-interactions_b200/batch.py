@@ -32,6 +32,7 @@ _FIELDS = {
     "pos_end": "int32",
     "sigma_end": "int8",
     "trace": "int32",
+    "m_field_in": "float64",
 }
 
 
@@ -55,12 +56,13 @@ def make_params(L, K, radius, D, lam, T, flags=0) -> ApsParams:
     return ApsParams(int(L), int(K), int(radius), int(flags), float(D), float(lam), float(T))
 
 
-def make_batch(n_replicas, n_max, M, record=0, max_events=0, trace_cap=0, **arrays):
+def make_batch(n_replicas, n_max, M, record=0, max_events=0, trace_cap=0, spec_from=-1, **arrays):
     """Returns (ApsBatch, keepalive list).  uint64 seeds may be passed as int64 torch tensors
     (torch has limited uint64 support); the bit pattern is what matters."""
     b = ApsBatch()
     b.n_replicas, b.n_max, b.M = int(n_replicas), int(n_max), int(M)
     b.record, b.max_events, b.trace_cap = int(record), int(max_events), int(trace_cap)
+    b.spec_from = int(spec_from)
     keep = []
     for name, arr in arrays.items():
         if name not in _FIELDS:

@@ -42,6 +42,7 @@ class ApsBatch(C.Structure):
         ("record", C.c_uint32),
         ("max_events", C.c_int64),
         ("trace_cap", C.c_int64),
+        ("spec_from", C.c_int64),
         ("times_obs", C.c_void_p),
         ("weights", C.c_void_p),
         ("beta", C.c_void_p),
@@ -68,7 +69,34 @@ class ApsBatch(C.Structure):
         ("pos_end", C.c_void_p),
         ("sigma_end", C.c_void_p),
         ("trace", C.c_void_p),
+        ("m_field_in", C.c_void_p),
     ]
+
+
+class ApsExpandArgs(C.Structure):
+    _fields_ = [("n_replicas", C.c_int32), ("M", C.c_int32), ("L", C.c_int32), ("reserved", C.c_int32),
+                ("dx", C.c_double), ("n", C.c_void_p), ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p),
+                ("obs_cm", C.c_void_p), ("rho_p", C.c_void_p), ("rho_m", C.c_void_p), ("total", C.c_void_p),
+                ("var", C.c_void_p)]
+
+
+APS_RED_V_EFF, APS_RED_D_EFF, APS_RED_M_MEAN, APS_RED_RHO_EFF, APS_RED_BLOCK = 0, 1, 2, 3, 4
+APS_RED_START, APS_RED_END, APS_RED_NOBS, APS_RED_N = 5, 6, 7, 8
+
+
+class ApsReduceArgs(C.Structure):
+    _fields_ = [("n_replicas", C.c_int32), ("M", C.c_int32), ("L", C.c_int32), ("n_max", C.c_int32),
+                ("dx", C.c_double), ("boundary_xmin", C.c_double), ("max_boundary_fraction", C.c_double),
+                ("min_window_fraction", C.c_double), ("window_fraction", C.c_double),
+                ("times_obs", C.c_void_p), ("n", C.c_void_p), ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p),
+                ("obs_cm", C.c_void_p), ("obs_pos", C.c_void_p), ("obs_sigma_sum", C.c_void_p),
+                ("out", C.c_void_p), ("v_eff", C.c_void_p)]
+
+
+class ApsProfileArgs(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("reps_per_point", C.c_int32), ("M", C.c_int32), ("L", C.c_int32),
+                ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("dx", C.c_double), ("n", C.c_void_p),
+                ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p), ("obs_cm", C.c_void_p), ("prof", C.c_void_p)]
 
 
 # every symbol include/aps.h declares: name -> (restype, argtypes)
@@ -84,6 +112,10 @@ SYMBOLS = {
     "aps_run_philox_host": (C.c_int, [_P(ApsParams), _P(ApsBatch)]),
     "aps_launch_count": (C.c_int64, []),
     "aps_replica_smem_bytes": (C.c_int64, [_P(ApsParams), C.c_int32]),
+    "aps_m_field_host": (C.c_int, [_P(ApsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "aps_expand_obs_device": (C.c_int, [_P(ApsExpandArgs), C.c_void_p]),
+    "aps_reduce_runs_device": (C.c_int, [_P(ApsReduceArgs), C.c_void_p]),
+    "aps_profile_sums_device": (C.c_int, [_P(ApsProfileArgs), C.c_void_p]),
     "aps_debug_set_guard_scale": (None, [C.c_double]),
     "aps_debug_set_k1_threads": (None, [C.c_int]),
     "aps_debug_set_use_lut": (None, [C.c_int]),

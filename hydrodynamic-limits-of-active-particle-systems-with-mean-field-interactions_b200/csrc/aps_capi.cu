@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "aps_k1.cuh"
+#include "aps_obs.cuh"
 
 namespace {
 
@@ -225,6 +226,69 @@ int aps_run_replay_device(const aps_params* p, const aps_batch* b, void* stream)
 int aps_run_philox_device(const aps_params* p, const aps_batch* b, void* stream) { return run_device(p, b, stream, true); }
 int aps_run_replay_host(const aps_params* p, const aps_batch* b) { return run_host(p, b, false); }
 int aps_run_philox_host(const aps_params* p, const aps_batch* b) { return run_host(p, b, true); }
+
+int aps_m_field_host(const aps_params* p, const double* weights, const int32_t* cp, const int32_t* cm, double* out) {
+    if (!p || !cp || !cm || !out || p->L < 1 || p->L > 65535 || (p->radius >= 0 && !weights))
+        return fail(APS_ERR_INVALID, "aps_m_field_host: bad argument");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    const int pad = p->radius > 0 ? p->radius : 0;
+    const size_t L = (size_t)p->L, smem = (size_t)(pad + 1) * 8 + (L + 2 * (size_t)pad) * 2 + 16;
+    if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "lattice + halo do not fit in shared memory");
+    Stager s;
+    const void *dw = nullptr, *dcp = nullptr, *dcm = nullptr; void* dout = nullptr;
+    TRY(s.in(weights, p->radius >= 0 ? (size_t)(2 * p->radius + 1) * 8 : 0, &dw));
+    TRY(s.in(cp, L * 4, &dcp));
+    TRY(s.in(cm, L * 4, &dcm));
+    TRY(s.out(out, L * 8, &dout, false));
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::field_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aps::field_kernel<<<1, 256, smem>>>(*p, (const double*)dw, (const int32_t*)dcp, (const int32_t*)dcm, (double*)dout);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return s.finish();
+}
+
+int aps_expand_obs_device(const aps_expand_args* a, void* stream) {
+    if (!a || a->L < 1 || a->M < 1 || !a->n || !a->n_obs || !a->obs_cp || !a->obs_cm)
+        return fail(APS_ERR_INVALID, "aps_expand_obs: missing argument");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (a->n_replicas == 0) return APS_OK;
+    size_t smem = a->var ? (size_t)a->L * 8 : 0;
+    if (smem > 200 * 1024) return fail(APS_ERR_CAPACITY, "L too large for the variance pass");
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(a->M, a->n_replicas);
+    aps::expand_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(*a);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+int aps_reduce_runs_device(const aps_reduce_args* a, void* stream) {
+    if (!a || a->L < 1 || a->M < 1 || !a->n || !a->n_obs || !a->obs_cp || !a->obs_cm || !a->obs_sigma_sum || !a->out ||
+        !a->times_obs)
+        return fail(APS_ERR_INVALID, "aps_reduce_runs: missing argument");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (a->n_replicas == 0) return APS_OK;
+    size_t smem = ((size_t)3 * a->M + 32) * 8;
+    if (smem > 200 * 1024) return fail(APS_ERR_CAPACITY, "too many observation rows for the reducer");
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aps::reduce_kernel<<<a->n_replicas, 128, smem, (cudaStream_t)stream>>>(*a);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+int aps_profile_sums_device(const aps_profile_args* a, void* stream) {
+    if (!a || a->L < 1 || a->M < 1 || !a->n || !a->n_obs || !a->obs_cp || !a->obs_cm || !a->prof || a->row_hi <= a->row_lo ||
+        a->row_lo < 0 || a->row_hi > a->M || a->reps_per_point < 1)
+        return fail(APS_ERR_INVALID, "aps_profile_sums: bad argument");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (a->n_points == 0) return APS_OK;
+    dim3 grid((a->L + 127) / 128, a->n_points);
+    aps::profile_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
 
 // Test / tuning hooks (declared in include/aps.h).
 void aps_debug_set_guard_scale(double s) { g_guard_scale = s; }

@@ -80,6 +80,7 @@ struct Smem {
     double* rates; double* w; double* node_val; double* wtot; double* misc;
     int32_t* node_a; int32_t* node_b; int32_t* node_kind; int32_t* desc;
     uint16_t* pk; uint16_t* code; uint16_t* pos; int8_t* sigma;
+    const double* m_in;   // optional injected field (global memory), see aps_batch.m_field_in
 };
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int pad, int max_nodes, int nwarps,
@@ -214,7 +215,7 @@ __device__ __forceinline__ double particle_rate(const Smem& s, const aps_params&
                                                 double m_global, int p, int sg, bool lut, int b2) {
     double rl, rr, ra;
     hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, rl, rr, ra);
-    double m = (P.radius < 0) ? m_global : site_m(s, P, pad, lut, b2, p);
+    double m = s.m_in ? s.m_in[p] : ((P.radius < 0) ? m_global : site_m(s, P, pad, lut, b2, p));
     double arg = APS_MUL(APS_MUL(-beta, (double)sg), m);
     double cv = aps_exp(arg);
     return APS_ADD(APS_ADD(APS_ADD(rl, rr), ra), cv);
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
     const int n = B.n[rep];
     const double beta = B.beta[rep], T = P.T;
     Smem s = carve(smem_raw, L, n_max, pad, A.max_nodes, NW, A.use_lut, P.K, r);
+    s.m_in = B.m_field_in ? B.m_field_in + (size_t)rep * (size_t)L : nullptr;
 
     // ---------------- prologue: stage the replica into shared memory ----------------
     {
@@ -460,6 +462,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
                 }
                 const int64_t left = draws_len - cursor;
                 avail = left >= 4 ? 4 : (int)(left < 0 ? 0 : left);
+                if (B.spec_from >= 0 && cursor >= B.spec_from && avail > 3) avail = 3;   // no direction variate there
                 const int o = (int)(cursor - rbase);
                 e = s.ring[o]; uc = s.ring[o + 1]; ue = s.ring[o + 2]; ud = s.ring[o + 3];
             }
@@ -620,6 +623,35 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
     bsync<NT>();
     if (B.pos_end) for (int i = tid; i < n; i += NT) B.pos_end[(size_t)rep * n_max + i] = (int32_t)s.pos[i];
     if (B.sigma_end) for (int i = tid; i < n; i += NT) B.sigma_end[(size_t)rep * n_max + i] = s.sigma[i];
+}
+
+// compute_local_m_field for one lattice (API parity entry; one CTA).
+__global__ void field_kernel(aps_params P, const double* __restrict__ weights, const int32_t* __restrict__ cp,
+                             const int32_t* __restrict__ cm, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char fk_raw[];
+    const int L = P.L, r = P.radius, pad = r > 0 ? r : 0;
+    double* w = reinterpret_cast<double*>(fk_raw);
+    uint16_t* pk = reinterpret_cast<uint16_t*>(w + pad + 1);
+    for (int i = threadIdx.x; i <= pad && r >= 0; i += blockDim.x) w[i] = weights[i];
+    for (int i = threadIdx.x; i < L + 2 * pad; i += blockDim.x) {
+        long long q = (long long)i - pad, per = 2LL * L;
+        long long m = q % per; if (m < 0) m += per; if (m >= L) m = per - 1 - m;
+        pk[i] = (uint16_t)((cp[m] & 0xff) | ((cm[m] & 0xff) << 8));
+    }
+    __syncthreads();
+    if (r < 0) {
+        __shared__ long long tot[2];
+        if (threadIdx.x == 0) {
+            long long s = 0, t = 0;
+            for (int l = 0; l < L; ++l) { s += cp[l] - cm[l]; t += cp[l] + cm[l]; }
+            tot[0] = s; tot[1] = t;
+        }
+        __syncthreads();
+        const double mg = APS_DIV((double)tot[0], (double)tot[1]);
+        for (int l = threadIdx.x; l < L; l += blockDim.x) out[l] = mg;
+        return;
+    }
+    for (int l = threadIdx.x; l < L; l += blockDim.x) out[l] = local_m(pk, w, pad, r, l);
 }
 
 }  // namespace aps

@@ -1,0 +1,287 @@
+// aps_obs.cuh — K4: on-device observables.  Nothing per-event or per-site crosses PCIe for an
+// ensemble: the observation rows K1 wrote (int8 counts, int32 positions) are reduced here.
+//
+//   expand_kernel    counts -> rho_plus / rho_minus / total density rows (+ np.var of total),
+//                    ParticleSystem.empirical_densities_from_particles (CLASS.py:198-214) and
+//                    run()'s per-row bookkeeping (:489-507, :518-535)
+//   reduce_kernel    the sweep drivers' per-run reducers
+//                    compute_v_eff_and_window      sweep_beta.py:123-162
+//                    compute_rho_eff               sweep_beta.py:165-194
+//                    compute_blocking_probability  sweep_beta.py:197-229
+//                    compute_mean_magnetizatoin    sweep_beta.py:316-319
+//                    compute_D_eff_active          sweep_beta.py:500-525
+//   profile_kernel   ensemble sums (over the replicas of one grid point and a row window) of the
+//                    density / magnetisation profiles — the payload of the NCCL allreduce.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/aps.h"
+#include "../../include/aps_math.h"
+
+namespace aps {
+
+// ---- block reduction helpers (sum of doubles / ints over a CTA, result broadcast) ----------
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    T tot = 0;
+    for (int w = 0; w < nw; ++w) tot += scratch[w];
+    return tot;
+}
+
+// numpy pairwise sum of a shared-memory array, executed by one thread (used for np.var parity;
+// rows are short and this runs M times per replica, far off the hot path)
+__device__ inline double pairwise_serial(const double* a, int n) {
+    if (n < 8) { double r = 0.0; for (int i = 0; i < n; ++i) r = APS_ADD(r, a[i]); return r; }
+    if (n <= 128) {
+        double r[8];
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) for (int k = 0; k < 8; ++k) r[k] = APS_ADD(r[k], a[i + k]);
+        double res = APS_ADD(APS_ADD(APS_ADD(r[0], r[1]), APS_ADD(r[2], r[3])), APS_ADD(APS_ADD(r[4], r[5]), APS_ADD(r[6], r[7])));
+        for (; i < n; ++i) res = APS_ADD(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2; n2 -= n2 % 8;
+    return APS_ADD(pairwise_serial(a, n2), pairwise_serial(a + n2, n - n2));
+}
+
+// One CTA per (replica, row).  rho = counts / (max(1,n)*dx)  (CLASS.py:208-213), total = rho_p+rho_m,
+// var = np.var(total) with numpy's evaluation order (mean by pairwise sum, then pairwise sum of squares).
+__global__ void expand_kernel(aps_expand_args a) {
+    extern __shared__ double sh[];   // [L] when var is requested
+    const int rep = blockIdx.y, m = blockIdx.x;
+    if (m >= a.n_obs[rep]) return;
+    const int L = a.L;
+    const size_t row = (size_t)rep * a.M + m;
+    const int8_t* cp = a.obs_cp + row * L;
+    const int8_t* cm = a.obs_cm + row * L;
+    const int n = a.n[rep];
+    const double denom = APS_MUL((double)(n > 1 ? n : 1), a.dx);
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+        double rp = APS_DIV((double)cp[l], denom), rm = APS_DIV((double)cm[l], denom);
+        double tot = APS_ADD(rp, rm);
+        if (a.rho_p) a.rho_p[row * L + l] = rp;
+        if (a.rho_m) a.rho_m[row * L + l] = rm;
+        if (a.total) a.total[row * L + l] = tot;
+        if (a.var) sh[l] = tot;
+    }
+    if (a.var) {
+        __syncthreads();
+        __shared__ double mean_s;
+        if (threadIdx.x == 0) mean_s = APS_DIV(pairwise_serial(sh, L), (double)L);
+        __syncthreads();
+        const double mean = mean_s;
+        for (int l = threadIdx.x; l < L; l += blockDim.x) { double x = APS_SUB(sh[l], mean); sh[l] = APS_MUL(x, x); }
+        __syncthreads();
+        if (threadIdx.x == 0) a.var[row] = APS_DIV(pairwise_serial(sh, L), (double)L);
+    }
+}
+
+// x_grid = np.linspace(0, 1, L): arange(L) * (1/(L-1)), last point forced to 1.0
+__device__ __forceinline__ double xgrid(int l, int L, double step) { return (l == L - 1 && L > 1) ? 1.0 : APS_MUL((double)l, step); }
+
+// One CTA per replica.  Shared: per-row scalars [M] x 4.
+__global__ void reduce_kernel(aps_reduce_args a) {
+    extern __shared__ double sh[];
+    const int rep = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const int M = a.M, L = a.L, n = a.n[rep], nobs = a.n_obs[rep];
+    double* mean_x = sh;            // [M]
+    double* frac_b = sh + M;        // [M]
+    double* aux = sh + 2 * M;       // [M] scratch (S_k of the MSD fit)
+    double* scr = sh + 3 * M;       // [32] reduction scratch
+    double* out = a.out + (size_t)rep * APS_RED_N;
+    const double step = L > 1 ? APS_DIV(1.0, (double)(L - 1)) : 0.0;
+    const double dxg = L > 1 ? APS_SUB(xgrid(1, L, step), xgrid(0, L, step)) : 0.0;
+    const double denom = APS_MUL((double)(n > 1 ? n : 1), a.dx);
+
+    // ---- per-row sums over the lattice (rows never reached are all-zero in the reference) ----
+    for (int m = 0; m < M; ++m) {
+        double sx = 0.0; double st = 0.0, sb = 0.0;
+        if (m < nobs) {
+            const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
+            const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
+            for (int l = tid; l < L; l += NT) {
+                int c = (int)cp[l] + (int)cm[l];
+                if (c) {
+                    double d = APS_ADD(APS_DIV((double)cp[l], denom), APS_DIV((double)cm[l], denom));
+                    double x = xgrid(l, L, step);
+                    st += d; sx += d * x;
+                    if (x >= a.boundary_xmin) sb += d;
+                }
+            }
+        }
+        st = block_sum(st, scr); sx = block_sum(sx, scr); sb = block_sum(sb, scr);
+        if (tid == 0) {
+            double Nt = st * dxg;
+            frac_b[m] = (sb * dxg) / (Nt + 1e-12);
+            mean_x[m] = sx / (st + 1e-12);
+        }
+    }
+    __syncthreads();
+
+    // ---- window selection, verbatim quirks of compute_v_eff_and_window (:139-154) ----
+    int start_idx = (int)(0.65 * (double)M), end_idx = M;
+    {
+        int unsafe = 0;
+        for (int m = 0; m < M; ++m) unsafe += (frac_b[m] >= a.max_boundary_fraction);
+        if (unsafe > 0 && unsafe > start_idx) {   // `safe[start_idx:]` non-empty -> `~idx` is always truthy
+            end_idx = start_idx;
+            int min_len = (int)(a.min_window_fraction * (double)M);
+            if (min_len < 3) min_len = 3;
+            if (end_idx - start_idx < min_len) end_idx = (start_idx + min_len < M) ? start_idx + min_len : M;
+        }
+    }
+    // ---- v_eff = np.gradient(mean_x, times) averaged over the window ----
+    const double* t = a.times_obs;
+    bool uniform = true;
+    for (int m = 1; m + 1 < M; ++m) if ((t[m + 1] - t[m]) != (t[1] - t[0])) uniform = false;
+    double mean_v = 0.0;
+    {
+        double acc = 0.0; int cnt = 0;
+        for (int m = start_idx + tid; m < end_idx; m += NT) {
+            double g;
+            if (M < 2) g = 0.0;
+            else if (m == 0) g = (mean_x[1] - mean_x[0]) / (t[1] - t[0]);
+            else if (m == M - 1) g = (mean_x[M - 1] - mean_x[M - 2]) / (t[M - 1] - t[M - 2]);
+            else if (uniform) g = (mean_x[m + 1] - mean_x[m - 1]) / (2.0 * (t[1] - t[0]));
+            else {
+                double hd = t[m + 1] - t[m], hs = t[m] - t[m - 1];
+                double ca = -hd / (hs * (hd + hs)), cb = (hd - hs) / (hd * hs), cc = hs / (hd * (hd + hs));
+                g = ca * mean_x[m - 1] + cb * mean_x[m] + cc * mean_x[m + 1];
+            }
+            if (a.v_eff) a.v_eff[(size_t)rep * M + m] = g;
+            acc += g; ++cnt;
+        }
+        acc = block_sum(acc, scr);
+        int w = end_idx - start_idx;
+        mean_v = w > 0 ? acc / (double)w : 0.0;
+    }
+    // ---- mean magnetisation over the window ----
+    double m_mean;
+    {
+        double acc = 0.0;
+        for (int m = start_idx + tid; m < end_idx; m += NT)
+            acc += (m < nobs) ? (double)a.obs_sigma_sum[(size_t)rep * M + m] / (double)n : 0.0;
+        acc = block_sum(acc, scr);
+        int w = end_idx - start_idx;
+        m_mean = w > 0 ? acc / (double)w : 0.0;
+    }
+    // ---- rho_eff (front density) and blocking probability ----
+    double rho_eff, block;
+    {
+        double rsum = 0.0; int rcnt = 0;
+        double attempts = 0.0, blocked = 0.0;
+        for (int m = start_idx; m < end_idx; ++m) {
+            int jmax = -1;
+            double att = 0.0, blk = 0.0;
+            if (m < nobs) {
+                const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
+                const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
+                for (int l = tid; l < L; l += NT) {
+                    int c = (int)cp[l] + (int)cm[l];
+                    if (c > 0 && l > jmax) jmax = l;
+                    if (cp[l] > 0 && l + 1 < L) {
+                        double rp = APS_DIV((double)cp[l], denom);
+                        att += rp;
+                        double tn = APS_ADD(APS_DIV((double)cp[l + 1], denom), APS_DIV((double)cm[l + 1], denom));
+                        if (tn >= 1.0) blk += rp;
+                    }
+                }
+            }
+            for (int o = 16; o > 0; o >>= 1) { int v = __shfl_xor_sync(0xffffffffu, jmax, o); jmax = v > jmax ? v : jmax; }
+            __syncthreads();
+            if ((tid & 31) == 0) scr[tid >> 5] = (double)jmax;
+            __syncthreads();
+            for (int w = 0; w < (NT + 31) / 32; ++w) { int v = (int)scr[w]; jmax = v > jmax ? v : jmax; }
+            attempts += block_sum(att, scr); blocked += block_sum(blk, scr);
+            if (jmax >= 0) {
+                const double xmax = xgrid(jmax, L, step);
+                const double lo = xmax - a.window_fraction;
+                const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
+                const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
+                double s2 = 0.0; int inmask = 0;
+                for (int l = tid; l <= jmax; l += NT) {
+                    double x = xgrid(l, L, step);
+                    if (x >= lo && x <= xmax) {
+                        ++inmask;
+                        s2 += APS_ADD(APS_DIV((double)cp[l], denom), APS_DIV((double)cm[l], denom));
+                    }
+                }
+                s2 = block_sum(s2, scr);
+                rsum += s2 * dxg / a.window_fraction; ++rcnt;
+            }
+        }
+        rho_eff = rcnt > 0 ? rsum / (double)rcnt : nan("");
+        block = attempts > 0.0 ? blocked / attempts : 0.0;
+    }
+    // ---- D_eff: slope of the per-particle MSD against time (np.polyfit degree 1) ----
+    double d_eff = nan("");
+    if (a.obs_pos && end_idx - start_idx >= 3 && n >= 2 && nobs >= end_idx) {
+        const int32_t* p0 = a.obs_pos + ((size_t)rep * M + start_idx) * a.n_max;
+        for (int k = start_idx + 1; k < end_idx; ++k) {
+            const int32_t* pk = a.obs_pos + ((size_t)rep * M + k) * a.n_max;
+            double s1 = 0.0;
+            for (int i = tid; i < n; i += NT) s1 += (double)pk[i] * a.dx - (double)p0[i] * a.dx;
+            s1 = block_sum(s1, scr);
+            const double rbar = s1 / (double)n;
+            double s2 = 0.0;
+            for (int i = tid; i < n; i += NT) { double ri = ((double)pk[i] * a.dx - (double)p0[i] * a.dx) - rbar; s2 += ri * ri; }
+            s2 = block_sum(s2, scr);
+            if (tid == 0) aux[k] = s2 / (double)(n - 1);
+        }
+        __syncthreads();
+        // least squares of S against (t - t0), centred for conditioning
+        const int cnt = end_idx - start_idx - 1;
+        double tb = 0.0, sb2 = 0.0;
+        for (int k = start_idx + 1; k < end_idx; ++k) { tb += t[k] - t[start_idx]; sb2 += aux[k]; }
+        tb /= cnt; sb2 /= cnt;
+        double num = 0.0, den = 0.0;
+        for (int k = start_idx + 1; k < end_idx; ++k) {
+            double dt = (t[k] - t[start_idx]) - tb;
+            num += dt * (aux[k] - sb2); den += dt * dt;
+        }
+        d_eff = num / den;
+    }
+    if (tid == 0) {
+        out[APS_RED_V_EFF] = mean_v; out[APS_RED_D_EFF] = d_eff; out[APS_RED_M_MEAN] = m_mean;
+        out[APS_RED_RHO_EFF] = rho_eff; out[APS_RED_BLOCK] = block;
+        out[APS_RED_START] = (double)start_idx; out[APS_RED_END] = (double)end_idx; out[APS_RED_NOBS] = (double)nobs;
+    }
+}
+
+// Ensemble profile sums.  Replicas are laid out grid-point-major: rep = g*reps_per_point + j.
+// For every grid point g and site l:   prof[g][q][l]   = sum_j  mean_{m in [row_lo,row_hi)} q_j(m,l)
+//                                      prof2[g][q][l]  = sum_j (mean_m q_j(m,l))^2
+// with q in {rho_plus, rho_minus}; dividing by reps_per_point (after the cross-GPU allreduce) gives the
+// ensemble mean profile and its standard error.
+__global__ void profile_kernel(aps_profile_args a) {
+    const int g = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= a.L) return;
+    const int L = a.L, M = a.M;
+    double sp = 0.0, sm = 0.0, sp2 = 0.0, sm2 = 0.0;
+    const int rows = a.row_hi - a.row_lo;
+    for (int j = 0; j < a.reps_per_point; ++j) {
+        const int rep = g * a.reps_per_point + j;
+        const int n = a.n[rep];
+        const double denom = (double)(n > 1 ? n : 1) * a.dx;
+        int cp = 0, cm = 0;
+        for (int m = a.row_lo; m < a.row_hi; ++m) {
+            if (m >= a.n_obs[rep]) break;
+            cp += a.obs_cp[((size_t)rep * M + m) * L + l];
+            cm += a.obs_cm[((size_t)rep * M + m) * L + l];
+        }
+        const double mp = (double)cp / denom / (double)rows, mm = (double)cm / denom / (double)rows;
+        sp += mp; sm += mm; sp2 += mp * mp; sm2 += mm * mm;
+    }
+    double* o = a.prof + ((size_t)g * 4) * L;
+    o[l] = sp; o[L + l] = sm; o[2 * L + l] = sp2; o[3 * L + l] = sm2;
+}
+
+}  // namespace aps

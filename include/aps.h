@@ -84,6 +84,11 @@ typedef struct aps_batch {
     uint32_t record;            /* APS_REC_* mask                                                 */
     int64_t max_events;         /* 0 = unlimited; otherwise stop each replica after this many     */
     int64_t trace_cap;          /* events per replica the trace can hold (0 = no trace)           */
+    int64_t spec_from;          /* replay: draws at offsets >= spec_from are SPECULATIVE triples  */
+                                /* (e,u,u) with no direction variate behind them: a diffusive hop */
+                                /* starting there stops the replica (APS_RUN_DRAWS_EXHAUSTED) so  */
+                                /* the host can draw the 4th variate in rng order. -1 = log is    */
+                                /* exact (default for recorded logs).                             */
 
     const double* times_obs;    /* [M]  exactly np.arange(0, T, obs_dt)                           */
     const double* weights;      /* [2*radius+1] normalised Gaussian taps (scipy _gaussian_kernel1d)*/
@@ -120,6 +125,9 @@ typedef struct aps_batch {
     int32_t* pos_end;           /* [n_replicas][n_max] optional final state                       */
     int8_t* sigma_end;          /* [n_replicas][n_max]                                            */
     int32_t* trace;             /* [n_replicas][trace_cap][3] = (particle, kind, new_site)        */
+    /* optional: use this magnetisation field instead of computing it (step_gillespie takes m_field
+     * as an argument, CLASS.py:254,261); only meaningful with max_events = 1 */
+    const double* m_field_in;   /* [n_replicas][L]                                                */
 } aps_batch;
 
 int aps_abi_version(void);
@@ -142,6 +150,70 @@ int aps_run_philox_host(const aps_params* p, const aps_batch* b);
 int64_t aps_launch_count(void);
 /* Shared-memory bytes and threads the K1 plan uses for (L, n_max, radius); <0 if it cannot fit. */
 int64_t aps_replica_smem_bytes(const aps_params* p, int32_t n_max);
+
+/* compute_local_m_field (CLASS.py:216-246) for one lattice; host buffers: counts int32[L] -> out double[L] */
+int aps_m_field_host(const aps_params* p, const double* weights, const int32_t* counts_p, const int32_t* counts_m,
+                     double* out);
+
+/* ---- K4: on-device observables ------------------------------------------------------------ */
+/* counts -> density rows, replaces empirical_densities_from_particles (CLASS.py:198-214) and the
+ * per-row bookkeeping of run() (:489-507,:518-535).  Rows >= n_obs[rep] are left untouched. */
+typedef struct aps_expand_args {
+    int32_t n_replicas, M, L, reserved;
+    double dx;                  /* ParticleSystem.dx = xlim / L                                   */
+    const int32_t* n;           /* [n_replicas]                                                   */
+    const int32_t* n_obs;       /* [n_replicas]                                                   */
+    const int8_t* obs_cp;       /* [n_replicas][M][L]                                             */
+    const int8_t* obs_cm;
+    double* rho_p;              /* [n_replicas][M][L] optional                                    */
+    double* rho_m;              /* optional                                                       */
+    double* total;              /* optional                                                       */
+    double* var;                /* [n_replicas][M] optional: np.var(total row), numpy's order     */
+} aps_expand_args;
+int aps_expand_obs_device(const aps_expand_args* a, void* stream);
+
+/* per-run reducers of the sweep drivers (sweep_beta.py:123-229,316-319,500-525) */
+#define APS_RED_V_EFF 0     /* mean of np.gradient(mean_x, times) over the window                 */
+#define APS_RED_D_EFF 1     /* slope of the per-particle MSD (NaN if obs_pos is NULL)             */
+#define APS_RED_M_MEAN 2    /* mean of m_global over the window                                   */
+#define APS_RED_RHO_EFF 3   /* front density                                                      */
+#define APS_RED_BLOCK 4     /* blocking probability                                               */
+#define APS_RED_START 5     /* window [start, end)                                                */
+#define APS_RED_END 6
+#define APS_RED_NOBS 7
+#define APS_RED_N 8
+typedef struct aps_reduce_args {
+    int32_t n_replicas, M, L, n_max;
+    double dx;
+    double boundary_xmin;           /* 0.99  (sweep_beta.py:85)                                   */
+    double max_boundary_fraction;   /* 0.06                                                       */
+    double min_window_fraction;     /* 0.10                                                       */
+    double window_fraction;         /* 0.05  (compute_rho_eff default)                            */
+    const double* times_obs;        /* [M]                                                        */
+    const int32_t* n;
+    const int32_t* n_obs;
+    const int8_t* obs_cp;
+    const int8_t* obs_cm;
+    const int32_t* obs_pos;         /* optional                                                   */
+    const int32_t* obs_sigma_sum;
+    double* out;                    /* [n_replicas][APS_RED_N]                                    */
+    double* v_eff;                  /* [n_replicas][M] optional (window rows only)                */
+} aps_reduce_args;
+int aps_reduce_runs_device(const aps_reduce_args* a, void* stream);
+
+/* ensemble profile sums per grid point (replicas grid-point-major); prof is [n_points][4][L]:
+ * sum of time-averaged rho_plus, rho_minus over the point's replicas, and the sums of their squares */
+typedef struct aps_profile_args {
+    int32_t n_points, reps_per_point, M, L;
+    int32_t row_lo, row_hi;
+    double dx;
+    const int32_t* n;
+    const int32_t* n_obs;
+    const int8_t* obs_cp;
+    const int8_t* obs_cm;
+    double* prof;
+} aps_profile_args;
+int aps_profile_sums_device(const aps_profile_args* a, void* stream);
 
 /* Test / tuning hooks: widen the selection guard band (forces the exact serial slow path) and
  * override the K1 block size (32, 64, 128, 256; 0 = heuristic). Not needed in production. */

