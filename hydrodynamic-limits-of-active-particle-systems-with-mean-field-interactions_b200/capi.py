@@ -73,6 +73,14 @@ class ApsBatch(C.Structure):
     ]
 
 
+class ApsInitArgs(C.Structure):
+    _fields_ = [("n_replicas", C.c_int32), ("L", C.c_int32), ("K", C.c_int32), ("n_max", C.c_int32),
+                ("mode", C.c_int32), ("N_fixed", C.c_int32), ("n_profiles", C.c_int32), ("reserved", C.c_int32),
+                ("rho0_plus", C.c_void_p), ("rho0_minus", C.c_void_p), ("profile_of", C.c_void_p),
+                ("N_of", C.c_void_p), ("seeds", C.c_void_p), ("pos0", C.c_void_p), ("sigma0", C.c_void_p),
+                ("n", C.c_void_p)]
+
+
 class ApsExpandArgs(C.Structure):
     _fields_ = [("n_replicas", C.c_int32), ("M", C.c_int32), ("L", C.c_int32), ("reserved", C.c_int32),
                 ("dx", C.c_double), ("n", C.c_void_p), ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p),
@@ -112,6 +120,7 @@ SYMBOLS = {
     "aps_run_philox_host": (C.c_int, [_P(ApsParams), _P(ApsBatch)]),
     "aps_launch_count": (C.c_int64, []),
     "aps_replica_smem_bytes": (C.c_int64, [_P(ApsParams), C.c_int32]),
+    "aps_init_particles_device": (C.c_int, [_P(ApsInitArgs), C.c_void_p]),
     "aps_m_field_host": (C.c_int, [_P(ApsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "aps_expand_obs_device": (C.c_int, [_P(ApsExpandArgs), C.c_void_p]),
     "aps_reduce_runs_device": (C.c_int, [_P(ApsReduceArgs), C.c_void_p]),

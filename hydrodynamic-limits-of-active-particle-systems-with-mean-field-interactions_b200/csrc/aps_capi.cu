@@ -11,6 +11,7 @@
 
 #include "aps_k1.cuh"
 #include "aps_obs.cuh"
+#include "aps_init.cuh"
 
 namespace {
 
@@ -226,6 +227,22 @@ int aps_run_replay_device(const aps_params* p, const aps_batch* b, void* stream)
 int aps_run_philox_device(const aps_params* p, const aps_batch* b, void* stream) { return run_device(p, b, stream, true); }
 int aps_run_replay_host(const aps_params* p, const aps_batch* b) { return run_host(p, b, false); }
 int aps_run_philox_host(const aps_params* p, const aps_batch* b) { return run_host(p, b, true); }
+
+int aps_init_particles_device(const aps_init_args* a, void* stream) {
+    if (!a || a->L < 1 || a->L > 65535 || a->K < 1 || a->K > 63 || a->n_max < 1 || !a->seeds || !a->pos0 || !a->sigma0 || !a->n)
+        return fail(APS_ERR_INVALID, "aps_init_particles: bad argument");
+    if (a->mode == 1 && (!a->rho0_plus || !a->rho0_minus)) return fail(APS_ERR_INVALID, "poisson init needs rho0_plus/rho0_minus");
+    if (a->mode != 0 && a->mode != 1) return fail(APS_ERR_INVALID, "mode must be 0 (fixed) or 1 (poisson)");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (a->n_replicas == 0) return APS_OK;
+    size_t smem = a->mode == 1 ? (size_t)a->L * 12 : (size_t)a->L * 3 + 8;
+    if (smem > 200 * 1024) return fail(APS_ERR_CAPACITY, "L too large for the init kernel");
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    aps::init_kernel<<<a->n_replicas, 128, smem, (cudaStream_t)stream>>>(*a);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
 
 int aps_m_field_host(const aps_params* p, const double* weights, const int32_t* cp, const int32_t* cm, double* out) {
     if (!p || !cp || !cm || !out || p->L < 1 || p->L > 65535 || (p->radius >= 0 && !weights))

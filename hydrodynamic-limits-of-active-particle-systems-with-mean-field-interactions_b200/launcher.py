@@ -1,0 +1,324 @@
+"""Ensemble / sweep launcher: replaces the serial loops of the sweep drivers.
+
+Reference loops replaced (all are `for b in betas: for run in range(n_runs): ParticleSystem(...).run()`):
+  sweep_beta_ensemble / sweep_over_betas      PARTICLE_solver_BIOLOGY_EXCLUSION_sweep_beta.py:56-117, :828-1028
+  (N_part, beta) double sweep                 ..._double_sweep.py:100-152, :665-873
+  (sigma, beta) sweep                         ..._sweep_beta_2.py:1030-1075
+  sweep_betas_for_structures                  PARTICLE_solver_BIOLOGY_local_structure.py:105-193
+
+Every replica is an independent ParticleSystem (private state and rng, sweep_beta.py:83), so the
+(grid point x replica) list is flattened, block-partitioned over the ranks (one process per GPU,
+`torch.distributed`), each rank runs its shard in ONE K1 launch (native Philox mode, device-side
+initial conditions), reduces every run on the device (K4) and only then communicates:
+  * per-replica scalars (8 doubles each)            -> all_gather
+  * per-grid-point profile sums [points][4][L] f64  -> all_reduce(sum)   (NCCL over NVLink)
+There is no data-path collective inside the time stepping.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import capi
+from .capi import APS_REC_COUNTS, APS_REC_POS, APS_RED_N, ApsInitArgs
+from .engine import ReplicaBatch, _dev, _stream, gaussian_weights
+
+
+def make_exp_gradient(L, N, frac_plus, decay_length, anchor_positions=(0.25, 0.60), anchor_peak_width=0.01,
+                      anchor_peak_mass=0.03):
+    """Initial-profile helper of the drivers (sweep_beta.py:16-53): exponential '+' profile, flat '-'
+    profile with optional Gaussian bumps; returns [rho0_plus(x), rho0_minus(x), rho_plus[], rho_minus[]]."""
+    xs = np.arange(L) / float(L)
+    plus = np.exp(-xs / decay_length)
+    minus = 0.05 * np.ones_like(xs)
+    if anchor_positions is not None:
+        for a in anchor_positions:
+            minus += anchor_peak_mass * np.exp(-0.5 * ((xs - a) / anchor_peak_width) ** 2)
+    rho_plus = N * frac_plus * (plus / plus.sum())
+    rho_minus = N * (1 - frac_plus) * (minus / minus.sum())
+
+    def rho0_plus(x):
+        return float(rho_plus[int(np.clip(np.round(x * L), 0, L - 1))])
+
+    def rho0_minus(x):
+        return float(rho_minus[int(np.clip(np.round(x * L), 0, L - 1))])
+
+    return [rho0_plus, rho0_minus, rho_plus, rho_minus]
+
+
+# ---- rank plumbing ---------------------------------------------------------------------------
+def dist_info():
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        return torch.distributed.get_rank(), torch.distributed.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_items: int, rank: int, world: int):
+    """Contiguous block partition; the first (n_items % world) ranks get one extra item."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def expected_poisson_particles(rho_p, rho_m, K):
+    """mean and an upper bound of n for the K-truncated Poisson init (CLASS.py:160-189)."""
+    lam = np.asarray(rho_p) + np.asarray(rho_m)
+    mean = 0.0
+    for l in lam:
+        pk, cdf, e = math.exp(-l), 0.0, 0.0
+        for k in range(K):
+            e += k * pk
+            cdf += pk
+            pk *= l / (k + 1)
+        mean += e + K * (1.0 - cdf)
+    return mean, int(math.ceil(mean + 8.0 * math.sqrt(max(mean, 1.0)) + 16))
+
+
+@dataclass
+class EnsembleSpec:
+    """One launch group: replicas that share the model parameters (L, K, D, lambda, sigma, T, obs_dt)."""
+    ps_kwargs: dict
+    run_kwargs: dict
+    betas: np.ndarray                 # [R] beta of every replica (grid-point-major)
+    point_of: np.ndarray              # [R] grid-point index of every replica
+    seeds: np.ndarray                 # [R] uint64 Philox keys
+    profiles_plus: np.ndarray | None = None    # [n_profiles][L] ('poisson')
+    profiles_minus: np.ndarray | None = None
+    profile_of: np.ndarray | None = None       # [R]
+    N_of: np.ndarray | None = None             # [R] ('fixed' with per-point N)
+    record: int = APS_REC_COUNTS | APS_REC_POS
+
+
+@dataclass
+class EnsembleResult:
+    reducers: np.ndarray              # [R][APS_RED_N] (all ranks, original replica order)
+    n_events: np.ndarray              # [R]
+    status: np.ndarray                # [R]
+    n_particles: np.ndarray           # [R]
+    profiles: np.ndarray | None       # [points][4][L] sums over the point's replicas (all ranks)
+    reps_per_point: np.ndarray | None
+    info: dict = field(default_factory=dict)
+
+
+def _model_params(ps_kwargs):
+    L = int(ps_kwargs["L"])
+    xlim = float(ps_kwargs.get("xlim", 1.0))
+    dx = xlim / L
+    D, lam = float(ps_kwargs["rate_diffusion"]), float(ps_kwargs["rate_active"])
+    if ps_kwargs.get("scale_rates", True):
+        D, lam = D / dx ** 2, lam / dx
+    sigma = float(ps_kwargs.get("local_kernel_sigma", 0.005))
+    if sigma > 0:
+        radius, weights = gaussian_weights(sigma / dx)
+    else:
+        radius, weights = -1, np.zeros(1)
+    for key, bad in [("flip_rate_fn", lambda v: v is not None), ("periodic", bool), ("anchor_positions", lambda v: v is not None)]:
+        if bad(ps_kwargs.get(key)):
+            raise NotImplementedError(f"{key} is outside the accelerated path")
+    return dict(L=L, dx=dx, D=D, lam=lam, K=int(ps_kwargs.get("site_capacity", 1)), radius=radius, weights=weights,
+                crowding=bool(ps_kwargs.get("crowding_suppresses_rates", False)), init=ps_kwargs.get("init", "fixed"),
+                N=int(ps_kwargs.get("N", 1000)))
+
+
+class DeviceEnsemble:
+    """This rank's shard of an EnsembleSpec, resident in HBM."""
+
+    def __init__(self, spec: EnsembleSpec, lo: int, hi: int, device=None):
+        self.spec, self.lo, self.hi = spec, lo, hi
+        self.mp = mp = _model_params(spec.ps_kwargs)
+        self.dev = _dev(device)
+        self.lib = capi.load()
+        T, obs_dt = float(spec.run_kwargs.get("T", 10.0)), float(spec.run_kwargs.get("obs_dt", 0.01))
+        self.times_obs = np.arange(0.0, T, obs_dt)
+        self.T = T
+        R = hi - lo
+        self.R = R
+        sl = slice(lo, hi)
+        if mp["init"] == "poisson":
+            self.n_max = max(expected_poisson_particles(spec.profiles_plus[p], spec.profiles_minus[p], mp["K"])[1]
+                             for p in range(len(spec.profiles_plus)))
+        else:
+            self.n_max = int(spec.N_of.max()) if spec.N_of is not None else mp["N"]
+        self.n_max = max(8, (self.n_max + 7) // 8 * 8)
+        # ---- host -> device: everything the shard needs (this is the e2e H2D traffic) ----
+        up = lambda a, dt: torch.as_tensor(np.array(a, dtype=dt, order="C", copy=True)).to(self.dev, non_blocking=True)
+        self.h2d_bytes = 0
+
+        def upc(a, dt):
+            t = up(a, dt)
+            self.h2d_bytes += t.numel() * t.element_size()
+            return t
+
+        self.seeds = upc(np.asarray(spec.seeds[sl], dtype=np.uint64).view(np.int64), np.int64)
+        self.betas_h = np.asarray(spec.betas[sl], dtype=np.float64)
+        self.rho_p = upc(spec.profiles_plus, np.float64) if mp["init"] == "poisson" else None
+        self.rho_m = upc(spec.profiles_minus, np.float64) if mp["init"] == "poisson" else None
+        self.profile_of = upc(spec.profile_of[sl], np.int32) if (mp["init"] == "poisson" and spec.profile_of is not None) else None
+        self.N_of = upc(spec.N_of[sl], np.int32) if (mp["init"] == "fixed" and spec.N_of is not None) else None
+        self.pos0 = torch.zeros((R, self.n_max), dtype=torch.int32, device=self.dev)
+        self.sigma0 = torch.ones((R, self.n_max), dtype=torch.int8, device=self.dev)
+        self.n = torch.zeros((R,), dtype=torch.int32, device=self.dev)
+        self.rb = ReplicaBatch(L=mp["L"], K=mp["K"], radius=mp["radius"], weights=mp["weights"], D=mp["D"], lam=mp["lam"],
+                               T=T, times_obs=self.times_obs, betas=self.betas_h, n=self.n, pos0=self.pos0,
+                               sigma0=self.sigma0, seeds=self.seeds, record=spec.record, crowding=mp["crowding"],
+                               device=self.dev.index, dx=mp["dx"])
+        self.h2d_bytes += (self.rb.times_obs.numel() + self.rb.beta.numel() + (self.rb.weights.numel() if self.rb.weights is not None else 0)) * 8
+        self.point_local = torch.as_tensor(np.asarray(spec.point_of[sl], dtype=np.int64)).to(self.dev)
+        self.n_points = int(spec.point_of.max()) + 1 if len(spec.point_of) else 0
+
+    def init_particles(self):
+        mp = self.mp
+        a = ApsInitArgs(self.R, mp["L"], mp["K"], self.n_max, 1 if mp["init"] == "poisson" else 0, mp["N"],
+                        int(self.rho_p.shape[0]) if self.rho_p is not None else 0, 0,
+                        self.rho_p.data_ptr() if self.rho_p is not None else None,
+                        self.rho_m.data_ptr() if self.rho_m is not None else None,
+                        self.profile_of.data_ptr() if self.profile_of is not None else None,
+                        self.N_of.data_ptr() if self.N_of is not None else None,
+                        self.seeds.data_ptr(), self.pos0.data_ptr(), self.sigma0.data_ptr(), self.n.data_ptr())
+        capi.check(self.lib.aps_init_particles_device(a, _stream()), "aps_init_particles_device")
+
+    def step(self, want_profiles=True):
+        """init -> K1 -> per-run reducers (-> per-point profile sums).  All on the device, no sync."""
+        self.init_particles()
+        self.rb.run_philox()
+        self.red = self.rb.reduce()
+        self.prof = None
+        if want_profiles and self.n_points:
+            per_rep = self.rb.profile_sums(1)                       # [R][4][L]
+            self.prof = torch.zeros((self.n_points, 4, self.mp["L"]), dtype=torch.float64, device=self.dev)
+            self.prof.index_add_(0, self.point_local, per_rep)
+        return self
+
+    def pack_scalars(self):
+        """[R][APS_RED_N + 3] f64: reducers, n_events, status, n — the only per-replica D2H payload."""
+        rb = self.rb
+        return torch.cat([self.red, rb.n_events.double()[:, None], rb.status.double()[:, None],
+                          self.n.double()[:, None]], dim=1)
+
+
+def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_cls=None) -> EnsembleResult:
+    """Run every replica of `spec` across the ranks of the current process group and return the
+    gathered result on every rank.  `ensemble_cls` lets the CPU tests substitute an oracle-backed
+    shard for DeviceEnsemble to exercise the sharding / collective logic under gloo."""
+    rank, world = dist_info()
+    Rtot = len(spec.betas)
+    lo, hi = shard_bounds(Rtot, rank, world)
+    ens = (ensemble_cls or DeviceEnsemble)(spec, lo, hi, device=device)
+    ens.step(want_profiles=want_profiles)
+    scal = ens.pack_scalars()
+    prof = ens.prof
+    if world > 1:
+        width = scal.shape[1]
+        most = shard_bounds(Rtot, 0, world)[1]
+        pad = torch.zeros((most, width), dtype=torch.float64, device=scal.device)
+        pad[: scal.shape[0]] = scal
+        gathered = [torch.zeros_like(pad) for _ in range(world)]
+        torch.distributed.all_gather(gathered, pad)
+        parts = []
+        for r in range(world):
+            a, b = shard_bounds(Rtot, r, world)
+            parts.append(gathered[r][: b - a])
+        scal = torch.cat(parts, dim=0)
+        if prof is not None:
+            torch.distributed.all_reduce(prof, op=torch.distributed.ReduceOp.SUM)
+    scal_h = scal.cpu().numpy()
+    prof_h = prof.cpu().numpy() if prof is not None else None
+    reps = np.bincount(np.asarray(spec.point_of, dtype=np.int64)) if len(spec.point_of) else None
+    info = dict(rank=rank, world=world, shard=(lo, hi), n_max=ens.n_max, h2d_bytes=ens.h2d_bytes,
+                d2h_bytes=int(scal.numel() * 8 + (prof.numel() * 8 if prof is not None else 0)), M=ens.rb.M)
+    n_part = scal_h[:, APS_RED_N + 2].astype(np.int64)
+    if (n_part < 0).any():
+        raise capi.ApsError("initial sample exceeded n_max; raise the particle bound")
+    return EnsembleResult(reducers=scal_h[:, :APS_RED_N], n_events=scal_h[:, APS_RED_N].astype(np.int64),
+                          status=scal_h[:, APS_RED_N + 1].astype(np.int32), n_particles=n_part, profiles=prof_h,
+                          reps_per_point=reps, info=info)
+
+
+# ---- reference-shaped entry points -------------------------------------------------------------
+def _profiles_from_init_kwargs(ps_kwargs, init_kwargs):
+    L = int(ps_kwargs["L"])
+    rp = np.array([init_kwargs["rho0_plus"](i / L) for i in range(L)], dtype=float)     # CLASS.py:71-72
+    rm = np.array([init_kwargs["rho0_minus"](i / L) for i in range(L)], dtype=float)
+    return rp, rm
+
+
+def _mean_std_se(x):
+    x = np.asarray(x, dtype=float)
+    mean = float(x.mean())
+    std = float(x.std(ddof=1)) if x.size > 1 else 0.0
+    return mean, std, std / np.sqrt(max(1, x.size))
+
+
+def build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, base_seed=0):
+    betas = np.repeat(np.asarray(beta_values, dtype=float), n_runs_per_beta)
+    point_of = np.repeat(np.arange(len(beta_values)), n_runs_per_beta)
+    run_idx = np.tile(np.arange(n_runs_per_beta), len(beta_values))
+    seeds = (np.uint64(base_seed) + np.uint64(10_000) * point_of.astype(np.uint64) + run_idx.astype(np.uint64))
+    ps = dict(ps_kwargs)
+    kw = {}
+    if ps.get("init", "fixed") == "poisson":
+        rp, rm = _profiles_from_init_kwargs(ps, init_kwargs)
+        kw = dict(profiles_plus=rp[None], profiles_minus=rm[None])
+    return EnsembleSpec(ps_kwargs=ps, run_kwargs=dict(run_kwargs), betas=betas, point_of=point_of, seeds=seeds, **kw)
+
+
+def sweep_over_betas(beta_values, n_runs_per_beta=10, ps_kwargs=None, init_kwargs=None, run_kwargs=None,
+                     base_seed=0, want_profiles=True, ensemble_cls=None):
+    """All (beta, run) replicas in one sharded launch; returns the arrays the reference's
+    sweep_over_betas collects (sweep_beta.py:880-931), keyed like its save_dict."""
+    spec = build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs or {}, init_kwargs or {}, run_kwargs or {},
+                                 base_seed=base_seed)
+    res = run_ensemble(spec, want_profiles=want_profiles, ensemble_cls=ensemble_cls)
+    nb = len(beta_values)
+    red = res.reducers.reshape(nb, n_runs_per_beta, APS_RED_N)
+    out = dict(beta_values=np.asarray(beta_values, dtype=float), raw_by_beta=[red[b, :, capi.APS_RED_V_EFF].copy() for b in range(nb)])
+    # key names of the reference's pre_dict / save_dict (sweep_beta.py:952-970,1002-1026)
+    for stem, col in [("", capi.APS_RED_V_EFF), ("D_", capi.APS_RED_D_EFF), ("m_", capi.APS_RED_M_MEAN),
+                      ("rho_", capi.APS_RED_RHO_EFF), ("block_", capi.APS_RED_BLOCK)]:
+        stats = [_mean_std_se(red[b, :, col]) for b in range(nb)]
+        out[stem + "means"] = np.array([s[0] for s in stats])
+        out[stem + "stds"] = np.array([s[1] for s in stats])
+        out[stem + "ses"] = np.array([s[2] for s in stats])
+    out["ps_kwargs"] = dict(ps_kwargs or {})
+    out["outs"] = []          # per-run dicts stay on the device; the reducers above replace them
+    out["n_events"] = res.n_events.reshape(nb, n_runs_per_beta)
+    out["status"] = res.status.reshape(nb, n_runs_per_beta)
+    if res.profiles is not None:
+        reps = float(n_runs_per_beta)
+        out["rho_plus_profile_mean"] = res.profiles[:, 0] / reps
+        out["rho_minus_profile_mean"] = res.profiles[:, 1] / reps
+        var_p = np.maximum(res.profiles[:, 2] / reps - (res.profiles[:, 0] / reps) ** 2, 0.0)
+        out["rho_plus_profile_se"] = np.sqrt(var_p / max(1.0, reps - 1.0))
+    out["info"] = res.info
+    return out
+
+
+def sweep_beta_ensemble(beta, n_runs=10, ps_kwargs=None, init_kwargs=None, run_kwargs=None, rng_seeds=None):
+    """Drop-in for sweep_beta.py:56-117 (same positional return tuple; `out_list` is empty because
+    the per-run reducers already ran on the device)."""
+    spec = build_beta_sweep_spec([beta], n_runs, ps_kwargs or {}, init_kwargs or {}, run_kwargs or {})
+    if rng_seeds is not None:
+        spec.seeds = np.asarray([int(s) for s in rng_seeds[:n_runs]], dtype=np.uint64)
+    res = run_ensemble(spec, want_profiles=False)
+    r = res.reducers
+    mean, std, se = _mean_std_se(r[:, capi.APS_RED_V_EFF])
+    D = _mean_std_se(r[:, capi.APS_RED_D_EFF]); m = _mean_std_se(r[:, capi.APS_RED_M_MEAN])
+    rho = _mean_std_se(r[:, capi.APS_RED_RHO_EFF]); blk = _mean_std_se(r[:, capi.APS_RED_BLOCK])
+    return (mean, std, se, r[:, capi.APS_RED_V_EFF].copy(), [], m[0], m[1], m[2], rho[0], rho[2], blk[0], blk[2], D[0], D[2])
+
+
+def init_distributed_from_env():
+    """One process per GPU, launched by torchrun: bind LOCAL_RANK's device and join the NCCL group."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+        capi.check(capi.load().aps_set_device(local), "aps_set_device")
+    if world > 1 and not torch.distributed.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.distributed.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
+    return int(os.environ.get("RANK", "0")), world

@@ -151,6 +151,23 @@ int64_t aps_launch_count(void);
 /* Shared-memory bytes and threads the K1 plan uses for (L, n_max, radius); <0 if it cannot fit. */
 int64_t aps_replica_smem_bytes(const aps_params* p, int32_t n_max);
 
+/* ---- K3: device-side initial conditions for native-mode ensembles (init_particles, CLASS.py:141-195) */
+typedef struct aps_init_args {
+    int32_t n_replicas, L, K, n_max;
+    int32_t mode;               /* 0 = 'fixed', 1 = 'poisson'                                     */
+    int32_t N_fixed;            /* 'fixed': particles per replica (unless N_of is given)          */
+    int32_t n_profiles, reserved;
+    const double* rho0_plus;    /* 'poisson': [n_profiles][L] intensities rho0_plus(i/L)          */
+    const double* rho0_minus;
+    const int32_t* profile_of;  /* [n_replicas] profile index per replica, NULL = profile 0       */
+    const int32_t* N_of;        /* [n_replicas] optional per-replica N for 'fixed'                */
+    const uint64_t* seeds;      /* [n_replicas] Philox keys (same keys as the run)                */
+    int32_t* pos0;              /* [n_replicas][n_max] out                                        */
+    int8_t* sigma0;             /* [n_replicas][n_max] out                                        */
+    int32_t* n;                 /* [n_replicas] out; -1 if the sample does not fit n_max          */
+} aps_init_args;
+int aps_init_particles_device(const aps_init_args* a, void* stream);
+
 /* compute_local_m_field (CLASS.py:216-246) for one lattice; host buffers: counts int32[L] -> out double[L] */
 int aps_m_field_host(const aps_params* p, const double* weights, const int32_t* counts_p, const int32_t* counts_m,
                      double* out);

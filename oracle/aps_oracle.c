@@ -29,6 +29,7 @@
 #include "../include/aps.h"
 #include "../include/aps_math.h"
 #include "../include/aps_philox.h"
+#include "../include/aps_sampling.h"
 
 /* ---- numpy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, pairwise_sum_DOUBLE),
  *      what `rates.sum()` does at CLASS.py:352 ------------------------------------------------ */
@@ -354,4 +355,48 @@ int aps_oracle_run(const aps_params* P, const aps_batch* B, int mode, int n_thre
     for (int i = 1; i < n_threads; ++i) { pthread_join(th[i], NULL); if (args[i].rc) rc = args[i].rc; }
     free(th); free(args);
     return rc;
+}
+
+/* ---- initial conditions: same sampling algorithm as csrc/aps_init.cuh (host pointers) ---- */
+int aps_oracle_init(const aps_init_args* a) {
+    for (int rep = 0; rep < a->n_replicas; ++rep) {
+        const uint32_t k0 = (uint32_t)a->seeds[rep], k1 = (uint32_t)(a->seeds[rep] >> 32);
+        int32_t* gpos = a->pos0 + (size_t)rep * a->n_max;
+        int8_t* gsig = a->sigma0 + (size_t)rep * a->n_max;
+        if (a->mode == 1) {
+            const int prof = a->profile_of ? a->profile_of[rep] : 0;
+            const double* rp = a->rho0_plus + (size_t)prof * a->L;
+            const double* rm = a->rho0_minus + (size_t)prof * a->L;
+            int n = 0, overflow = 0;
+            for (int x = 0; x < a->L; ++x) {
+                uint64_t m;
+                int c = sample_site((uint32_t)x, rp[x], rm[x], a->K, k0, k1, &m);
+                for (int j = 0; j < c; ++j) {
+                    if (n < a->n_max) { gpos[n] = x; gsig[n] = ((m >> j) & 1ULL) ? 1 : -1; } else overflow = 1;
+                    ++n;
+                }
+            }
+            a->n[rep] = overflow ? -1 : n;
+        } else {
+            const int N = a->N_of ? a->N_of[rep] : a->N_fixed;
+            if (N > a->n_max || (long long)N > (long long)a->L * a->K) { a->n[rep] = -1; continue; }
+            uint16_t* avail = malloc(2 * (size_t)a->L);
+            uint8_t* fill = calloc((size_t)a->L, 1);
+            for (int x = 0; x < a->L; ++x) avail[x] = (uint16_t)x;
+            int navail = a->L;
+            for (int i = 0; i < N; ++i) {
+                aps_u32x4 r4 = aps_philox4x32_10((uint32_t)i, 0u, APS_RNG_INIT_POS, 0u, k0, k1);
+                int j = (int)(aps_u53(r4.v[0], r4.v[1]) * (double)navail);
+                if (j >= navail) j = navail - 1;
+                int site = avail[j];
+                gpos[i] = site;
+                if (++fill[site] >= a->K) avail[j] = avail[--navail];
+                aps_u32x4 s4 = aps_philox4x32_10((uint32_t)i, 0u, APS_RNG_INIT_SIGMA, 0u, k0, k1);
+                gsig[i] = (s4.v[0] & 1u) ? 1 : -1;
+            }
+            free(avail); free(fill);
+            a->n[rep] = N;
+        }
+    }
+    return 0;
 }

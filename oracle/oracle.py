@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from aps_b200.capi import ApsBatch, ApsParams  # noqa: E402  (shared descriptor layout)
+from aps_b200.capi import ApsBatch, ApsInitArgs, ApsParams  # noqa: E402  (shared descriptor layout)
 
 LIB = os.path.join(HERE, "libaps_oracle.so")
 _lib = None
@@ -41,5 +41,7 @@ def load():
         lib.aps_oracle_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.aps_oracle_m_field.restype = C.c_int
         lib.aps_oracle_m_field.argtypes = [C.POINTER(ApsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.aps_oracle_init.restype = C.c_int
+        lib.aps_oracle_init.argtypes = [C.POINTER(ApsInitArgs)]
         _lib = lib
     return _lib

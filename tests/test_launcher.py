@@ -1,0 +1,152 @@
+"""Launcher: sharding, collectives (gloo, world_size 2, on CPU) and the reference-shaped sweep API."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from aps_b200 import launcher as la
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+PS = dict(L=64, xlim=1, rate_diffusion=0.4, rate_active=3, flip_rate_fn=None, init="poisson", N=30, scale_rates=False,
+          local_kernel_sigma=0.03, minus_anchor=True, periodic=False, anchor_positions=None, site_capacity=1,
+          crowding_suppresses_rates=False, k_on=0, k_off=0, k_exit=0)
+RUN = dict(T=3.0, obs_dt=0.1, record_fft=True, record_var=True)
+
+
+def init_kwargs():
+    g = la.make_exp_gradient(L=64, N=30, frac_plus=0.75, decay_length=0.35, anchor_positions=None)
+    return dict(rho0_plus=g[0], rho0_minus=g[1])
+
+
+def _sweep(betas=(0.0, 1.0, 2.5), runs=3):
+    from oracle_ensemble import OracleEnsemble
+    return la.sweep_over_betas(list(betas), runs, PS, init_kwargs(), RUN, base_seed=5, ensemble_cls=OracleEnsemble)
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    out = _sweep()
+    q.put((rank, {k: v for k, v in out.items() if isinstance(v, np.ndarray)}, out["info"]))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_shard_bounds_cover_everything():
+    for n in [0, 1, 7, 64, 4096, 4097]:
+        for w in [1, 2, 3, 8]:
+            b = [la.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_world2_gloo_equals_single_process():
+    single = _sweep()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=300) for _ in range(2)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    for rank, arrs, info in got:
+        assert info["world"] == 2 and info["shard"] == la.shard_bounds(9, rank, 2)
+        for k, v in arrs.items():
+            np.testing.assert_array_equal(v, single[k], err_msg=k) if v.dtype.kind in "iu" else \
+                np.testing.assert_allclose(v, single[k], rtol=1e-13, atol=1e-15, err_msg=k)
+
+
+def test_reference_shaped_outputs():
+    out = _sweep(betas=(0.5, 2.0), runs=4)
+    for k in ["beta_values", "means", "stds", "ses", "D_means", "D_ses", "m_means", "m_stds", "m_ses", "rho_means",
+              "rho_ses", "block_means", "block_ses", "ps_kwargs", "outs"]:      # sweep_beta.py:952-970
+        assert k in out, k
+    assert out["means"].shape == (2,) and out["n_events"].shape == (2, 4)
+    assert (out["status"] == 0).all() and (out["n_events"] > 10).all()
+    assert out["m_means"][1] != out["m_means"][0]
+    assert out["rho_plus_profile_mean"].shape == (2, 64)
+    # sum over sites of the time-averaged total density * dx == 1 for every replica (CLASS.py:209-213)
+    tot = (out["rho_plus_profile_mean"] + out["rho_minus_profile_mean"]).sum(1) * (1.0 / 64)
+    np.testing.assert_allclose(tot, 1.0, rtol=1e-12)
+
+
+def test_make_exp_gradient_matches_driver_fixture():
+    from common import load_case
+    c = load_case("c2_sweep_b0")
+    g = la.make_exp_gradient(L=1000, N=500, frac_plus=0.75, decay_length=0.35, anchor_positions=None)
+    assert np.array_equal(g[2], c["rho0_plus"]) and np.array_equal(g[3], c["rho0_minus"])
+    assert g[0](0.25) == c["rho0_plus"][250]
+
+
+@pytest.mark.gpu
+def test_gpu_launcher_matches_oracle_ensemble():
+    """End to end on the GPU (device init + K1 + K4 + gather) vs the oracle-backed ensemble:
+    event counts and windows exact, reducers to 1e-9 (different summation association)."""
+    from oracle_ensemble import OracleEnsemble
+    ik = init_kwargs()
+    a = la.sweep_over_betas([0.0, 1.0, 2.5], 3, PS, ik, RUN, base_seed=5)
+    b = la.sweep_over_betas([0.0, 1.0, 2.5], 3, PS, ik, RUN, base_seed=5, ensemble_cls=OracleEnsemble)
+    assert np.array_equal(a["n_events"], b["n_events"]) and np.array_equal(a["status"], b["status"])
+    for k in ["means", "ses", "D_means", "m_means", "rho_means", "block_means"]:
+        np.testing.assert_allclose(a[k], b[k], rtol=1e-9, atol=1e-13, err_msg=k)
+    np.testing.assert_allclose(a["rho_plus_profile_mean"], b["rho_plus_profile_mean"], rtol=1e-12, atol=1e-15)
+    # fixed init with per-point N (double-sweep style)
+    ps = dict(PS, init="fixed", N=20)
+    a = la.sweep_over_betas([0.3, 1.7], 4, ps, {}, RUN, base_seed=9)
+    b = la.sweep_over_betas([0.3, 1.7], 4, ps, {}, RUN, base_seed=9, ensemble_cls=OracleEnsemble)
+    assert np.array_equal(a["n_events"], b["n_events"])
+    np.testing.assert_allclose(a["means"], b["means"], rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_gpu_init_matches_oracle_init_bitwise():
+    from oracle_ensemble import OracleEnsemble
+    for init, K in [("poisson", 1), ("poisson", 2), ("fixed", 1), ("fixed", 3)]:
+        ps = dict(PS, init=init, site_capacity=K, N=40)
+        spec = la.build_beta_sweep_spec([0.5, 1.5], 5, ps, init_kwargs(), RUN, base_seed=3)
+        dev = la.DeviceEnsemble(spec, 0, 10)
+        dev.init_particles()
+        seeds, pos0, sg0, n = OracleEnsemble(spec, 0, 10).init_states()
+        assert np.array_equal(dev.n.cpu().numpy(), n)
+        for r in range(10):
+            assert np.array_equal(dev.pos0[r, :n[r]].cpu().numpy(), pos0[r, :n[r]])
+            assert np.array_equal(dev.sigma0[r, :n[r]].cpu().numpy(), sg0[r, :n[r]])
+        occ = np.zeros(64, int)
+        np.add.at(occ, pos0[0, :n[0]], 1)
+        assert occ.max() <= K
+
+
+def test_oracle_init_statistics_match_reference_init():
+    """Device-side init (restated in the oracle) vs the reference's numpy init: mean particle number and
+    mean '+' occupancy profile agree within 4 standard errors (different RNG, same law)."""
+    from oracle_ensemble import OracleEnsemble
+    sys.path.insert(0, os.path.join(HERE, "..", "dropin"))
+    from PARTICLE_solver_CLASS import ParticleSystem
+    R = 400
+    for init, K in [("poisson", 1), ("poisson", 2), ("fixed", 1), ("fixed", 2)]:
+        ps = dict(PS, init=init, site_capacity=K, N=40)
+        spec = la.build_beta_sweep_spec([1.0], R, ps, init_kwargs(), RUN, base_seed=11)
+        seeds, pos0, sg0, n = OracleEnsemble(spec, 0, R).init_states()
+        ours_n = n.astype(float)
+        ours_plus = np.zeros((R, 64))
+        for r in range(R):
+            np.add.at(ours_plus[r], pos0[r, :n[r]][sg0[r, :n[r]] == 1], 1)
+        ref_n, ref_plus = np.zeros(R), np.zeros((R, 64))
+        g = np.random.default_rng(123)
+        for r in range(R):
+            psys = ParticleSystem(beta=1.0, rng=g, **ps, **init_kwargs())
+            p, s = psys.init_particles()
+            ref_n[r] = p.size
+            np.add.at(ref_plus[r], p[s == 1], 1)
+        se = np.sqrt(ours_n.var(ddof=1) / R + ref_n.var(ddof=1) / R) + 1e-12
+        assert abs(ours_n.mean() - ref_n.mean()) <= 4 * se, (init, K)
+        se_prof = np.sqrt(ours_plus.var(0, ddof=1) / R + ref_plus.var(0, ddof=1) / R) + 1e-9
+        z = np.abs(ours_plus.mean(0) - ref_plus.mean(0)) / se_prof
+        assert (z < 4.5).all(), (init, K, z.max())
