@@ -297,6 +297,36 @@ def reducer_golden(PS):
     print("reducers:", {k: {kk: vv for kk, vv in v.items() if not isinstance(vv, list)} for k, v in res.items()})
 
 
+STAT_PS = dict(L=100, xlim=1, rate_diffusion=0.3, rate_active=3, init="fixed", N=40, scale_rates=False,
+               local_kernel_sigma=0.03, site_capacity=1)
+STAT_RUN = dict(T=4.0, obs_dt=0.25, record_fft=False, record_var=False)
+
+
+def stat_fixture(PS, n_runs=300):
+    """Ensemble statistics of the unmodified reference (seeded numpy Generators) for the native-mode
+    statistical parity test: per-site mean/variance over replicas of the time-averaged (second half)
+    rho_plus / rho_minus profiles and the per-replica time-averaged m_global."""
+    save = dict(meta=np.array(json.dumps(dict(ps=STAT_PS, run=STAT_RUN, n_runs=n_runs, betas=[0.5, 2.0]))))
+    for bi, beta in enumerate([0.5, 2.0]):
+        prof_p, prof_m, mbar, nev = [], [], [], []
+        for r in range(n_runs):
+            kw = dict(BASE); kw.update(STAT_PS)
+            rec = RecordingRNG(np.random.default_rng(900000 + 1000 * bi + r))
+            ps = PS(beta=beta, rng=rec, **kw)
+            out = ps.run(**STAT_RUN)
+            M = len(out["times_obs"])
+            assert all(p is not None for p in out["pos_list"])
+            prof_p.append(out["rho_p_list"][M // 2:].mean(0)); prof_m.append(out["rho_m_list"][M // 2:].mean(0))
+            mbar.append(out["m_global"][M // 2:].mean())
+            nev.append(sum(1 for _ in rec.log) )
+        prof_p, prof_m = np.array(prof_p), np.array(prof_m)
+        save[f"b{bi}_rho_p_mean"] = prof_p.mean(0); save[f"b{bi}_rho_p_var"] = prof_p.var(0, ddof=1)
+        save[f"b{bi}_rho_m_mean"] = prof_m.mean(0); save[f"b{bi}_rho_m_var"] = prof_m.var(0, ddof=1)
+        save[f"b{bi}_mbar"] = np.array(mbar)
+        print(f"stat beta={beta}: mean m = {np.mean(mbar):.4f} +- {np.std(mbar) / np.sqrt(n_runs):.4f}")
+    np.savez_compressed(os.path.join(OUT, "stat_ensemble.npz"), **save)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     PS = import_reference()
@@ -307,6 +337,8 @@ def main():
         run_case(PS, name, spec)
     if not want or "reducers" in want:
         reducer_golden(PS)
+    if not want or "stat" in want:
+        stat_fixture(PS)
 
 
 if __name__ == "__main__":
