@@ -12,6 +12,7 @@
 #include "aps_k1.cuh"
 #include "aps_obs.cuh"
 #include "aps_init.cuh"
+#include "aps_k2.cuh"
 
 namespace {
 
@@ -302,6 +303,79 @@ int aps_profile_sums_device(const aps_profile_args* a, void* stream) {
     if (a->n_points == 0) return APS_OK;
     dim3 grid((a->L + 127) / 128, a->n_points);
     aps::profile_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates* out) {
+    if (!out || !(D >= 0) || !(lam >= 0) || !(dt > 0)) return fail(APS_ERR_INVALID, "aps_k2_rates_init: bad argument");
+    if (aps_k2_make_rates(D, lam, beta, dt, out)) return fail(APS_ERR_INVALID, "B*32*dt must be in (0, 24]: reduce dt");
+    return APS_OK;
+}
+
+static size_t k2_smem(int radius) {
+    size_t work = (size_t)(aps::kK2Tile + 128 + ((aps::kK2Tile + 128) >> 6) * 4) + 16;
+    work = (work + 15) & ~(size_t)15;
+    if (radius < 0) return work;
+    return work + (size_t)((radius + 3) & ~3) + aps::kK2Tile + 32 + radius + 16;
+}
+
+int aps_k2_pass_device(const aps_k2_args* a, void* stream) {
+    if (!a || a->L < aps::kK2Tile || a->L % aps::kK2Tile || a->global_offset % aps::kK2Tile || !a->in || !a->out || a->in == a->out)
+        return fail(APS_ERR_INVALID, "aps_k2_pass: L and global_offset must be multiples of 8192, in != out");
+    if (a->radius > 1024) return fail(APS_ERR_INVALID, "aps_k2_pass: radius too large");
+    if (a->radius >= 0 && !a->w16) return fail(APS_ERR_INVALID, "aps_k2_pass: local field needs w16 taps");
+    if (a->radius < 0 && (!a->msum_in || a->n_particles < 1)) return fail(APS_ERR_INVALID, "aps_k2_pass: global field needs msum_in and n_particles");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    const size_t smem = k2_smem(a->radius);
+    const int grid = (int)(a->L / aps::kK2Tile);
+    if (a->radius >= 0) {
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::k2_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aps::k2_pass_kernel<true><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a);
+    } else {
+        aps::k2_pass_kernel<false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a);
+    }
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+int aps_k2_run_device(aps_k2_args* a, int n_passes, void* stream) {
+    if (!a || n_passes < 0) return fail(APS_ERR_INVALID, "aps_k2_run: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int p = 0; p < n_passes; ++p) {
+        if (a->radius < 0) {
+            if (!a->msum_out) return fail(APS_ERR_INVALID, "aps_k2_run: global field needs msum_in/msum_out");
+            CU(cudaMemcpyAsync(a->msum_out, a->msum_in, 8, cudaMemcpyDeviceToDevice, st));
+        }
+        TRY(aps_k2_pass_device(a, stream));
+        const uint8_t* t = a->in; a->in = a->out; a->out = const_cast<uint8_t*>(t);
+        if (a->radius < 0) { const int64_t* m = a->msum_in; a->msum_in = a->msum_out; a->msum_out = const_cast<int64_t*>(m); }
+        a->pass += 1;
+    }
+    return APS_OK;
+}
+
+int aps_k2_init_device(uint8_t* state, int64_t L, int64_t global_offset, uint64_t seed, double density, double frac_plus,
+                       void* stream) {
+    if (!state || L < 1 || !(density >= 0 && density <= 1) || !(frac_plus >= 0 && frac_plus <= 1))
+        return fail(APS_ERR_INVALID, "aps_k2_init: bad argument");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    auto thr = [](double p) { double v = p * 4294967296.0; return (uint32_t)(v >= 4294967295.0 ? 4294967295.0 : v); };
+    const long long threads = (L + 1) / 2;
+    aps::k2_init_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(state, L, global_offset, seed, thr(density), thr(frac_plus));
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset, int64_t L_global, int32_t nbins,
+                          uint64_t* cnt_plus, uint64_t* cnt_minus, void* stream) {
+    if (!state || L < 1 || nbins < 1 || !cnt_plus || !cnt_minus || L_global < L) return fail(APS_ERR_INVALID, "aps_k2_profile: bad argument");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    aps::k2_profile_kernel<<<(unsigned)((L + 4095) / 4096), 256, 0, (cudaStream_t)stream>>>(
+        state, L, global_offset, L_global, nbins, (unsigned long long*)cnt_plus, (unsigned long long*)cnt_minus);
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return APS_OK;

@@ -232,6 +232,38 @@ typedef struct aps_profile_args {
 } aps_profile_args;
 int aps_profile_sums_device(const aps_profile_args* a, void* stream);
 
+/* ---- K2: sublattice-parallel kernel for one lattice too large for shared memory -------------- */
+#include "aps_k2_model.h"
+typedef struct aps_k2_args {
+    int64_t L;                  /* sites in this call's buffers (multiple of 8192); a slab incl. ghosts */
+    int64_t L_global;           /* sites of the whole lattice (profile binning)                     */
+    int64_t global_offset;      /* global index of buffer site 0 (multiple of 8192); keys the RNG   */
+    int64_t n_particles;        /* global-field mode: N                                             */
+    uint64_t seed;
+    uint64_t pass;              /* pass counter; parity = pass & 1; two passes advance time by dt   */
+    int32_t radius;             /* local Gaussian field radius in sites; -1 = global magnetisation  */
+    int32_t reserved;
+    aps_k2_rates rates;         /* aps_k2_make_rates(D, lambda, beta, dt)                            */
+    const int32_t* w16;         /* [radius+1] taps round(w_j * 65536), centre first (device)         */
+    const uint8_t* in;          /* [L] site bytes 0/1/2                                              */
+    uint8_t* out;               /* [L] ping-pong target                                              */
+    const int64_t* msum_in;     /* global-field mode: sum(sigma) at pass start (device)             */
+    int64_t* msum_out;          /* must hold *msum_in on entry; receives the flips' increments      */
+} aps_k2_args;
+/* thresholds / Poisson table for (D, lambda, beta, dt); returns non-zero if B*32*dt is out of (0, 24] */
+int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates* out);
+/* one pass (in -> out) */
+int aps_k2_pass_device(const aps_k2_args* a, void* stream);
+/* n_passes passes ping-ponging between a->in and a->out (a->pass, in/out and msum are advanced in the
+ * struct); the final state is in a->in after the call.  msum buffers are handled internally. */
+int aps_k2_run_device(aps_k2_args* a, int n_passes, void* stream);
+/* Bernoulli(density) occupancy, '+' with probability frac_plus */
+int aps_k2_init_device(uint8_t* state, int64_t L, int64_t global_offset, uint64_t seed, double density, double frac_plus,
+                       void* stream);
+/* counts of '+' / '-' per coarse bin (uint64 accumulators, caller zeroes them) */
+int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset, int64_t L_global, int32_t nbins,
+                          uint64_t* cnt_plus, uint64_t* cnt_minus, void* stream);
+
 /* Test / tuning hooks: widen the selection guard band (forces the exact serial slow path) and
  * override the K1 block size (32, 64, 128, 256; 0 = heuristic). Not needed in production. */
 void aps_debug_set_guard_scale(double scale);

@@ -400,3 +400,94 @@ int aps_oracle_init(const aps_init_args* a) {
     }
     return 0;
 }
+
+/* ---- K2: sublattice-parallel update rule (include/aps_k2_model.h), sequential restatement -------
+ * Host pointers.  Processes segments one after another; active regions are disjoint, so the order
+ * does not matter and the result must equal the CUDA kernel's bit for bit. */
+static long long k2_reflect_idx(long long i, long long L) {
+    long long per = 2 * L, m = i % per;
+    if (m < 0) m += per;
+    if (m >= L) m = per - 1 - m;
+    return m;
+}
+
+int aps_oracle_k2_pass(const aps_k2_args* a) {
+    const long long L = a->L;
+    const int q = (int)(a->pass & 1ULL), r = a->radius;
+    const uint8_t* in = a->in;
+    uint8_t* out = a->out;
+    memcpy(out, in, (size_t)L);
+    const uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
+    long long dsig = 0;
+    const double mg = r < 0 ? (double)(*a->msum_in) / (double)a->n_particles : 0.0;
+    for (long long seg = 0; seg * APS_K2_SEG < L; ++seg) {
+        const long long abase = seg * APS_K2_SEG + q * APS_K2_HALF;
+        if (abase + APS_K2_HALF > L) continue;
+        const uint64_t sg64 = (uint64_t)(a->global_offset / APS_K2_SEG) + (uint64_t)seg;
+        const uint32_t c0 = (uint32_t)sg64, c1 = (uint32_t)a->pass;
+        const uint32_t chi = (uint32_t)(sg64 >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
+        aps_u32x4 pn = aps_philox4x32_10(c0, c1, 0xFFFFFFFFu, chi, k0, k1);
+        const double un = aps_u53(pn.v[0], pn.v[1]);
+        int ntr = 0;
+        while (ntr < APS_K2_MAX_TRIALS - 1 && un >= a->rates.cdf[ntr]) ++ntr;
+        for (int t = 0; t < ntr; ++t) {
+            aps_u32x4 w4 = aps_philox4x32_10(c0, c1, (uint32_t)(t / 2), chi, k0, k1);
+            const uint32_t wa = w4.v[2 * (t & 1)], wb = w4.v[2 * (t & 1) + 1];
+            const long long x = abase + (long long)(wa >> 27);
+            const uint32_t slot = wa << 5;
+            const uint8_t v = out[x];
+            if (v == APS_K2_EMPTY) continue;
+            if (slot < a->rates.t_left) {
+                if (x > 0 && out[x - 1] == APS_K2_EMPTY) { out[x - 1] = v; out[x] = APS_K2_EMPTY; }
+            } else if (slot < a->rates.t_right || (slot < a->rates.t_active && v == APS_K2_PLUS)) {
+                if (x < L - 1 && out[x + 1] == APS_K2_EMPTY) { out[x + 1] = v; out[x] = APS_K2_EMPTY; }
+            } else if (slot >= a->rates.t_active) {
+                const int sg = (v == APS_K2_PLUS) ? 1 : -1;
+                double m;
+                if (r >= 0) {
+                    int sw = 0, tw = 0;
+                    for (int j = -r; j <= r; ++j) {
+                        const int cv = in[k2_reflect_idx(x + j, L)];      /* frozen pre-pass state */
+                        const int wj = a->w16[j < 0 ? -j : j];
+                        sw += wj * ((cv == APS_K2_PLUS) - (cv == APS_K2_MINUS));
+                        tw += wj * (cv != 0);
+                    }
+                    m = tw > 0 ? (double)sw / (double)tw : 0.0;
+                } else m = mg;
+                const double cflip = aps_exp(((-a->rates.beta) * (double)sg) * m);
+                if ((double)wb * 2.3283064365386963e-10 < cflip * a->rates.inv_cmax) {
+                    out[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS;
+                    dsig -= 2 * sg;
+                }
+            }
+        }
+    }
+    if (a->msum_out) *a->msum_out += dsig;
+    return 0;
+}
+
+int aps_oracle_k2_run(aps_k2_args* a, int n_passes) {
+    for (int p = 0; p < n_passes; ++p) {
+        if (a->radius < 0) *a->msum_out = *a->msum_in;
+        aps_oracle_k2_pass(a);
+        const uint8_t* t = a->in; a->in = a->out; a->out = (uint8_t*)t;
+        if (a->radius < 0) { const int64_t* m = a->msum_in; a->msum_in = a->msum_out; a->msum_out = (int64_t*)m; }
+        a->pass += 1;
+    }
+    return 0;
+}
+
+int aps_oracle_k2_rates(double D, double lam, double beta, double dt, aps_k2_rates* out) {
+    return aps_k2_make_rates(D, lam, beta, dt, out);
+}
+
+void aps_oracle_k2_init(uint8_t* state, int64_t L, int64_t global_offset, uint64_t seed, double density, double frac_plus) {
+    double vo = density * 4294967296.0, vp = frac_plus * 4294967296.0;
+    uint32_t t_occ = (uint32_t)(vo >= 4294967295.0 ? 4294967295.0 : vo), t_plus = (uint32_t)(vp >= 4294967295.0 ? 4294967295.0 : vp);
+    for (int64_t i = 0; i < L; i += 2) {
+        uint64_t g = (uint64_t)(global_offset + i);
+        aps_u32x4 w = aps_philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0u, APS_RNG_INIT_SITE, (uint32_t)seed, (uint32_t)(seed >> 32));
+        state[i] = (w.v[0] < t_occ) ? ((w.v[1] < t_plus) ? APS_K2_PLUS : APS_K2_MINUS) : APS_K2_EMPTY;
+        if (i + 1 < L) state[i + 1] = (w.v[2] < t_occ) ? ((w.v[3] < t_plus) ? APS_K2_PLUS : APS_K2_MINUS) : APS_K2_EMPTY;
+    }
+}

@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
-from aps_b200.capi import ApsBatch, ApsInitArgs, ApsParams  # noqa: E402  (shared descriptor layout)
+from aps_b200.capi import ApsBatch, ApsInitArgs, ApsK2Args, ApsK2Rates, ApsParams  # noqa: E402  (shared descriptor layout)
 
 LIB = os.path.join(HERE, "libaps_oracle.so")
 _lib = None
@@ -43,5 +43,13 @@ def load():
         lib.aps_oracle_m_field.argtypes = [C.POINTER(ApsParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.aps_oracle_init.restype = C.c_int
         lib.aps_oracle_init.argtypes = [C.POINTER(ApsInitArgs)]
+        lib.aps_oracle_k2_pass.restype = C.c_int
+        lib.aps_oracle_k2_pass.argtypes = [C.POINTER(ApsK2Args)]
+        lib.aps_oracle_k2_run.restype = C.c_int
+        lib.aps_oracle_k2_run.argtypes = [C.POINTER(ApsK2Args), C.c_int]
+        lib.aps_oracle_k2_rates.restype = C.c_int
+        lib.aps_oracle_k2_rates.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(ApsK2Rates)]
+        lib.aps_oracle_k2_init.restype = None
+        lib.aps_oracle_k2_init.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double]
         _lib = lib
     return _lib

@@ -1,0 +1,157 @@
+"""K2 (sublattice-parallel kernel).  K2 has no reference counterpart (the reference cannot run large
+lattices); it is the discrete-time sublattice version of the same model, so parity is
+  * bit-exact GPU == oracle restatement of the same update rule (include/aps_k2_model.h),
+  * bit-exact multi-slab (ghost zones, world_size 2/3, gloo) == single slab,
+  * statistical agreement with the exact Gillespie chain (oracle K1) in the dt -> 0 regime,
+  * conservation / exclusion invariants at any size."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from aps_b200 import capi
+from aps_b200.sublattice import SublatticeLattice, TILE, fixed_point_taps
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def oracle_lattice(L, **kw):
+    from oracle_k2 import OracleK2Backend
+    return SublatticeLattice(L, backend=OracleK2Backend(), **kw)
+
+
+PARAMS = dict(D=0.3, lam=3.0, beta=1.2, dt=0.01)
+
+
+def test_invariants_and_walls():
+    for sigma in [None, 2.5]:
+        lat = oracle_lattice(2 * TILE, sigma_sites=sigma, seed=3, **PARAMS)
+        lat.init_random(0.5, 0.7)
+        s0 = lat.state.numpy().copy()
+        lat.run(25)
+        s1 = lat.state.numpy()
+        assert set(np.unique(s1)) <= {0, 1, 2}
+        assert (s1 != 0).sum() == (s0 != 0).sum()                      # particles conserved (reflecting walls)
+        assert not np.array_equal(s0, s1)
+        if sigma is None:                                               # running sum(sigma) stays exact
+            assert int(lat.msum[0][0]) == int((s1 == 1).sum()) - int((s1 == 2).sum())
+
+
+def test_drift_piles_particles_at_the_right_wall():
+    lat = oracle_lattice(TILE, sigma_sites=None, seed=5, D=0.05, lam=5.0, beta=0.0, dt=0.02)
+    lat.init_random(0.3, 1.0)
+    lat.run(400)                                  # T = 8: '+' particles drift ~ lam*T*(1-rho)/2 ~ 15 sites
+    rp, rm = lat.profile(TILE // 16)
+    tot = rp + rm
+    assert tot[-1] > 0.45 and tot[0] < 0.2 and abs(tot[100:400].mean() - 0.3) < 0.02
+
+
+def _slab_worker(rank, world, port, q, sigma, passes):
+    sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    lat = oracle_lattice(6 * TILE, sigma_sites=sigma, seed=11, **PARAMS)
+    lat.init_random(0.5, 0.6)
+    lat.refresh_every = 20                       # force several ghost refreshes
+    lat.run_passes(passes)
+    full = lat.gather_state()
+    rp, rm = lat.profile(24)
+    q.put((rank, full, rp, rm, lat.n_particles))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_decomposition_is_bit_identical_to_single_slab(world):
+    sigma, passes = 3.0, 70
+    single = oracle_lattice(6 * TILE, sigma_sites=sigma, seed=11, **PARAMS)
+    single.init_random(0.5, 0.6)
+    single.run_passes(passes)
+    want = single.state.numpy()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 7 * world
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, q, sigma, passes)) for r in range(world)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=600) for _ in range(world)]
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    rp1, rm1 = single.profile(24)
+    for rank, full, rp, rm, n in got:
+        assert np.array_equal(full, want), f"rank {rank}: slab run differs from the single-slab run"
+        assert np.array_equal(rp, rp1) and np.array_equal(rm, rm1) and n == single.n_particles
+
+
+def test_small_dt_limit_matches_exact_gillespie():
+    """Global-field mode, L = 8192, N ~ 4100: magnetisation relaxation and the coarse density profile after
+    T = 1.5 against the exact chain (oracle K1, Philox).  Both are single realisations of a self-averaging
+    lattice; tolerance = 5 combined standard errors of the bin counts + 2 % (dt bias at dt = 0.004)."""
+    from aps_b200.batch import make_params
+    from common import HostRun
+    from oracle import oracle
+    L, T = TILE, 1.5
+    D, lam, beta, dt = 0.2, 2.0, 0.6, 0.004
+    lat = oracle_lattice(L, sigma_sites=None, seed=21, D=D, lam=lam, beta=beta, dt=dt)
+    lat.init_random(0.5, 0.9)
+    s0 = lat.state.numpy().copy()
+    lat.run(int(round(T / dt)))
+    s1 = lat.state.numpy()
+    pos0 = np.nonzero(s0)[0].astype(np.int32)
+    sg0 = np.where(s0[pos0] == 1, 1, -1).astype(np.int8)
+    n = len(pos0)
+    times = np.array([0.0, T])                  # the run itself goes on to T + 0.01 so that row 1 is reached
+    hr = HostRun(L, n, 2, [n], pos0, sg0, [beta], times, None, seeds=np.array([77], np.uint64), record=1)
+    P = make_params(L, 1, -1, D, lam, T + 0.01)
+    assert oracle.load().aps_oracle_run(P, hr.batch, 1, 1) == 0
+    assert hr.n_obs[0] == 2
+    cp, cm = hr.obs_cp[0, 1].astype(int), hr.obs_cm[0, 1].astype(int)
+    m_exact = (cp.sum() - cm.sum()) / n
+    m_k2 = ((s1 == 1).sum() - (s1 == 2).sum()) / n
+    m0 = (sg0.sum()) / n
+    assert abs(m0) > 0.7 and abs(m_exact) < 0.45                       # it did relax
+    assert abs(m_k2 - m_exact) < 5 * 2 / np.sqrt(n) + 0.02
+    nb = 16
+    k2_tot = ((s1 != 0).reshape(nb, -1)).sum(1)
+    ex_tot = (cp + cm).reshape(nb, -1).sum(1)
+    se = np.sqrt(k2_tot + ex_tot)
+    assert (np.abs(k2_tot - ex_tot) < 5 * se + 0.02 * ex_tot).all(), (k2_tot, ex_tot)
+
+
+# ---------------------------------------------------------------- GPU ----------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("sigma", [None, 0.4, 5.0, 40.0])
+@pytest.mark.parametrize("tiles", [1, 3])
+def test_gpu_pass_equals_oracle_bitwise(sigma, tiles):
+    L = tiles * TILE
+    kw = dict(sigma_sites=sigma, seed=99, **PARAMS)
+    g = SublatticeLattice(L, **kw)
+    o = oracle_lattice(L, **kw)
+    g.init_random(0.55, 0.65)
+    o.init_random(0.55, 0.65)
+    assert np.array_equal(g.state.cpu().numpy(), o.state.numpy())       # init kernel == oracle init
+    assert g.n_particles == o.n_particles
+    for chunk in [1, 2, 7, 20]:
+        g.run_passes(chunk); o.run_passes(chunk)
+        assert np.array_equal(g.state.cpu().numpy(), o.state.numpy()), (sigma, tiles, chunk)
+    if sigma is None:
+        assert int(g.msum[0][0]) == int(o.msum[0][0])
+    gp, gm = g.profile(40)
+    op, om = o.profile(40)
+    assert np.array_equal(gp, op) and np.array_equal(gm, om)
+
+
+@pytest.mark.gpu
+def test_gpu_large_lattice_invariants():
+    """2^24 sites (16 MiB per buffer): conservation, exclusion and a flat interior profile at beta = 0."""
+    L = 1 << 24
+    lat = SublatticeLattice(L, D=0.02, lam=5.0, beta=0.0, dt=0.01, sigma_sites=5.0, seed=1)
+    lat.init_random(0.5, 0.5)
+    n0 = lat.n_particles
+    lat.run(50)
+    s = lat.state
+    assert int((s != 0).sum()) == n0 and int(s.max()) <= 2
+    rp, rm = lat.profile(64)
+    assert np.allclose((rp + rm)[4:-4], 0.5, atol=0.01)
