@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(CSRC, "libaps_b200.so")
-SOURCES = ["aps_capi.cu"]
+SOURCES = ["aps_capi.cu", "aps_fast.cu"]
 
 
 def nvcc_path() -> str:
@@ -33,14 +33,17 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
-    cmd = [
-        nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-        "--fmad=false", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-cudart", "static",
-        "-I", INCLUDE, "-o", OUT,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--fmad=false",
+             "-Xcompiler", "-fPIC,-ffp-contract=off", "-I", INCLUDE]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd, cwd=CSRC)
+        flags.insert(0, "-Xptxas=-v")
+    objs = [os.path.join(CSRC, s[:-3] + ".o") for s in SOURCES]
+    procs = [subprocess.Popen([nvcc_path()] + flags + ["-c", os.path.join(CSRC, s), "-o", o], cwd=CSRC)
+             for s, o in zip(SOURCES, objs)]          # translation units compile in parallel
+    if any(p.wait() != 0 for p in procs):
+        raise subprocess.CalledProcessError(1, "nvcc -c")
+    subprocess.check_call([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static",
+                           "-o", OUT] + objs, cwd=CSRC)
     return OUT
 
 

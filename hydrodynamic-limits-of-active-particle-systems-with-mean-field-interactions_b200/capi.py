@@ -149,6 +149,7 @@ SYMBOLS = {
     "aps_debug_set_guard_scale": (None, [C.c_double]),
     "aps_debug_set_k1_threads": (None, [C.c_int]),
     "aps_debug_set_use_lut": (None, [C.c_int]),
+    "aps_debug_set_use_fast": (None, [C.c_int]),
 }
 
 _lib = None

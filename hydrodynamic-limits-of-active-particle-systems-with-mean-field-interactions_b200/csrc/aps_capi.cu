@@ -14,6 +14,8 @@
 #include "aps_init.cuh"
 #include "aps_k2.cuh"
 
+namespace aps { cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched); }
+
 namespace {
 
 thread_local std::string g_err;
@@ -21,6 +23,7 @@ std::atomic<int64_t> g_launches{0};
 double g_guard_scale = 1.0;
 int g_k1_threads = 0;  // 0 = heuristic
 int g_use_lut = 1;
+int g_use_fast = 1;
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -110,6 +113,15 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     const size_t smem = aps::k1_smem_bytes(p->L, b->n_max, p->radius, a.max_nodes, nt / 32, a.use_lut, p->K);
     if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "replica does not fit in 227 KB of shared memory");
     cudaStream_t st = (cudaStream_t)stream;
+    a.only_retry = 0; a.reserved = 0;
+    // specialised kernel for K = 1 with a local field (every shipped sweep configuration)
+    const bool fast_ok = g_use_fast && p->K == 1 && p->radius >= 0 && p->radius < p->L && !(p->flags & APS_FLAG_CROWDING) &&
+                         !b->m_field_in && b->n_max <= 1024 && b->status != nullptr;
+    if (fast_ok) {
+        int launched = 0;
+        CU(aps::launch_fast(a, philox, st, g_use_fast == 1, nt, &launched));
+        if (launched) { g_launches.fetch_add(1); a.only_retry = 1; }   // 2nd launch: replicas violating K = 1 only
+    }
     switch (nt) {
         case 32: return launch_nt<32>(a, philox, smem, st);
         case 64: return launch_nt<64>(a, philox, smem, st);
@@ -385,5 +397,6 @@ int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset
 void aps_debug_set_guard_scale(double s) { g_guard_scale = s; }
 void aps_debug_set_k1_threads(int nt) { g_k1_threads = (nt == 32 || nt == 64 || nt == 128 || nt == 256) ? nt : 0; }
 void aps_debug_set_use_lut(int on) { g_use_lut = on ? 1 : 0; }
+void aps_debug_set_use_fast(int on) { g_use_fast = on; }   // 0 generic only, 1 capacity classes, 2 run-time layout
 
 }  // extern "C"

@@ -1,0 +1,48 @@
+// aps_fast.cu — instantiations and dispatch of the K = 1 specialised K1 kernel (aps_k1_fast.cuh).
+// Separate translation unit so that the two halves of the library compile in parallel.
+#include <cuda_runtime.h>
+
+#include "aps_k1_fast.cuh"
+
+namespace aps {
+
+template <int NT, int RCAP, int NCAP, int LPCAP>
+static cudaError_t launch_nt(const K1Args& a, bool philox, cudaStream_t st) {
+    const size_t smem = k1_fast_smem_bytes(a.p.L, a.b.n_max, a.p.radius, RCAP, NCAP, LPCAP);
+    if (philox) {
+        auto k = k1_fast_kernel<NT, true, RCAP, NCAP, LPCAP>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<a.b.n_replicas, NT, smem, st>>>(a);
+    } else {
+        auto k = k1_fast_kernel<NT, false, RCAP, NCAP, LPCAP>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<a.b.n_replicas, NT, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+static int g_fast_nt = 64;
+template <int RCAP, int NCAP, int LPCAP>
+static cudaError_t launch_class(const K1Args& a, bool philox, cudaStream_t st) {
+    return g_fast_nt == 32 ? launch_nt<32, RCAP, NCAP, LPCAP>(a, philox, st) : launch_nt<64, RCAP, NCAP, LPCAP>(a, philox, st);
+}
+
+// Returns cudaSuccess and *launched = 1 if a specialised kernel was enqueued; *launched = 0 if the
+// configuration does not qualify (the caller then uses the generic kernel only).
+cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched) {
+    *launched = 0;
+    g_fast_nt = nt == 32 ? 32 : 64;
+    const int r1 = a.p.radius + 1, nm = a.b.n_max, lp = a.p.L + 2 * a.p.radius;
+    if (k1_fast_smem_bytes(a.p.L, nm, a.p.radius, 0, 0, 0) > 227 * 1024) return cudaSuccess;
+    *launched = 1;
+    if (allow_static) {
+        if (r1 <= 21 && nm <= 512 && lp <= 1056) return launch_class<21, 512, 1056>(a, philox, st);
+        if (r1 <= 21 && nm <= 1024 && lp <= 1056) return launch_class<21, 1024, 1056>(a, philox, st);
+        if (r1 <= 81 && nm <= 512 && lp <= 1184) return launch_class<81, 512, 1184>(a, philox, st);
+        if (r1 <= 81 && nm <= 1024 && lp <= 1184) return launch_class<81, 1024, 1184>(a, philox, st);
+    }
+    return launch_class<0, 0, 0>(a, philox, st);
+}
+
+}  // namespace aps

@@ -43,6 +43,8 @@ struct K1Args {
     int32_t max_nodes;    // tree nodes the shared-memory plan reserves
     int32_t pad;          // halo width = max(radius, 0)
     int32_t use_lut;      // 1: filter taps come from the product table (see local_m_lut)
+    int32_t only_retry;   // 1: run only the replicas the fast kernel flagged (status == 100)
+    int32_t reserved;
     int32_t bcode;        // 2K+1: radix of the per-site code c_plus + bcode*c_minus
 };
 
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
     const aps_params& P = A.p;
     const aps_batch& B = A.b;
     const int rep = blockIdx.x;
+    if (A.only_retry && B.status[rep] != 100) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int L = P.L, pad = A.pad, r = P.radius, n_max = B.n_max, M = B.M;
     const bool crowd = (P.flags & APS_FLAG_CROWDING) != 0;
@@ -626,7 +629,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
 }
 
 // compute_local_m_field for one lattice (API parity entry; one CTA).
-__global__ void field_kernel(aps_params P, const double* __restrict__ weights, const int32_t* __restrict__ cp,
+static __global__ void field_kernel(aps_params P, const double* __restrict__ weights, const int32_t* __restrict__ cp,
                              const int32_t* __restrict__ cm, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char fk_raw[];
     const int L = P.L, r = P.radius, pad = r > 0 ? r : 0;

@@ -75,7 +75,7 @@ def expected_poisson_particles(rho_p, rho_m, K):
             cdf += pk
             pk *= l / (k + 1)
         mean += e + K * (1.0 - cdf)
-    return mean, int(math.ceil(mean + 8.0 * math.sqrt(max(mean, 1.0)) + 16))
+    return mean, int(math.ceil(mean + 6.5 * math.sqrt(max(mean, 1.0)) + 8))
 
 
 @dataclass

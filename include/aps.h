@@ -269,6 +269,7 @@ int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset
 void aps_debug_set_guard_scale(double scale);
 void aps_debug_set_k1_threads(int threads);
 void aps_debug_set_use_lut(int on); /* 0: evaluate filter taps arithmetically instead of by table */
+void aps_debug_set_use_fast(int on); /* 0: always use the generic K1 kernel (no K=1 specialisation) */
 
 #ifdef __cplusplus
 }

@@ -25,18 +25,23 @@ def run_gpu(lib, params, hr, philox=False):
     return hr
 
 
-@pytest.mark.parametrize("threads,use_lut", [(0, 1), (32, 1), (64, 0), (128, 1), (256, 0), (32, 0)])
+@pytest.mark.parametrize("threads,use_lut,use_fast", [(0, 1, 1), (0, 1, 2), (64, 0, 0), (128, 1, 0),
+                                                      (256, 0, 0), (32, 0, 0), (64, 1, 0)])
 @pytest.mark.parametrize("name", case_names())
-def test_replay_matches_reference_and_oracle(lib, name, threads, use_lut):
-    """Every block-size variant and both filter-tap paths (product table / arithmetic)."""
+def test_replay_matches_reference_and_oracle(lib, name, threads, use_lut, use_fast):
+    """Every block-size variant, both filter-tap paths (product table / arithmetic) of the generic kernel,
+    and the K=1 specialised kernel (taken by the K=1 local-field cases: use_fast=1 capacity-class layout,
+    use_fast=2 run-time layout)."""
     c = load_case(name)
     lib.aps_debug_set_k1_threads(threads)
     lib.aps_debug_set_use_lut(use_lut)
+    lib.aps_debug_set_use_fast(use_fast)
     try:
         g = run_gpu(lib, params_from_case(c), hostrun_from_case(c))
     finally:
         lib.aps_debug_set_k1_threads(0)
         lib.aps_debug_set_use_lut(1)
+        lib.aps_debug_set_use_fast(1)
     assert_matches_reference(c, g)
     o = run_oracle(params_from_case(c), hostrun_from_case(c))
     assert_same_outputs(g, o)
