@@ -86,10 +86,16 @@ __global__ void expand_kernel(aps_expand_args a) {
 // x_grid = np.linspace(0, 1, L): arange(L) * (1/(L-1)), last point forced to 1.0
 __device__ __forceinline__ double xgrid(int l, int L, double step) { return (l == L - 1 && L > 1) ? 1.0 : APS_MUL((double)l, step); }
 
-// One CTA per replica.  Shared: per-row scalars [M] x 4.
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One CTA per replica; every warp owns whole observation rows (lane-strided over the lattice, shuffle
+// reductions only), so the row loops run without block barriers.  Shared: per-row scalars [M] x 3.
 __global__ void reduce_kernel(aps_reduce_args a) {
     extern __shared__ double sh[];
-    const int rep = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+    const int rep = blockIdx.x, tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
     const int M = a.M, L = a.L, n = a.n[rep], nobs = a.n_obs[rep];
     double* mean_x = sh;            // [M]
     double* frac_b = sh + M;        // [M]
@@ -101,23 +107,23 @@ __global__ void reduce_kernel(aps_reduce_args a) {
     const double denom = APS_MUL((double)(n > 1 ? n : 1), a.dx);
 
     // ---- per-row sums over the lattice (rows never reached are all-zero in the reference) ----
-    for (int m = 0; m < M; ++m) {
-        double sx = 0.0; double st = 0.0, sb = 0.0;
+    for (int m = wid; m < M; m += NW) {
+        double sx = 0.0, st = 0.0, sb = 0.0;
         if (m < nobs) {
             const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
             const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
-            for (int l = tid; l < L; l += NT) {
-                int c = (int)cp[l] + (int)cm[l];
-                if (c) {
-                    double d = APS_ADD(APS_DIV((double)cp[l], denom), APS_DIV((double)cm[l], denom));
+            for (int l = lane; l < L; l += 32) {
+                const int p = cp[l], q = cm[l];
+                if (p | q) {
+                    double d = APS_ADD(APS_DIV((double)p, denom), APS_DIV((double)q, denom));
                     double x = xgrid(l, L, step);
                     st += d; sx += d * x;
                     if (x >= a.boundary_xmin) sb += d;
                 }
             }
         }
-        st = block_sum(st, scr); sx = block_sum(sx, scr); sb = block_sum(sb, scr);
-        if (tid == 0) {
+        st = warp_sum(st); sx = warp_sum(sx); sb = warp_sum(sb);
+        if (lane == 0) {
             double Nt = st * dxg;
             frac_b[m] = (sb * dxg) / (Nt + 1e-12);
             mean_x[m] = sx / (st + 1e-12);
@@ -137,107 +143,85 @@ __global__ void reduce_kernel(aps_reduce_args a) {
             if (end_idx - start_idx < min_len) end_idx = (start_idx + min_len < M) ? start_idx + min_len : M;
         }
     }
-    // ---- v_eff = np.gradient(mean_x, times) averaged over the window ----
+    const int wlen = end_idx - start_idx;
+    // ---- v_eff = np.gradient(mean_x, times) averaged over the window; mean magnetisation ----
     const double* t = a.times_obs;
     bool uniform = true;
     for (int m = 1; m + 1 < M; ++m) if ((t[m + 1] - t[m]) != (t[1] - t[0])) uniform = false;
-    double mean_v = 0.0;
-    {
-        double acc = 0.0; int cnt = 0;
-        for (int m = start_idx + tid; m < end_idx; m += NT) {
-            double g;
-            if (M < 2) g = 0.0;
-            else if (m == 0) g = (mean_x[1] - mean_x[0]) / (t[1] - t[0]);
-            else if (m == M - 1) g = (mean_x[M - 1] - mean_x[M - 2]) / (t[M - 1] - t[M - 2]);
-            else if (uniform) g = (mean_x[m + 1] - mean_x[m - 1]) / (2.0 * (t[1] - t[0]));
-            else {
-                double hd = t[m + 1] - t[m], hs = t[m] - t[m - 1];
-                double ca = -hd / (hs * (hd + hs)), cb = (hd - hs) / (hd * hs), cc = hs / (hd * (hd + hs));
-                g = ca * mean_x[m - 1] + cb * mean_x[m] + cc * mean_x[m + 1];
-            }
-            if (a.v_eff) a.v_eff[(size_t)rep * M + m] = g;
-            acc += g; ++cnt;
+    double acc_v = 0.0, acc_m = 0.0;
+    for (int m = start_idx + tid; m < end_idx; m += NT) {
+        double g;
+        if (M < 2) g = 0.0;
+        else if (m == 0) g = (mean_x[1] - mean_x[0]) / (t[1] - t[0]);
+        else if (m == M - 1) g = (mean_x[M - 1] - mean_x[M - 2]) / (t[M - 1] - t[M - 2]);
+        else if (uniform) g = (mean_x[m + 1] - mean_x[m - 1]) / (2.0 * (t[1] - t[0]));
+        else {
+            double hd = t[m + 1] - t[m], hs = t[m] - t[m - 1];
+            double ca = -hd / (hs * (hd + hs)), cb = (hd - hs) / (hd * hs), cc = hs / (hd * (hd + hs));
+            g = ca * mean_x[m - 1] + cb * mean_x[m] + cc * mean_x[m + 1];
         }
-        acc = block_sum(acc, scr);
-        int w = end_idx - start_idx;
-        mean_v = w > 0 ? acc / (double)w : 0.0;
+        if (a.v_eff) a.v_eff[(size_t)rep * M + m] = g;
+        acc_v += g;
+        acc_m += (m < nobs) ? (double)a.obs_sigma_sum[(size_t)rep * M + m] / (double)n : 0.0;
     }
-    // ---- mean magnetisation over the window ----
-    double m_mean;
-    {
-        double acc = 0.0;
-        for (int m = start_idx + tid; m < end_idx; m += NT)
-            acc += (m < nobs) ? (double)a.obs_sigma_sum[(size_t)rep * M + m] / (double)n : 0.0;
-        acc = block_sum(acc, scr);
-        int w = end_idx - start_idx;
-        m_mean = w > 0 ? acc / (double)w : 0.0;
-    }
-    // ---- rho_eff (front density) and blocking probability ----
-    double rho_eff, block;
-    {
-        double rsum = 0.0; int rcnt = 0;
-        double attempts = 0.0, blocked = 0.0;
-        for (int m = start_idx; m < end_idx; ++m) {
-            int jmax = -1;
-            double att = 0.0, blk = 0.0;
-            if (m < nobs) {
-                const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
-                const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
-                for (int l = tid; l < L; l += NT) {
-                    int c = (int)cp[l] + (int)cm[l];
-                    if (c > 0 && l > jmax) jmax = l;
-                    if (cp[l] > 0 && l + 1 < L) {
-                        double rp = APS_DIV((double)cp[l], denom);
-                        att += rp;
-                        double tn = APS_ADD(APS_DIV((double)cp[l + 1], denom), APS_DIV((double)cm[l + 1], denom));
-                        if (tn >= 1.0) blk += rp;
-                    }
-                }
-            }
-            for (int o = 16; o > 0; o >>= 1) { int v = __shfl_xor_sync(0xffffffffu, jmax, o); jmax = v > jmax ? v : jmax; }
-            __syncthreads();
-            if ((tid & 31) == 0) scr[tid >> 5] = (double)jmax;
-            __syncthreads();
-            for (int w = 0; w < (NT + 31) / 32; ++w) { int v = (int)scr[w]; jmax = v > jmax ? v : jmax; }
-            attempts += block_sum(att, scr); blocked += block_sum(blk, scr);
-            if (jmax >= 0) {
-                const double xmax = xgrid(jmax, L, step);
-                const double lo = xmax - a.window_fraction;
-                const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
-                const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
-                double s2 = 0.0; int inmask = 0;
-                for (int l = tid; l <= jmax; l += NT) {
-                    double x = xgrid(l, L, step);
-                    if (x >= lo && x <= xmax) {
-                        ++inmask;
-                        s2 += APS_ADD(APS_DIV((double)cp[l], denom), APS_DIV((double)cm[l], denom));
-                    }
-                }
-                s2 = block_sum(s2, scr);
-                rsum += s2 * dxg / a.window_fraction; ++rcnt;
+    acc_v = block_sum(acc_v, scr); acc_m = block_sum(acc_m, scr);
+    const double mean_v = wlen > 0 ? acc_v / (double)wlen : 0.0;
+    const double m_mean = wlen > 0 ? acc_m / (double)wlen : 0.0;
+
+    // ---- rho_eff (front density) and blocking probability: one warp per window row ----
+    double rsum = 0.0, rcnt = 0.0, attempts = 0.0, blocked = 0.0;
+    for (int m = start_idx + wid; m < end_idx; m += NW) {
+        if (m >= nobs) continue;
+        const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
+        const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
+        int jmax = -1;
+        double att = 0.0, blk = 0.0;
+        for (int l = lane; l < L; l += 32) {
+            const int p = cp[l], q = cm[l];
+            if ((p + q) > 0 && l > jmax) jmax = l;
+            if (p > 0 && l + 1 < L) {
+                double rp = APS_DIV((double)p, denom);
+                att += rp;
+                double tn = APS_ADD(APS_DIV((double)cp[l + 1], denom), APS_DIV((double)cm[l + 1], denom));
+                if (tn >= 1.0) blk += rp;
             }
         }
-        rho_eff = rcnt > 0 ? rsum / (double)rcnt : nan("");
-        block = attempts > 0.0 ? blocked / attempts : 0.0;
+        for (int o = 16; o > 0; o >>= 1) { int v = __shfl_xor_sync(0xffffffffu, jmax, o); jmax = v > jmax ? v : jmax; }
+        attempts += warp_sum(att); blocked += warp_sum(blk);
+        if (jmax >= 0) {
+            const double xmax = xgrid(jmax, L, step), lo = xmax - a.window_fraction;
+            double s2 = 0.0;
+            for (int l = lane; l <= jmax; l += 32) {
+                double x = xgrid(l, L, step);
+                if (x >= lo && x <= xmax) s2 += APS_ADD(APS_DIV((double)cp[l], denom), APS_DIV((double)cm[l], denom));
+            }
+            s2 = warp_sum(s2);
+            rsum += s2 * dxg / a.window_fraction; rcnt += 1.0;
+        }
     }
-    // ---- D_eff: slope of the per-particle MSD against time (np.polyfit degree 1) ----
+    // every lane of a warp holds the same partials: count each warp once
+    rsum = block_sum(lane == 0 ? rsum : 0.0, scr); rcnt = block_sum(lane == 0 ? rcnt : 0.0, scr);
+    attempts = block_sum(lane == 0 ? attempts : 0.0, scr); blocked = block_sum(lane == 0 ? blocked : 0.0, scr);
+    const double rho_eff = rcnt > 0.0 ? rsum / rcnt : nan("");
+    const double block = attempts > 0.0 ? blocked / attempts : 0.0;
+
+    // ---- D_eff: slope of the per-particle MSD against time (np.polyfit degree 1), one warp per row ----
     double d_eff = nan("");
-    if (a.obs_pos && end_idx - start_idx >= 3 && n >= 2 && nobs >= end_idx) {
+    if (a.obs_pos && wlen >= 3 && n >= 2 && nobs >= end_idx) {
         const int32_t* p0 = a.obs_pos + ((size_t)rep * M + start_idx) * a.n_max;
-        for (int k = start_idx + 1; k < end_idx; ++k) {
+        for (int k = start_idx + 1 + wid; k < end_idx; k += NW) {
             const int32_t* pk = a.obs_pos + ((size_t)rep * M + k) * a.n_max;
             double s1 = 0.0;
-            for (int i = tid; i < n; i += NT) s1 += (double)pk[i] * a.dx - (double)p0[i] * a.dx;
-            s1 = block_sum(s1, scr);
+            for (int i = lane; i < n; i += 32) s1 += (double)pk[i] * a.dx - (double)p0[i] * a.dx;
+            s1 = warp_sum(s1);
             const double rbar = s1 / (double)n;
             double s2 = 0.0;
-            for (int i = tid; i < n; i += NT) { double ri = ((double)pk[i] * a.dx - (double)p0[i] * a.dx) - rbar; s2 += ri * ri; }
-            s2 = block_sum(s2, scr);
-            if (tid == 0) aux[k] = s2 / (double)(n - 1);
+            for (int i = lane; i < n; i += 32) { double ri = ((double)pk[i] * a.dx - (double)p0[i] * a.dx) - rbar; s2 += ri * ri; }
+            s2 = warp_sum(s2);
+            if (lane == 0) aux[k] = s2 / (double)(n - 1);
         }
         __syncthreads();
-        // least squares of S against (t - t0), centred for conditioning
-        const int cnt = end_idx - start_idx - 1;
+        const int cnt = wlen - 1;
         double tb = 0.0, sb2 = 0.0;
         for (int k = start_idx + 1; k < end_idx; ++k) { tb += t[k] - t[start_idx]; sb2 += aux[k]; }
         tb /= cnt; sb2 /= cnt;

@@ -73,12 +73,12 @@ class CudaK2Backend:
 
 
 class SublatticeLattice:
-    def __init__(self, L, D, lam, beta, dt, sigma_sites=None, seed=0, backend=None, ghost=TILE):
+    def __init__(self, L, D, lam, beta, dt, sigma_sites=None, seed=0, backend=None, ghost=TILE, single_rank=False):
         if L % TILE:
             raise ValueError(f"L must be a multiple of {TILE}")
         self.be = backend or CudaK2Backend()
         self.L_global, self.dt, self.seed = int(L), float(dt), int(seed)
-        self.rank, self.world = dist_info()
+        self.rank, self.world = (0, 1) if single_rank else dist_info()
         tiles = L // TILE
         if tiles < self.world:
             raise ValueError("fewer tiles than ranks")
