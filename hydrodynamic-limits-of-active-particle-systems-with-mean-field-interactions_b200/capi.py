@@ -111,15 +111,15 @@ APS_K2_MAX_TRIALS = 64
 
 
 class ApsK2Rates(C.Structure):
-    _fields_ = [("t_left", C.c_uint32), ("t_right", C.c_uint32), ("t_active", C.c_uint32), ("_pad", C.c_uint32),
+    _fields_ = [("t_left", C.c_uint32), ("t_right", C.c_uint32), ("t_active", C.c_uint32), ("n_cdf", C.c_uint32),
                 ("inv_cmax", C.c_double), ("beta", C.c_double), ("mu", C.c_double),
-                ("cdf", C.c_double * APS_K2_MAX_TRIALS)]
+                ("cdf32", C.c_uint32 * APS_K2_MAX_TRIALS)]
 
 
 class ApsK2Args(C.Structure):
     _fields_ = [("L", C.c_int64), ("L_global", C.c_int64), ("global_offset", C.c_int64), ("n_particles", C.c_int64),
                 ("seed", C.c_uint64), ("pass_", C.c_uint64), ("radius", C.c_int32), ("reserved", C.c_int32),
-                ("rates", ApsK2Rates), ("w16", C.c_void_p), ("in_", C.c_void_p), ("out", C.c_void_p),
+                ("rates", ApsK2Rates), ("w16", C.c_void_p), ("flip_tab", C.c_void_p), ("in_", C.c_void_p), ("out", C.c_void_p),
                 ("msum_in", C.c_void_p), ("msum_out", C.c_void_p)]
 
 
@@ -142,6 +142,7 @@ SYMBOLS = {
     "aps_reduce_runs_device": (C.c_int, [_P(ApsReduceArgs), C.c_void_p]),
     "aps_profile_sums_device": (C.c_int, [_P(ApsProfileArgs), C.c_void_p]),
     "aps_k2_rates_init": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double, _P(ApsK2Rates)]),
+    "aps_k2_flip_table": (C.c_int, [C.c_double, C.c_void_p]),
     "aps_k2_pass_device": (C.c_int, [_P(ApsK2Args), C.c_void_p]),
     "aps_k2_run_device": (C.c_int, [_P(ApsK2Args), C.c_int, C.c_void_p]),
     "aps_k2_init_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_void_p]),
@@ -150,6 +151,7 @@ SYMBOLS = {
     "aps_debug_set_k1_threads": (None, [C.c_int]),
     "aps_debug_set_use_lut": (None, [C.c_int]),
     "aps_debug_set_use_fast": (None, [C.c_int]),
+    "aps_debug_set_k2_ctas_per_sm": (None, [C.c_int]),
 }
 
 _lib = None

@@ -24,6 +24,7 @@ double g_guard_scale = 1.0;
 int g_k1_threads = 0;  // 0 = heuristic
 int g_use_lut = 1;
 int g_use_fast = 1;
+int g_k2_ctas_per_sm = 6;
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -327,25 +328,43 @@ int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates
 }
 
 static size_t k2_smem(int radius) {
-    size_t work = (size_t)(aps::kK2Tile + 128 + ((aps::kK2Tile + 128) >> 6) * 4) + 16;
-    work = (work + 15) & ~(size_t)15;
-    if (radius < 0) return work;
-    return work + (size_t)((radius + 3) & ~3) + aps::kK2Tile + 32 + radius + 16;
+    const size_t WB = aps::kK2Tile + 32;
+    const size_t R16 = radius >= 0 ? (size_t)((radius + 15) & ~15) : 0;
+    const size_t stride = WB + (radius >= 0 ? WB + 2 * R16 : 0);
+    return 128 + (size_t)(radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal) * stride;
+}
+
+int aps_k2_flip_table(double beta, uint32_t* out) {
+    if (!out) return fail(APS_ERR_INVALID, "aps_k2_flip_table: null output");
+    const double cmax = aps_exp(beta < 0 ? -beta : beta), inv = 1.0 / cmax;
+    for (int sgi = 0; sgi < 2; ++sgi)
+        for (int i = 0; i <= 2 * APS_K2_MQ; ++i)
+            out[sgi * (2 * APS_K2_MQ + 1) + i] = aps_k2_flip_thr(beta, sgi == 0 ? 1 : -1, (double)(i - APS_K2_MQ) / (double)APS_K2_MQ, inv);
+    return APS_OK;
 }
 
 int aps_k2_pass_device(const aps_k2_args* a, void* stream) {
     if (!a || a->L < aps::kK2Tile || a->L % aps::kK2Tile || a->global_offset % aps::kK2Tile || !a->in || !a->out || a->in == a->out)
         return fail(APS_ERR_INVALID, "aps_k2_pass: L and global_offset must be multiples of 8192, in != out");
     if (a->radius > 1024) return fail(APS_ERR_INVALID, "aps_k2_pass: radius too large");
-    if (a->radius >= 0 && !a->w16) return fail(APS_ERR_INVALID, "aps_k2_pass: local field needs w16 taps");
+    if (a->radius >= 0 && (!a->w16 || !a->flip_tab)) return fail(APS_ERR_INVALID, "aps_k2_pass: local field needs w16 taps and flip_tab");
     if (a->radius < 0 && (!a->msum_in || a->n_particles < 1)) return fail(APS_ERR_INVALID, "aps_k2_pass: global field needs msum_in and n_particles");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
     const size_t smem = k2_smem(a->radius);
-    const int grid = (int)(a->L / aps::kK2Tile);
+    if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_k2_pass: radius too large for the shared-memory ring");
+    const int ntiles = (int)(a->L / aps::kK2Tile);
+    static int n_sm = 0;
+    if (!n_sm) { int dev = 0; CU(cudaGetDevice(&dev)); CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    int per_sm = (int)((size_t)(220 * 1024) / smem);
+    if (per_sm > g_k2_ctas_per_sm) per_sm = g_k2_ctas_per_sm;
+    if (per_sm < 1) per_sm = 1;
+    int grid = n_sm * per_sm;                       // persistent CTAs: a multiple of the SM count
+    if (grid > ntiles) grid = ntiles;
     if (a->radius >= 0) {
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::k2_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         aps::k2_pass_kernel<true><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a);
     } else {
+        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         aps::k2_pass_kernel<false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a);
     }
     CU(cudaGetLastError());
@@ -397,6 +416,7 @@ int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset
 void aps_debug_set_guard_scale(double s) { g_guard_scale = s; }
 void aps_debug_set_k1_threads(int nt) { g_k1_threads = (nt == 32 || nt == 64 || nt == 128 || nt == 256) ? nt : 0; }
 void aps_debug_set_use_lut(int on) { g_use_lut = on ? 1 : 0; }
+void aps_debug_set_k2_ctas_per_sm(int n) { g_k2_ctas_per_sm = n > 0 ? n : 6; }
 void aps_debug_set_use_fast(int on) { g_use_fast = on; }   // 0 generic only, 1 capacity classes, 2 run-time layout
 
 }  // extern "C"

@@ -23,7 +23,6 @@ constexpr int kK2Tile = 8192;                       // sites per CTA window
 constexpr int kK2Threads = kK2Tile / APS_K2_SEG;    // one thread per segment = 128
 constexpr int kK2Margin = APS_K2_HALF / 2;          // window shift: borders in the middle of inactive halves
 
-__device__ __forceinline__ int k2_pad(int p) { return p + (p >> 6) * 4; }   // one pad word per 64-site segment
 
 __device__ __forceinline__ long long k2_reflect(long long i, long long L) {
     long long per = 2 * L, m = i % per;
@@ -32,82 +31,137 @@ __device__ __forceinline__ long long k2_reflect(long long i, long long L) {
     return m;
 }
 
-// One pass.  LOCAL: Gaussian local field from the frozen snapshot; otherwise the global magnetisation.
+// ---- TMA (cp.async.bulk) + mbarrier helpers: 1-D bulk copies global <-> shared memory ----
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k2_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void k2_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k2_mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(k2_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void k2_tma_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(k2_smem_u32(dst)), "l"(src), "r"(bytes), "r"(k2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void k2_tma_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(k2_smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+
+constexpr int kK2StagesGlobal = 4;   // global field: copy-bound, deep prefetch
+constexpr int kK2StagesLocal = 2;    // local field: compute-bound, favour resident CTAs over prefetch depth
+
+// One pass, persistent CTAs.  Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through a
+// kK2Stages-deep ring of shared-memory buffers: TMA bulk loads (mbarrier complete_tx) bring the window
+// (and, for the local field, a second read-only copy with the +-r halo) in, the 128 threads run the
+// trials of their segments in place, and a TMA bulk store writes the window to the ping-pong buffer.
+// LOCAL: Gaussian local field from the frozen copy; otherwise the global magnetisation.
 template <bool LOCAL>
 __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_constant__ aps_k2_args a) {
-    extern __shared__ __align__(16) unsigned char k2_raw[];
+    extern __shared__ __align__(128) unsigned char k2_raw[];
     const int tid = threadIdx.x;
     const long long L = a.L;                         // sites held by this call (slab incl. ghosts)
     const int qpar = (int)(a.pass & 1ULL);           // parity; slabs start on tile boundaries, so it is global
     const int r = LOCAL ? a.radius : 0;
-    const long long t0 = (long long)blockIdx.x * kK2Tile;
+    const int R16 = LOCAL ? ((r + 15) & ~15) : 0;
     const int sh = qpar * APS_K2_HALF - kK2Margin;
-    long long lo = t0 + sh, hi = t0 + kK2Tile + sh;
-    if (blockIdx.x == 0) lo = 0;
-    if (blockIdx.x == gridDim.x - 1) hi = L;
-    // shared memory: work (padded, origin = t0 - 64), snap (unpadded, origin = lo - r)
-    unsigned char* work = k2_raw;
-    const int work_bytes = k2_pad(kK2Tile + 128) + 16;
-    unsigned char* snap = k2_raw + ((work_bytes + 15) & ~15);
+    const int ntiles = (int)(L / kK2Tile);
+    constexpr int WB = kK2Tile + 32;                 // largest window
+    constexpr int kK2Stages = LOCAL ? kK2StagesLocal : kK2StagesGlobal;
+    const int stride = WB + (LOCAL ? WB + 2 * R16 : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(k2_raw);
+    unsigned char* bufs = k2_raw + 128;
+    __shared__ uint32_t thr_glob[2];
     const uint8_t* __restrict__ in = a.in;
     uint8_t* __restrict__ out = a.out;
 
-    // ---- stage the window (16-byte vector loads; lo/hi are multiples of 16) ----
-    for (long long i = lo + 16LL * tid; i < hi; i += 16LL * kK2Threads) {
-        uint4 v = *reinterpret_cast<const uint4*>(in + i);
-        int p = (int)(i - t0) + 64;
-        uint32_t* w = reinterpret_cast<uint32_t*>(work + k2_pad(p));
-        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-        if (LOCAL) {
-            uint32_t* s4 = reinterpret_cast<uint32_t*>(snap + (i - lo) + ((r + 3) & ~3));
-            s4[0] = v.x; s4[1] = v.y; s4[2] = v.z; s4[3] = v.w;
-        }
-    }
-    if (LOCAL) {   // +-r halo of the frozen copy (reflect only at true walls; slab ends behave like walls)
-        const int ro = (r + 3) & ~3;
-        for (int j = tid; j < r; j += kK2Threads) {
-            snap[ro - 1 - j] = in[k2_reflect(lo - 1 - j, L)];
-            snap[ro + (hi - lo) + j] = in[k2_reflect(hi + j, L)];
+    if (tid == 0) {
+        for (int s2 = 0; s2 < kK2Stages; ++s2) k2_mbar_init(&bars[s2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (!LOCAL) {
+            const double m = APS_DIV((double)(*a.msum_in), (double)a.n_particles);
+            thr_glob[0] = aps_k2_flip_thr(a.rates.beta, +1, m, a.rates.inv_cmax);
+            thr_glob[1] = aps_k2_flip_thr(a.rates.beta, -1, m, a.rates.inv_cmax);
         }
     }
     __syncthreads();
 
-    // ---- trials of this thread's segment ----
-    const long long seg_local = (long long)blockIdx.x * kK2Threads + tid;          // segment index in this slab
-    const uint64_t seg_global = (uint64_t)(a.global_offset / APS_K2_SEG) + (uint64_t)seg_local;
+    auto window = [&](int t, long long& lo, long long& hi) {
+        lo = (long long)t * kK2Tile + sh; hi = lo + kK2Tile;
+        if (t == 0) lo = 0;
+        if (t == ntiles - 1) hi = L;
+    };
+    auto issue_load = [&](int t, int s2) {          // thread 0 only
+        long long lo, hi; window(t, lo, hi);
+        unsigned char* work = bufs + (size_t)s2 * stride;
+        uint32_t bytes = (uint32_t)(hi - lo);
+        long long slo = lo - R16, shi = hi + R16;
+        if (slo < 0) slo = 0;
+        if (shi > L) shi = L;
+        k2_mbar_expect_tx(&bars[s2], bytes + (LOCAL ? (uint32_t)(shi - slo) : 0u));
+        k2_tma_load(work, in + lo, bytes, &bars[s2]);
+        if (LOCAL) k2_tma_load(work + WB + (slo - (lo - R16)), in + slo, (uint32_t)(shi - slo), &bars[s2]);
+    };
+
+    const int my_first = blockIdx.x, step_t = gridDim.x;
+    if (tid == 0) {
+        for (int k = 0; k < kK2Stages - 1; ++k) { int t = my_first + k * step_t; if (t < ntiles) issue_load(t, k); }
+    }
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-    const uint32_t c0 = (uint32_t)seg_global, c1 = (uint32_t)a.pass;
-    const uint32_t chi = (uint32_t)(seg_global >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;   // folds high bits into word 3
-    const long long abase = t0 + (long long)tid * APS_K2_SEG + qpar * APS_K2_HALF;     // first active site (slab index)
     int dsig = 0;
-    if (abase + APS_K2_HALF <= L) {
-        aps_u32x4 pn = aps_philox4x32_10(c0, c1, 0xFFFFFFFFu, chi, k0, k1);
-        const double un = aps_u53(pn.v[0], pn.v[1]);
-        int ntr = 0;
-        while (ntr < APS_K2_MAX_TRIALS - 1 && un >= a.rates.cdf[ntr]) ++ntr;
-        const int pbase = (int)(abase - t0) + 64;      // padded-layout position of the first active site
-        const double mg = LOCAL ? 0.0 : APS_DIV((double)(*a.msum_in), (double)a.n_particles);
-        for (int pair = 0; 2 * pair < ntr; ++pair) {
-            aps_u32x4 w4 = aps_philox4x32_10(c0, c1, (uint32_t)pair, chi, k0, k1);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (2 * pair + h >= ntr) break;
-                const uint32_t wa = w4.v[2 * h], wb = w4.v[2 * h + 1];
+    int it = 0;
+    for (int t = my_first; t < ntiles; t += step_t, ++it) {
+        const int s2 = it % kK2Stages;
+        long long lo, hi; window(t, lo, hi);
+        unsigned char* work = bufs + (size_t)s2 * stride;
+        unsigned char* snap = work + WB;             // snap[i - (lo - R16)] = site i (LOCAL only)
+        k2_mbar_wait(&bars[s2], (uint32_t)((it / kK2Stages) & 1));
+        if (LOCAL && (t == 0 || t == ntiles - 1)) {   // reflect padding at the ends of this slab
+            for (int j = tid; j < r; j += kK2Threads) {
+                if (t == 0) snap[R16 - 1 - j] = snap[R16 + k2_reflect(-1 - j, L)];
+                if (t == ntiles - 1) snap[R16 + (L - lo) + j] = snap[R16 + (k2_reflect(L + j, L) - lo)];
+            }
+            __syncthreads();
+        }
+        // ---- trials of this thread's segment ----
+        const long long t0 = (long long)t * kK2Tile;
+        const long long seg_local = (long long)t * kK2Threads + tid;
+        const uint64_t seg_global = (uint64_t)(a.global_offset / APS_K2_SEG) + (uint64_t)seg_local;
+        const uint32_t c0 = (uint32_t)seg_global, c1 = (uint32_t)a.pass;
+        const uint32_t chi = (uint32_t)(seg_global >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
+        const long long abase = t0 + (long long)tid * APS_K2_SEG + qpar * APS_K2_HALF;     // first active site (slab index)
+        if (abase + APS_K2_HALF <= L) {
+            aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
+            int ntr = 0;
+            while (ntr < (int)a.rates.n_cdf && w4.v[0] >= a.rates.cdf32[ntr]) ++ntr;
+            unsigned char* act = work + (abase - lo);
+            for (int tr = 0; tr < ntr; ++tr) {
+                uint32_t wa, wb;
+                if (tr == 0) { wa = w4.v[2]; wb = w4.v[3]; }
+                else {
+                    if (tr & 1) w4 = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
+                    wa = (tr & 1) ? w4.v[0] : w4.v[2]; wb = (tr & 1) ? w4.v[1] : w4.v[3];
+                }
                 const int x = (int)(wa >> 27);
                 const uint32_t slot = wa << 5;
-                const int p = pbase + x;
-                const long long lx = abase + x;                        // slab-local site index (slab ends act as walls)
-                const unsigned char v = work[k2_pad(p)];
+                const long long lx = abase + x;
+                const unsigned char v = act[x];
                 if (v == APS_K2_EMPTY) continue;
                 if (slot < a.rates.t_left) {
-                    if (lx > 0 && work[k2_pad(p - 1)] == APS_K2_EMPTY) { work[k2_pad(p - 1)] = v; work[k2_pad(p)] = APS_K2_EMPTY; }
+                    if (lx > 0 && act[x - 1] == APS_K2_EMPTY) { act[x - 1] = v; act[x] = APS_K2_EMPTY; }
                 } else if (slot < a.rates.t_right || (slot < a.rates.t_active && v == APS_K2_PLUS)) {
-                    if (lx < L - 1 && work[k2_pad(p + 1)] == APS_K2_EMPTY) { work[k2_pad(p + 1)] = v; work[k2_pad(p)] = APS_K2_EMPTY; }
+                    if (lx < L - 1 && act[x + 1] == APS_K2_EMPTY) { act[x + 1] = v; act[x] = APS_K2_EMPTY; }
                 } else if (slot >= a.rates.t_active) {
                     const int sg = (v == APS_K2_PLUS) ? 1 : -1;
-                    double m;
+                    uint32_t thr;
                     if (LOCAL) {
-                        const unsigned char* c = snap + ((r + 3) & ~3) + (abase + x - lo);
+                        const unsigned char* c = snap + R16 + (lx - lo);
                         int sw, tw;
                         { const int cv = c[0]; const int wj = a.w16[0]; sw = wj * ((cv == APS_K2_PLUS) - (cv == APS_K2_MINUS)); tw = wj * (cv != 0); }
                         for (int j = 1; j <= r; ++j) {
@@ -115,25 +169,24 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
                             sw += wj * (((cl == APS_K2_PLUS) - (cl == APS_K2_MINUS)) + ((cr == APS_K2_PLUS) - (cr == APS_K2_MINUS)));
                             tw += wj * ((cl != 0) + (cr != 0));
                         }
-                        m = tw > 0 ? APS_DIV((double)sw, (double)tw) : 0.0;
-                    } else m = mg;
-                    const double cflip = aps_exp(APS_MUL(APS_MUL(-a.rates.beta, (double)sg), m));
-                    if (APS_MUL((double)wb, 2.3283064365386963e-10) < APS_MUL(cflip, a.rates.inv_cmax)) {
-                        work[k2_pad(p)] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS;
-                        dsig -= 2 * sg;
-                    }
+                        thr = a.flip_tab[(sg == 1 ? 0 : (2 * APS_K2_MQ + 1)) + aps_k2_mq_index(sw, tw)];
+                    } else thr = thr_glob[sg == 1 ? 0 : 1];
+                    if (wb < thr) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
                 }
             }
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
+        __syncthreads();
+        if (tid == 0) {
+            k2_tma_store(out + lo, work, (uint32_t)(hi - lo));
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the buffer used one iteration ago is free once its store has finished READING shared memory
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            const int tn = t + (kK2Stages - 1) * step_t;
+            if (tn < ntiles) issue_load(tn, (it + kK2Stages - 1) % kK2Stages);
+        }
     }
-    __syncthreads();
-
-    // ---- write the window back ----
-    for (long long i = lo + 16LL * tid; i < hi; i += 16LL * kK2Threads) {
-        int p = (int)(i - t0) + 64;
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(work + k2_pad(p));
-        *reinterpret_cast<uint4*>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (a.msum_out) {   // running sum(sigma) for the global magnetisation of the next pass
         for (int o = 16; o > 0; o >>= 1) dsig += __shfl_xor_sync(0xffffffffu, dsig, o);
         if ((tid & 31) == 0 && dsig != 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.msum_out), (unsigned long long)(long long)dsig);

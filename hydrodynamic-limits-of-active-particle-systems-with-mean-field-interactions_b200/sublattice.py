@@ -55,6 +55,11 @@ class CudaK2Backend:
         capi.check(self.lib.aps_k2_rates_init(D, lam, beta, dt, r), "aps_k2_rates_init")
         return r
 
+    def flip_table(self, beta):
+        t = np.zeros(2 * 1025, np.uint32)
+        capi.check(self.lib.aps_k2_flip_table(beta, t.ctypes.data), "aps_k2_flip_table")
+        return torch.from_numpy(t.view(np.int32).copy()).to(self.dev)
+
     def run(self, args, n_passes):
         capi.check(self.lib.aps_k2_run_device(args, n_passes, torch.cuda.current_stream().cuda_stream), "aps_k2_run_device")
 
@@ -98,6 +103,7 @@ class SublatticeLattice:
         else:
             self.radius, w = fixed_point_taps(sigma_sites)
             self.w16 = self.be.from_numpy(w)
+        self.flip_tab = self.be.flip_table(float(beta)) if self.radius >= 0 else None
         self.rates = self.be.rates(float(D), float(lam), float(beta), float(dt))
         self.buf = [self.be.zeros_u8(self.L), self.be.zeros_u8(self.L)]
         self.cur = 0
@@ -144,6 +150,7 @@ class SublatticeLattice:
         a.seed, a.pass_, a.radius = self.seed, self.passes_done, self.radius
         a.rates = self.rates
         a.w16 = self.be.ptr(self.w16) if self.w16 is not None else None
+        a.flip_tab = self.be.ptr(self.flip_tab) if self.flip_tab is not None else None
         a.in_, a.out = self.be.ptr(self.buf[self.cur]), self.be.ptr(self.buf[1 - self.cur])
         a.msum_in, a.msum_out = self.be.ptr(self.msum[0]), self.be.ptr(self.msum[1])
         return a

@@ -245,6 +245,7 @@ typedef struct aps_k2_args {
     int32_t reserved;
     aps_k2_rates rates;         /* aps_k2_make_rates(D, lambda, beta, dt)                            */
     const int32_t* w16;         /* [radius+1] taps round(w_j * 65536), centre first (device)         */
+    const uint32_t* flip_tab;   /* local field: [2][2*512+1] acceptance thresholds (aps_k2_flip_table) */
     const uint8_t* in;          /* [L] site bytes 0/1/2                                              */
     uint8_t* out;               /* [L] ping-pong target                                              */
     const int64_t* msum_in;     /* global-field mode: sum(sigma) at pass start (device)             */
@@ -252,6 +253,8 @@ typedef struct aps_k2_args {
 } aps_k2_args;
 /* thresholds / Poisson table for (D, lambda, beta, dt); returns non-zero if B*32*dt is out of (0, 24] */
 int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates* out);
+/* local-field acceptance thresholds: out[s][i] for sigma = +1 (s=0) / -1 (s=1) and m = (i-512)/512; host buffer of 2*1025 */
+int aps_k2_flip_table(double beta, uint32_t* out);
 /* one pass (in -> out) */
 int aps_k2_pass_device(const aps_k2_args* a, void* stream);
 /* n_passes passes ping-ponging between a->in and a->out (a->pass, in/out and msum are advanced in the
@@ -269,6 +272,7 @@ int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset
 void aps_debug_set_guard_scale(double scale);
 void aps_debug_set_k1_threads(int threads);
 void aps_debug_set_use_lut(int on); /* 0: evaluate filter taps arithmetically instead of by table */
+void aps_debug_set_k2_ctas_per_sm(int n); /* persistent K2 CTAs per SM (default 6) */
 void aps_debug_set_use_fast(int on); /* 0: always use the generic K1 kernel (no K=1 specialisation) */
 
 #ifdef __cplusplus

@@ -14,10 +14,15 @@
  *     of the rate slots [0,D) hop left, [D,2D) hop right, [2D,2D+lambda) active hop (sigma=+1),
  *     [2D+lambda, B) flip accepted with probability exp(-beta*sigma*m)/exp(beta), B = 2D+lambda+exp(beta);
  *   - the magnetisation m is frozen at the start of the pass: global (sum sigma / N) or local with
- *     integer (2^-16 fixed-point) Gaussian taps over +-r sites with reflect padding at the walls;
+ *     integer (2^-16 fixed-point) Gaussian taps over +-r sites with reflect padding at the walls, the
+ *     local value being quantised to 1/512 so that the acceptance threshold is a table lookup;
+ *   - every decision is an integer comparison of a 32-bit Philox word with a precomputed threshold;
  *   - two passes (q = 0, 1) advance every particle by dt.
  * Site encoding (one byte per site): 0 empty, 1 = '+', 2 = '-'.
- * Random numbers: Philox4x32-10, key = seed, counter = (segment, pass, trial pair, APS_RNG_SUBLATTICE).
+ * Random numbers: Philox4x32-10, key = seed, counter = (segment, pass, call, APS_RNG_SUBLATTICE):
+ * call 0 -> word 0: Poisson trial count, words 2,3: trial 0; call c >= 1 -> words (0,1): trial 2c-1,
+ * words (2,3): trial 2c.  In a trial the first word gives site (top 5 bits) and rate slot, the second
+ * the flip acceptance.
  */
 #ifndef APS_K2_MODEL_H
 #define APS_K2_MODEL_H
@@ -32,13 +37,32 @@
 #define APS_K2_MINUS 2
 #define APS_K2_MAX_TRIALS 64
 
+#define APS_K2_MQ 512                   /* local field is quantised to multiples of 1/512 for the flip table */
+
 typedef struct aps_k2_rates {
     uint32_t t_left, t_right, t_active; /* cumulative 32-bit thresholds of the rate slots           */
-    double inv_cmax;                    /* exp(-beta)                                               */
+    uint32_t n_cdf;                     /* entries of cdf32 in use                                  */
+    double inv_cmax;                    /* exp(-|beta|)                                             */
     double beta;
     double mu;                          /* B*H*dt, mean trials per active half per pass             */
-    double cdf[APS_K2_MAX_TRIALS];      /* Poisson(mu) cdf for inversion                            */
+    uint32_t cdf32[APS_K2_MAX_TRIALS];  /* floor(2^32 * Poisson(mu) cdf): n = #{k : w >= cdf32[k]}   */
 } aps_k2_rates;
+
+/* 32-bit acceptance threshold of a flip with rate c = exp(-beta*sigma*m): accept iff word < thr */
+APS_HD uint32_t aps_k2_flip_thr(double beta, int sigma, double m, double inv_cmax) {
+    double c = aps_exp(APS_MUL(APS_MUL(-beta, (double)sigma), m));
+    double v = APS_MUL(APS_MUL(c, inv_cmax), 4294967296.0);
+    return v >= 4294967295.0 ? 4294967295u : (uint32_t)v;
+}
+/* quantised local field index in [0, 2*MQ]: round(MQ * sw / tw) + MQ (half away from zero), integer only */
+APS_HD int aps_k2_mq_index(int sw, int tw) {
+    if (tw <= 0) return APS_K2_MQ;
+    long long num = (long long)sw * APS_K2_MQ;
+    long long q = (num >= 0 ? num + tw / 2 : num - tw / 2) / tw;
+    if (q < -APS_K2_MQ) q = -APS_K2_MQ;
+    if (q > APS_K2_MQ) q = APS_K2_MQ;
+    return (int)q + APS_K2_MQ;
+}
 
 /* Host-side (and oracle) construction of the thresholds; plain double arithmetic, done once. */
 static inline int aps_k2_make_rates(double D, double lam, double beta, double dt, aps_k2_rates* r) {
@@ -54,11 +78,15 @@ static inline int aps_k2_make_rates(double D, double lam, double beta, double dt
     r->mu = B * (double)APS_K2_HALF * dt;
     if (!(r->mu > 0.0) || r->mu > 24.0) return -1;   /* keep the truncated Poisson tail < 1e-10 */
     double p = aps_exp(-r->mu), F = p;
+    r->n_cdf = 0;
     for (int k = 0; k < APS_K2_MAX_TRIALS; ++k) {
-        r->cdf[k] = F;
+        double v = F * two32;
+        r->cdf32[k] = v >= 4294967295.0 ? 4294967295u : (uint32_t)v;
+        if (r->cdf32[k] < 4294967295u) r->n_cdf = (uint32_t)(k + 1);
         p = p * r->mu / (double)(k + 1);
         F += p;
     }
+    if (r->n_cdf >= APS_K2_MAX_TRIALS) r->n_cdf = APS_K2_MAX_TRIALS - 1;
     return 0;
 }
 

@@ -419,20 +419,28 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
     memcpy(out, in, (size_t)L);
     const uint32_t k0 = (uint32_t)a->seed, k1 = (uint32_t)(a->seed >> 32);
     long long dsig = 0;
-    const double mg = r < 0 ? (double)(*a->msum_in) / (double)a->n_particles : 0.0;
+    uint32_t thr_glob[2] = {0, 0};
+    if (r < 0) {
+        const double m = (double)(*a->msum_in) / (double)a->n_particles;
+        thr_glob[0] = aps_k2_flip_thr(a->rates.beta, +1, m, a->rates.inv_cmax);
+        thr_glob[1] = aps_k2_flip_thr(a->rates.beta, -1, m, a->rates.inv_cmax);
+    }
     for (long long seg = 0; seg * APS_K2_SEG < L; ++seg) {
         const long long abase = seg * APS_K2_SEG + q * APS_K2_HALF;
         if (abase + APS_K2_HALF > L) continue;
         const uint64_t sg64 = (uint64_t)(a->global_offset / APS_K2_SEG) + (uint64_t)seg;
         const uint32_t c0 = (uint32_t)sg64, c1 = (uint32_t)a->pass;
         const uint32_t chi = (uint32_t)(sg64 >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
-        aps_u32x4 pn = aps_philox4x32_10(c0, c1, 0xFFFFFFFFu, chi, k0, k1);
-        const double un = aps_u53(pn.v[0], pn.v[1]);
+        aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
         int ntr = 0;
-        while (ntr < APS_K2_MAX_TRIALS - 1 && un >= a->rates.cdf[ntr]) ++ntr;
+        while (ntr < (int)a->rates.n_cdf && w4.v[0] >= a->rates.cdf32[ntr]) ++ntr;
         for (int t = 0; t < ntr; ++t) {
-            aps_u32x4 w4 = aps_philox4x32_10(c0, c1, (uint32_t)(t / 2), chi, k0, k1);
-            const uint32_t wa = w4.v[2 * (t & 1)], wb = w4.v[2 * (t & 1) + 1];
+            uint32_t wa, wb;
+            if (t == 0) { wa = w4.v[2]; wb = w4.v[3]; }
+            else {
+                aps_u32x4 c4 = aps_philox4x32_10(c0, c1, (uint32_t)((t + 1) >> 1), chi, k0, k1);
+                wa = (t & 1) ? c4.v[0] : c4.v[2]; wb = (t & 1) ? c4.v[1] : c4.v[3];
+            }
             const long long x = abase + (long long)(wa >> 27);
             const uint32_t slot = wa << 5;
             const uint8_t v = out[x];
@@ -443,7 +451,7 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
                 if (x < L - 1 && out[x + 1] == APS_K2_EMPTY) { out[x + 1] = v; out[x] = APS_K2_EMPTY; }
             } else if (slot >= a->rates.t_active) {
                 const int sg = (v == APS_K2_PLUS) ? 1 : -1;
-                double m;
+                uint32_t thr;
                 if (r >= 0) {
                     int sw = 0, tw = 0;
                     for (int j = -r; j <= r; ++j) {
@@ -452,13 +460,9 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
                         sw += wj * ((cv == APS_K2_PLUS) - (cv == APS_K2_MINUS));
                         tw += wj * (cv != 0);
                     }
-                    m = tw > 0 ? (double)sw / (double)tw : 0.0;
-                } else m = mg;
-                const double cflip = aps_exp(((-a->rates.beta) * (double)sg) * m);
-                if ((double)wb * 2.3283064365386963e-10 < cflip * a->rates.inv_cmax) {
-                    out[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS;
-                    dsig -= 2 * sg;
-                }
+                    thr = a->flip_tab[(sg == 1 ? 0 : (2 * APS_K2_MQ + 1)) + aps_k2_mq_index(sw, tw)];
+                } else thr = thr_glob[sg == 1 ? 0 : 1];
+                if (wb < thr) { out[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
             }
         }
     }
@@ -479,6 +483,13 @@ int aps_oracle_k2_run(aps_k2_args* a, int n_passes) {
 
 int aps_oracle_k2_rates(double D, double lam, double beta, double dt, aps_k2_rates* out) {
     return aps_k2_make_rates(D, lam, beta, dt, out);
+}
+
+void aps_oracle_k2_flip_table(double beta, uint32_t* out) {
+    const double cmax = aps_exp(beta < 0 ? -beta : beta), inv = 1.0 / cmax;
+    for (int sgi = 0; sgi < 2; ++sgi)
+        for (int i = 0; i <= 2 * APS_K2_MQ; ++i)
+            out[sgi * (2 * APS_K2_MQ + 1) + i] = aps_k2_flip_thr(beta, sgi == 0 ? 1 : -1, (double)(i - APS_K2_MQ) / (double)APS_K2_MQ, inv);
 }
 
 void aps_oracle_k2_init(uint8_t* state, int64_t L, int64_t global_offset, uint64_t seed, double density, double frac_plus) {
