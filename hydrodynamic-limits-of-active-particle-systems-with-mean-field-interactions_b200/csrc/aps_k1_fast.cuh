@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
         accslot[i] = (uint8_t)((lf << 3) | (body ? (j & 7) : 0) | (body ? 0 : 0x80));
     }
     const int nnodes = F.desc[D_NNODES], nleaf = F.desc[12], maxlev = F.desc[13];
-    int cs_shift = 3;
-    while (((n + (1 << cs_shift) - 1) >> cs_shift) > NT) ++cs_shift;
+    int cs_shift = STATIC ? (NCAP <= 256 ? 3 : NCAP <= 512 ? 4 : 5) : 3;
+    while (((n + (1 << cs_shift) - 1) >> cs_shift) > 32) ++cs_shift;     // at most one chunk per lane of the selection warp
     const int CS = 1 << cs_shift;
     const int nchunks = (n + CS - 1) >> cs_shift;
 
@@ -299,56 +299,6 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
         if (avail < 3) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
         const int seq = (int)(n_done & 0x3fffffff) + 1;
 
-        // ---- A1: refresh dirty chunk sums / pairwise accumulators, scan the chunk sums ----
-        double cs = 0.0;
-        const int c0 = tid << cs_shift;
-        if (tid < nchunks) {
-            if (F.dirty_c[tid]) {
-                const int hi_i = (c0 + CS < n) ? c0 + CS : n;
-                for (int i = c0; i < hi_i; ++i) cs = APS_ADD(cs, rates[i]);
-                F.csum[tid] = cs; F.dirty_c[tid] = 0;
-            } else cs = F.csum[tid];
-        }
-        double incl = cs;
-        for (int o = 1; o < 32; o <<= 1) {
-            double up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl = APS_ADD(incl, up);
-        }
-        double prev = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) prev = 0.0;
-        if (lane == 31) F.wtot[wid] = incl;
-        for (int g = tid >> 3; g < nleaf; g += NT / 8) {
-            if (!F.dirty_leaf[g]) continue;                       // uniform within the 8-lane group
-            const unsigned gmask = 0xffu << (lane & 24);
-            const int k = tid & 7, start = F.leaf_start[g], len = F.leaf_len[g];
-            double res;
-            if (len < 8) {
-                res = 0.0;
-                for (int i = 0; i < len; ++i) res = APS_ADD(res, rates[start + i]);
-            } else {
-                const int body = len - (len & 7);
-                double acc;
-                if (F.dirty_a[g * 8 + k]) {
-                    acc = rates[start + k];
-                    for (int i = 8; i < body; i += 8) acc = APS_ADD(acc, rates[start + i + k]);
-                    F.acc[g * 8 + k] = acc; F.dirty_a[g * 8 + k] = 0;
-                } else acc = F.acc[g * 8 + k];
-                acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 1));
-                acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 2));
-                acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 4));
-                res = acc;
-                for (int i = body; i < len; ++i) res = APS_ADD(res, rates[start + i]);
-            }
-            __syncwarp(gmask);
-            if (k == 0) { F.leafsum[g] = res; F.dirty_leaf[g] = 0; }
-        }
-        bsync<NT>();  // BAR1
-
-        // ---- A2: winner picks + applies the event; last warp combines the tree and advances the clock ----
-        double base = 0.0, atot = 0.0;
-        for (int w2 = 0; w2 < NW; ++w2) { if (w2 == wid) base = atot; atot = APS_ADD(atot, F.wtot[w2]); }
-        const double target = APS_MUL(uc, atot);
-        const double excl = APS_ADD(base, prev), inc2 = APS_ADD(base, incl);
         auto decode_apply = [&](int sel) {
             const int p = pos[sel], sg = sigma[sel];
             double rl, rr, ra;
@@ -374,22 +324,85 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
             F.desc[D_PART] = sel; F.desc[D_KIND] = kind; F.desc[D_OLD] = p; F.desc[D_NEW] = newp;
             F.desc[D_STOP] = 0; F.desc[D_SEQ] = seq;
         };
-        if (excl <= target && target < inc2 && tid < nchunks) {
-            double run = 0.0, lo = excl, hi = excl; int sel = -1;
-            for (int j = 0; j < CS; ++j) {
-                const int i = c0 + j; if (i >= n) break;
-                run = APS_ADD(run, rates[i]);
-                const bool last = (j == CS - 1) || (i == n - 1);
-                hi = last ? inc2 : APS_ADD(base, APS_ADD(prev, run));
-                if (target < hi) { sel = i; break; }
-                lo = hi;
+
+        // ---- warp 0 = SELECTION warp: chunk sums (<= 32 chunks, dirty ones re-summed), warp scan, cooperative
+        //      walk of the winning chunk, event decode + apply.  The prefix sums are an approximation of the
+        //      reference's serial cumsum in any association; the guard band below makes the decision exact. ----
+        if (wid == 0) {
+            double cs = 0.0;
+            if (lane < nchunks) {
+                if (F.dirty_c[lane]) {
+                    const int c0 = lane << cs_shift;
+                    const int hi_i = (c0 + CS < n) ? c0 + CS : n;
+                    for (int i = c0; i < hi_i; ++i) cs = APS_ADD(cs, rates[i]);
+                    F.csum[lane] = cs; F.dirty_c[lane] = 0;
+                } else cs = F.csum[lane];
             }
-            const double band = APS_MUL(guard, atot);
-            if (sel < 0 || (target - lo) < band || (hi - target) < band) F.desc[D_EXACT] = 1;
-            else decode_apply(sel);
+            double incl = cs;
+            for (int o = 1; o < 32; o <<= 1) {
+                double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = APS_ADD(incl, up);
+            }
+            double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) prev = 0.0;
+            const double atot = __shfl_sync(0xffffffffu, incl, 31);
+            const double target = APS_MUL(uc, atot);
+            const unsigned wmask = __ballot_sync(0xffffffffu, lane < nchunks && prev <= target && target < incl);
+            bool exact = (__popc(wmask) != 1);
+            if (!exact) {
+                const int wl = __ffs(wmask) - 1;
+                const double prev_w = __shfl_sync(0xffffffffu, prev, wl), inc_w = __shfl_sync(0xffffffffu, incl, wl);
+                const int i = (wl << cs_shift) + lane;
+                const bool mine = lane < CS && i < n;
+                double run = mine ? rates[i] : 0.0;
+                for (int o = 1; o < CS; o <<= 1) {
+                    double up = __shfl_up_sync(0xffffffffu, run, o);
+                    if (lane >= o) run = APS_ADD(run, up);
+                }
+                const bool last = mine && (lane == CS - 1 || i == n - 1);
+                const double hi = last ? inc_w : APS_ADD(prev_w, run);
+                double lo = __shfl_up_sync(0xffffffffu, hi, 1);
+                if (lane == 0) lo = prev_w;
+                const unsigned smask = __ballot_sync(0xffffffffu, mine && lo <= target && target < hi);
+                if (__popc(smask) != 1) exact = true;
+                else if (lane == __ffs(smask) - 1) {
+                    const double band = APS_MUL(guard, atot);
+                    if ((target - lo) < band || (hi - target) < band) F.desc[D_EXACT] = 1;
+                    else decode_apply(i);
+                }
+            }
+            if (exact && lane == 0) F.desc[D_EXACT] = 1;
         }
+        // ---- last warp = CLOCK warp: numpy's pairwise sum exactly (dirty accumulators re-summed, 8 lanes per
+        //      leaf, level-synchronous tree), R, tau, the event clock and the observation-crossing count ----
         if (wid == NW - 1) {
-            // level-synchronous evaluation of numpy's pairwise tree: lane g holds node g
+            for (int g = lane >> 3; g < nleaf; g += 4) {
+                if (!F.dirty_leaf[g]) continue;                       // uniform within the 8-lane group
+                const unsigned gmask = 0xffu << (lane & 24);
+                const int k = lane & 7, start = F.leaf_start[g], len = F.leaf_len[g];
+                double res;
+                if (len < 8) {
+                    res = 0.0;
+                    for (int i = 0; i < len; ++i) res = APS_ADD(res, rates[start + i]);
+                } else {
+                    const int body = len - (len & 7);
+                    double acc;
+                    if (F.dirty_a[g * 8 + k]) {
+                        acc = rates[start + k];
+                        for (int i = 8; i < body; i += 8) acc = APS_ADD(acc, rates[start + i + k]);
+                        F.acc[g * 8 + k] = acc; F.dirty_a[g * 8 + k] = 0;
+                    } else acc = F.acc[g * 8 + k];
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 1));
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 2));
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 4));
+                    res = acc;
+                    for (int i = body; i < len; ++i) res = APS_ADD(res, rates[start + i]);
+                }
+                __syncwarp(gmask);
+                if (k == 0) { F.leafsum[g] = res; F.dirty_leaf[g] = 0; }
+            }
+            __syncwarp();
+            // level-synchronous evaluation of the tree: lane g holds node g
             const bool have = lane < nnodes;
             const int kd = have ? F.node_kind[lane] : 0, lv = have ? F.node_level[lane] : -1;
             const int ca = (have && kd) ? F.node_a[lane] : 0, cb = (have && kd) ? F.node_b[lane] : 0;
@@ -475,7 +488,9 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
         int wlo = mn - reach, whi = mx + reach;
         if (wlo < 0) wlo = 0;
         if (whi > L - 1) whi = L - 1;
-        constexpr int NB = NW < 2 ? 1 : 2;
+        // narrow windows (<= 64 sites, i.e. r <= 30) are handled by warp 0 alone: one compaction, dense lanes;
+        // wide windows are compacted by both warps, which then take alternate 32-particle blocks
+        const int NB = (NW > 1 && whi - wlo + 1 > 64) ? 2 : 1;
         if (wid < NB) {
             int count = 0, done = 0;
             uint16_t* lst = F.list[wid];
