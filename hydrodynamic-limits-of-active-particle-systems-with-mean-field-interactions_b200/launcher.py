@@ -322,3 +322,98 @@ def init_distributed_from_env():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.distributed.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
     return int(os.environ.get("RANK", "0")), world
+
+
+# ---- (N_part, beta) double sweep: ..._double_sweep.py:851-873 -------------------------------------
+def build_double_sweep_spec(n_part_values, beta_values, n_runs, ps_kwargs, run_kwargs, frac_plus=0.75, decay_plus=0.2,
+                            decay_minus=0.2, base_seed=0):
+    """Grid points ordered N_part-major, beta-minor (the order of the reference's nested loops); every
+    density gets its own Poisson intensity profile (make_exp_gradient with N = N_part)."""
+    n_part_values = [int(v) for v in n_part_values]
+    nb = len(beta_values)
+    L = int(ps_kwargs["L"])
+    prof_p = np.stack([make_exp_gradient(L=L, N=N, frac_plus=frac_plus, decay_length=decay_plus, anchor_positions=None)[2]
+                       for N in n_part_values])
+    prof_m = np.stack([make_exp_gradient(L=L, N=N, frac_plus=frac_plus, decay_length=decay_minus, anchor_positions=None)[3]
+                       for N in n_part_values])
+    point = np.arange(len(n_part_values) * nb)
+    betas = np.repeat(np.tile(np.asarray(beta_values, dtype=float), len(n_part_values)), n_runs)
+    point_of = np.repeat(point, n_runs)
+    profile_of = np.repeat(np.repeat(np.arange(len(n_part_values)), nb), n_runs).astype(np.int32)
+    run_idx = np.tile(np.arange(n_runs), len(point))
+    seeds = np.uint64(base_seed) + np.uint64(10_000) * point_of.astype(np.uint64) + run_idx.astype(np.uint64)
+    ps = dict(ps_kwargs, init="poisson")
+    return EnsembleSpec(ps_kwargs=ps, run_kwargs=dict(run_kwargs), betas=betas, point_of=point_of, seeds=seeds,
+                        profiles_plus=prof_p, profiles_minus=prof_m, profile_of=profile_of)
+
+
+def double_sweep(n_part_values, beta_values, n_runs, ps_kwargs, run_kwargs, **kw):
+    """Returns {N_part: dict like sweep_over_betas' save_dict} for every density of the grid."""
+    spec = build_double_sweep_spec(n_part_values, beta_values, n_runs, ps_kwargs, run_kwargs, **kw)
+    res = run_ensemble(spec, want_profiles=False)
+    nb = len(beta_values)
+    red = res.reducers.reshape(len(n_part_values), nb, n_runs, APS_RED_N)
+    out = {}
+    for i, N in enumerate(n_part_values):
+        d = dict(beta_values=np.asarray(beta_values, dtype=float))
+        for stem, col in [("", capi.APS_RED_V_EFF), ("D_", capi.APS_RED_D_EFF), ("m_", capi.APS_RED_M_MEAN),
+                          ("rho_", capi.APS_RED_RHO_EFF), ("block_", capi.APS_RED_BLOCK)]:
+            stats = [_mean_std_se(red[i, b, :, col]) for b in range(nb)]
+            d[stem + "means"] = np.array([s[0] for s in stats])
+            d[stem + "stds"] = np.array([s[1] for s in stats])
+            d[stem + "ses"] = np.array([s[2] for s in stats])
+        out[int(N)] = d
+    out["info"] = res.info
+    return out
+
+
+# ---- structure observables: PARTICLE_solver_BIOLOGY_local_structure.py:55-193 -----------------------
+def structure_observables(rb: ReplicaBatch, start_fraction=0.5, k_max=None):
+    """extract_structure_observables_from_out (local_structure.py:55-103) for every replica of a batch, on
+    the device: density rows and np.var by the K4 expansion kernel, |FFT| by cuFFT (torch.fft), the row
+    statistics by torch reductions.  Returns a dict of device tensors with a leading replica axis."""
+    rho_p, rho_m, total, var = rb.expand(want_var=True)
+    M = rb.M
+    s = int(start_fraction * M)
+    amp = torch.fft.fft(total, dim=-1).abs()                          # [R][M][L]
+    if k_max is not None:
+        amp = amp[:, :, :k_max]
+    fft_mean = amp[:, s:].mean(dim=1)
+    fft_std = amp[:, s:].std(dim=1, unbiased=True)
+    k_cut = min(25, fft_mean.shape[1])
+    out = dict(var_mean=var[:, s:].mean(dim=1), var_std=var[:, s:].std(dim=1, unbiased=True), fft_mean=fft_mean,
+               fft_std=fft_std, dominant_k=fft_mean[:, 1:].argmax(dim=1) + 1, low_k_power=fft_mean[:, 1:k_cut].sum(dim=1),
+               lowk_variance=(amp[:, s:, 1:k_cut] ** 2).sum(dim=2).mean(dim=1))
+    if rb.obs_m_local is not None:
+        ml = rb.obs_m_local[:, s:].reshape(rb.R, -1)
+        out["m_local_var"] = ml.var(dim=1, unbiased=False)
+    return out
+
+
+def sweep_betas_for_structures(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, start_fraction=0.5,
+                               k_max=None, base_seed=0):
+    """Drop-in for local_structure.py:167-193 (dict keyed by beta, same ensemble keys, no 'raw' outs).
+    Single rank; shard beta values over ranks by calling it with different beta subsets."""
+    from .capi import APS_REC_MLOCAL
+    spec = build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, base_seed=base_seed)
+    spec.record = APS_REC_COUNTS | APS_REC_POS | APS_REC_MLOCAL
+    ens = DeviceEnsemble(spec, 0, len(spec.betas))
+    ens.init_particles()
+    ens.rb.run_philox()
+    obs = {k: v.cpu().numpy() for k, v in structure_observables(ens.rb, start_fraction, k_max).items()}
+    nb, nr = len(beta_values), n_runs_per_beta
+    results = {}
+    for b, beta in enumerate(beta_values):
+        sl = slice(b * nr, (b + 1) * nr)
+        se = lambda x: x.std(ddof=1) / np.sqrt(nr)
+        results[beta] = {
+            "var_mean": obs["var_mean"][sl].mean(), "var_se": se(obs["var_mean"][sl]),
+            "low_k_power_mean": obs["low_k_power"][sl].mean(), "low_k_power_se": se(obs["low_k_power"][sl]),
+            "dominant_k_mode": int(np.round(obs["dominant_k"][sl].mean())),
+            "m_local_var_mean": obs["m_local_var"][sl].mean(), "m_local_var_se": se(obs["m_local_var"][sl]),
+            "fft_mean_mean": obs["fft_mean"][sl].mean(axis=0),
+            "fft_mean_se": obs["fft_mean"][sl].std(axis=0, ddof=1) / np.sqrt(nr),
+            "lowk_var_mean": obs["lowk_variance"][sl].mean(), "lowk_var_se": se(obs["lowk_variance"][sl]),
+            "n_events": ens.rb.n_events[sl].cpu().numpy(),
+        }
+    return results

@@ -150,3 +150,47 @@ def test_oracle_init_statistics_match_reference_init():
         se_prof = np.sqrt(ours_plus.var(0, ddof=1) / R + ref_plus.var(0, ddof=1) / R) + 1e-9
         z = np.abs(ours_plus.mean(0) - ref_plus.mean(0)) / se_prof
         assert (z < 4.5).all(), (init, K, z.max())
+
+
+@pytest.mark.gpu
+def test_structure_observables_match_the_reference_function():
+    """local_structure.py:55-103 restated with numpy on the downloaded run vs the device version.
+    Tolerance 1e-9 relative (cuFFT vs pocketfft, different summation order)."""
+    ps = dict(PS, init="fixed", N=40, local_kernel_sigma=0.03)
+    run = dict(T=4.0, obs_dt=0.25)
+    res = la.sweep_betas_for_structures([0.5, 2.0], 3, ps, {}, run, start_fraction=0.5, k_max=None, base_seed=4)
+    assert set(res) == {0.5, 2.0}
+    # recompute replica by replica with numpy from the raw observation rows
+    from aps_b200.capi import APS_REC_COUNTS, APS_REC_MLOCAL, APS_REC_POS
+    spec = la.build_beta_sweep_spec([0.5, 2.0], 3, ps, {}, run, base_seed=4)
+    spec.record = APS_REC_COUNTS | APS_REC_POS | APS_REC_MLOCAL
+    ens = la.DeviceEnsemble(spec, 0, 6)
+    ens.init_particles(); ens.rb.run_philox()
+    cp, cm = ens.rb.obs_cp.cpu().numpy().astype(np.int64), ens.rb.obs_cm.cpu().numpy().astype(np.int64)
+    ml = ens.rb.obs_m_local.cpu().numpy()
+    n = ens.n.cpu().numpy()
+    M = cp.shape[1]; s = M // 2
+    for b, beta in enumerate([0.5, 2.0]):
+        var_means, lowk, mlv, fmeans = [], [], [], []
+        for j in range(3):
+            r = 3 * b + j
+            total = cp[r] / (n[r] * (1.0 / 64)) + cm[r] / (n[r] * (1.0 / 64))
+            var_ts = np.array([np.var(u) for u in total])
+            amp = np.abs(np.fft.fft(total, axis=1))
+            fm = amp[s:].mean(axis=0)
+            var_means.append(var_ts[s:].mean()); lowk.append(fm[1:25].sum()); mlv.append(np.var(ml[r, s:])); fmeans.append(fm)
+        np.testing.assert_allclose(res[beta]["var_mean"], np.mean(var_means), rtol=1e-9)
+        np.testing.assert_allclose(res[beta]["low_k_power_mean"], np.mean(lowk), rtol=1e-9)
+        np.testing.assert_allclose(res[beta]["m_local_var_mean"], np.mean(mlv), rtol=1e-9)
+        np.testing.assert_allclose(res[beta]["fft_mean_mean"], np.mean(fmeans, axis=0), rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_double_sweep_grid():
+    ps = dict(PS)
+    out = la.double_sweep([10, 30, 50], [0.0, 1.5], 4, ps, RUN, frac_plus=0.75, decay_plus=0.2, base_seed=2)
+    assert set(out) == {10, 30, 50, "info"}
+    for N in [10, 30, 50]:
+        assert out[N]["means"].shape == (2,) and np.isfinite(out[N]["block_means"]).all()
+    # denser systems block more (exclusion): blocking probability grows with N
+    assert out[50]["block_means"].mean() > out[10]["block_means"].mean()
