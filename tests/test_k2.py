@@ -155,3 +155,49 @@ def test_gpu_large_lattice_invariants():
     assert int((s != 0).sum()) == n0 and int(s.max()) <= 2
     rp, rm = lat.profile(64)
     assert np.allclose((rp + rm)[4:-4], 0.5, atol=0.01)
+
+
+@pytest.mark.gpu
+def test_config5_profiles_against_the_reference_pde():
+    """BASELINE config 5: K2 profiles against the reference's IMEXPDE (tests/golden/stat_pde_config5.npz, produced by
+    the unmodified IMEX_PDE_solver_class.py in tools/gen_golden.py pde_fixture) under the hydrodynamic scaling
+    x = site/L, gamma = D/L^2, lam = lambda/L, in the regime where both describe the same dynamics (SURVEY R6:
+    only '+' advected, dilute so that exclusion is negligible, global magnetisation, bump away from the walls).
+    8 independent lattices of 2^17 sites (~2100 particles in total).  Tolerances: magnetisation 0.04 (3 sigma of the
+    particle noise + O(rho) exclusion), drift of the centre of mass 4 %, width 10 %, coarse profile L1 distance 0.2."""
+    import json
+    from common import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "stat_pde_config5.npz"))
+    c = json.loads(str(z["meta"]))
+    L, T, dt = c["L_lattice"], c["T"], 0.02
+    x = (np.arange(L) + 0.5) / L
+    rho0 = c["peak_density"] * np.exp(-np.abs(x - 0.5) / 0.05)
+    tot_counts = np.zeros(L // 1024)
+    n_plus = n_minus = 0
+    xs = []
+    for seed in range(8):
+        rng = np.random.default_rng(1000 + seed)
+        occ = rng.random(L) < rho0
+        state = np.where(occ, np.where(rng.random(L) < c["frac_plus"], 1, 2), 0).astype(np.uint8)
+        lat = SublatticeLattice(L, D=c["D"], lam=c["lam"], beta=c["beta"], dt=dt, sigma_sites=None, seed=seed)
+        lat.set_state(state)
+        lat.run(int(round(T / dt)))
+        s = lat.state.cpu().numpy()
+        assert (s != 0).sum() == occ.sum()
+        n_plus += int((s == 1).sum()); n_minus += int((s == 2).sum())
+        xs.append(x[s != 0])
+        tot_counts += (s != 0).reshape(-1, 1024).sum(1)
+    xs = np.concatenate(xs)
+    pde_tot = z["rho_p"] + z["rho_m"]
+    xp = np.arange(1000) / 1000.0
+    mean_pde = (pde_tot * xp).sum() / pde_tot.sum()
+    std_pde = np.sqrt((pde_tot * xp ** 2).sum() / pde_tot.sum() - mean_pde ** 2)
+    m_pde = float(z["m_series"][-1])
+    m_k2 = (n_plus - n_minus) / (n_plus + n_minus)
+    assert abs(m_k2 - m_pde) < 0.04, (m_k2, m_pde)
+    assert abs((xs.mean() - 0.5) - (mean_pde - 0.5)) < 0.04 * (mean_pde - 0.5), (xs.mean(), mean_pde)
+    assert abs(xs.std() - std_pde) < 0.10 * std_pde, (xs.std(), std_pde)
+    nb = 20
+    h_k2 = np.histogram(xs, bins=nb, range=(0, 1))[0] / len(xs)
+    h_pde = pde_tot.reshape(nb, -1).sum(1) / pde_tot.sum()
+    assert np.abs(h_k2 - h_pde).sum() < 0.2, np.abs(h_k2 - h_pde).sum()

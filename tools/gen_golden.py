@@ -327,6 +327,42 @@ def stat_fixture(PS, n_runs=300):
     np.savez_compressed(os.path.join(OUT, "stat_ensemble.npz"), **save)
 
 
+PDE_CASE = dict(L_lattice=131072, peak_density=0.02, frac_plus=0.8, D=0.5, lam=20.0, beta=1.5, T=1760.0,
+                init="exp(-|x-0.5|/0.05) bump (IMEXPDE.initialize mode='poisson', noise=0)")
+
+
+def pde_fixture():
+    """BASELINE config 5 comparison target: the reference's IMEXPDE (IMEX_PDE_solver_class.py, unmodified,
+    matplotlib stubbed) run on the hydrodynamic scaling of the K2 lattice of PDE_CASE:
+        x = site / L_lattice,  gamma = D / L_lattice^2,  lam = lambda / L_lattice,  same time unit,
+    in the setting where the PDE and the particle model describe the same dynamics: only '+'
+    particles are advected (active_model='anchored_minus'), reflecting walls (bc='neumann'), global
+    magnetisation (kernel_sigma = 1e5: flat kernel, as IMEX_PDE_solver_run_sweep.py uses), dilute lattice (the PDE has no exclusion term)."""
+    for m in ["matplotlib", "matplotlib.pyplot"]:
+        sys.modules.setdefault(m, MagicMock())
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from IMEX_PDE_solver_class import IMEXPDE  # type: ignore
+    c = PDE_CASE
+    Lk = c["L_lattice"]
+    pde = IMEXPDE(L=1000, xlim=1.0, T=c["T"], dt=0.1, gamma=c["D"] / Lk ** 2, lam=c["lam"] / Lk, beta=c["beta"],
+                  bc="neumann", active_model="anchored_minus", gaussian_kernel=True, kernel_sigma=1e5,
+                  snapshot_interval=10 ** 9, outdir="/tmp/imex_fixture", seed=1)
+    pde.initialize(mode="poisson", rho0=1.0, noise=0.0, n_tracers=4)
+    tot = pde.rho_p + pde.rho_m
+    pde.rho_p = tot * c["frac_plus"]
+    pde.rho_m = tot * (1.0 - c["frac_plus"])
+    with np.errstate(all="ignore"):
+        pde.solve()
+    out = pde.get_output()
+    np.savez_compressed(os.path.join(OUT, "stat_pde_config5.npz"), meta=np.array(json.dumps(c)),
+                        rho_p=out["rho_p"], rho_m=out["rho_m"], m_series=out["m_series"][::100])
+    tot = out["rho_p"] + out["rho_m"]
+    x = (np.arange(1000) + 0.0) / 1000
+    print("pde: mass", tot.sum(), "m_final", out["m_series"][-1], "mean x", (tot * x).sum() / tot.sum(),
+          "std x", np.sqrt((tot * x * x).sum() / tot.sum() - ((tot * x).sum() / tot.sum()) ** 2))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     PS = import_reference()
@@ -339,6 +375,8 @@ def main():
         reducer_golden(PS)
     if not want or "stat" in want:
         stat_fixture(PS)
+    if not want or "pde" in want:
+        pde_fixture()
 
 
 if __name__ == "__main__":
