@@ -502,3 +502,21 @@ void aps_oracle_k2_init(uint8_t* state, int64_t L, int64_t global_offset, uint64
         if (i + 1 < L) state[i + 1] = (w.v[2] < t_occ) ? ((w.v[3] < t_plus) ? APS_K2_PLUS : APS_K2_MINUS) : APS_K2_EMPTY;
     }
 }
+
+/* The native-mode variate stream of one replica as a replay log: for every event e = -log(1-u), u_choice,
+ * u_event and, only where kinds[ev] is a diffusive hop, u_dir (what aps_run_replay_* consumes).
+ * Returns the number of doubles written. */
+int64_t aps_oracle_philox_log(uint64_t seed, int64_t ev0, int64_t n_events, const int32_t* kinds, double* out) {
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    int64_t w = 0;
+    for (int64_t i = 0; i < n_events; ++i) {
+        uint64_t ev = (uint64_t)(ev0 + i);
+        aps_u32x4 a = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_A, 0, k0, k1);
+        aps_u32x4 b = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_B, 0, k0, k1);
+        out[w++] = -aps_log(1.0 - aps_u53(a.v[0], a.v[1]));
+        out[w++] = aps_u53(a.v[2], a.v[3]);
+        out[w++] = aps_u53(b.v[0], b.v[1]);
+        if (kinds[i] == APS_EV_DIFF_LEFT || kinds[i] == APS_EV_DIFF_RIGHT) out[w++] = aps_u53(b.v[2], b.v[3]);
+    }
+    return w;
+}
