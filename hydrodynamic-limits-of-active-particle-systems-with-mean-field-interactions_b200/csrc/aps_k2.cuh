@@ -136,44 +136,76 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         const uint32_t c0 = (uint32_t)seg_global, c1 = (uint32_t)a.pass;
         const uint32_t chi = (uint32_t)(seg_global >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
         const long long abase = t0 + (long long)tid * APS_K2_SEG + qpar * APS_K2_HALF;     // first active site (slab index)
-        if (abase + APS_K2_HALF <= L) {
-            aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
-            int ntr = 0;
-            while (ntr < (int)a.rates.n_cdf && w4.v[0] >= a.rates.cdf32[ntr]) ++ntr;
-            unsigned char* act = work + (abase - lo);
-            for (int tr = 0; tr < ntr; ++tr) {
-                uint32_t wa, wb;
+        // The trial loop runs in warp lock-step up to the largest trial count of the warp so that the local
+        // field of any lane can be evaluated COOPERATIVELY: the 2r+1 integer taps are spread over the 32 lanes
+        // and summed with redux.sync, instead of one lane walking them while 31 wait.
+        const bool seg_ok = abase + APS_K2_HALF <= L;
+        aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
+        int ntr = 0;
+        if (seg_ok) while (ntr < (int)a.rates.n_cdf && w4.v[0] >= a.rates.cdf32[ntr]) ++ntr;
+        const int ntr_max = LOCAL ? __reduce_max_sync(0xffffffffu, ntr) : ntr;
+        int wreg0 = 0, wreg1 = 0;       // this lane's Gaussian taps (k = lane and lane + 32) when r <= 31
+        if (LOCAL && r <= 31) {
+            const int l2 = tid & 31;
+            if (l2 <= 2 * r) wreg0 = a.w16[l2 < r ? r - l2 : l2 - r];
+            if (l2 + 32 <= 2 * r) wreg1 = a.w16[l2 + 32 - r];
+        }
+        unsigned char* act = work + (abase - lo);
+        for (int tr = 0; tr < ntr_max; ++tr) {
+            const bool live = tr < ntr;
+            uint32_t wa = 0, wb = 0;
+            if (live) {
                 if (tr == 0) { wa = w4.v[2]; wb = w4.v[3]; }
                 else {
                     if (tr & 1) w4 = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
                     wa = (tr & 1) ? w4.v[0] : w4.v[2]; wb = (tr & 1) ? w4.v[1] : w4.v[3];
                 }
-                const int x = (int)(wa >> 27);
-                const uint32_t slot = wa << 5;
-                const long long lx = abase + x;
-                const unsigned char v = act[x];
-                if (v == APS_K2_EMPTY) continue;
+            }
+            const int x = (int)(wa >> 27);
+            const uint32_t slot = wa << 5;
+            const long long lx = abase + x;
+            const unsigned char v = live ? act[x] : (unsigned char)APS_K2_EMPTY;
+            bool want_flip = false;
+            if (v != APS_K2_EMPTY) {
                 if (slot < a.rates.t_left) {
                     if (lx > 0 && act[x - 1] == APS_K2_EMPTY) { act[x - 1] = v; act[x] = APS_K2_EMPTY; }
                 } else if (slot < a.rates.t_right || (slot < a.rates.t_active && v == APS_K2_PLUS)) {
                     if (lx < L - 1 && act[x + 1] == APS_K2_EMPTY) { act[x + 1] = v; act[x] = APS_K2_EMPTY; }
-                } else if (slot >= a.rates.t_active) {
-                    const int sg = (v == APS_K2_PLUS) ? 1 : -1;
-                    uint32_t thr;
-                    if (LOCAL) {
-                        const unsigned char* c = snap + R16 + (lx - lo);
-                        int sw, tw;
-                        { const int cv = c[0]; const int wj = a.w16[0]; sw = wj * ((cv == APS_K2_PLUS) - (cv == APS_K2_MINUS)); tw = wj * (cv != 0); }
-                        for (int j = 1; j <= r; ++j) {
-                            const int cl = c[-j], cr = c[j], wj = a.w16[j];
-                            sw += wj * (((cl == APS_K2_PLUS) - (cl == APS_K2_MINUS)) + ((cr == APS_K2_PLUS) - (cr == APS_K2_MINUS)));
-                            tw += wj * ((cl != 0) + (cr != 0));
-                        }
-                        thr = a.flip_tab[(sg == 1 ? 0 : (2 * APS_K2_MQ + 1)) + aps_k2_mq_index(sw, tw)];
-                    } else thr = thr_glob[sg == 1 ? 0 : 1];
-                    if (wb < thr) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
-                }
+                } else if (slot >= a.rates.t_active) want_flip = true;
             }
+            const int sg = (v == APS_K2_PLUS) ? 1 : -1;
+            uint32_t thr = 0;
+            if (LOCAL) {
+                int my_sw = 0, my_tw = 0;
+                unsigned need = __ballot_sync(0xffffffffu, want_flip);
+                const int lane = tid & 31;
+                const int centre = (int)(lx - lo) + R16;                  // snap index of this lane's site
+                while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int cidx = __shfl_sync(0xffffffffu, centre, src);
+                    int sw, tw;
+                    if (r <= 31) {          // at most two taps per lane, weights held in registers
+                        const int cv0 = snap[cidx - r + lane];
+                        const int cv1 = (lane + 32 <= 2 * r) ? snap[cidx - r + lane + 32] : 0;
+                        sw = wreg0 * ((cv0 & 1) - (cv0 >> 1)) + wreg1 * ((cv1 & 1) - (cv1 >> 1));
+                        tw = wreg0 * (cv0 != 0) + wreg1 * (cv1 != 0);
+                    } else {
+                        sw = 0; tw = 0;
+                        for (int k = lane; k <= 2 * r; k += 32) {
+                            const int cv = snap[cidx - r + k];
+                            const int wj = a.w16[k < r ? r - k : k - r];
+                            sw += wj * ((cv & 1) - (cv >> 1));
+                            tw += wj * (cv != 0);
+                        }
+                    }
+                    sw = __reduce_add_sync(0xffffffffu, sw);
+                    tw = __reduce_add_sync(0xffffffffu, tw);
+                    if (lane == src) { my_sw = sw; my_tw = tw; }
+                }
+                if (want_flip) thr = a.flip_tab[(sg == 1 ? 0 : (2 * APS_K2_MQ + 1)) + aps_k2_mq_index(my_sw, my_tw)];
+            } else if (want_flip) thr = thr_glob[sg == 1 ? 0 : 1];
+            if (want_flip && wb < thr) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
         __syncthreads();

@@ -57,8 +57,8 @@ APS_HD uint32_t aps_k2_flip_thr(double beta, int sigma, double m, double inv_cma
 /* quantised local field index in [0, 2*MQ]: round(MQ * sw / tw) + MQ (half away from zero), integer only */
 APS_HD int aps_k2_mq_index(int sw, int tw) {
     if (tw <= 0) return APS_K2_MQ;
-    long long num = (long long)sw * APS_K2_MQ;
-    long long q = (num >= 0 ? num + tw / 2 : num - tw / 2) / tw;
+    int num = sw * APS_K2_MQ;                       /* |sw| <= sum of taps ~ 2^16 -> fits in 32 bits */
+    int q = (num >= 0 ? num + tw / 2 : num - tw / 2) / tw;
     if (q < -APS_K2_MQ) q = -APS_K2_MQ;
     if (q > APS_K2_MQ) q = APS_K2_MQ;
     return (int)q + APS_K2_MQ;
