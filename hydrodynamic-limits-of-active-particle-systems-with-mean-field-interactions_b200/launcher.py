@@ -417,3 +417,27 @@ def sweep_betas_for_structures(beta_values, n_runs_per_beta, ps_kwargs, init_kwa
             "n_events": ens.rb.n_events[sl].cpu().numpy(),
         }
     return results
+
+
+# ---- result caching with the reference's npz key names (sweep_beta.py:933-970) ----------------------
+NPZ_KEYS = ["beta_values", "means", "stds", "ses", "D_means", "D_ses", "m_means", "m_stds", "m_ses", "rho_means",
+            "rho_ses", "block_means", "block_ses", "ps_kwargs", "outs"]
+
+
+def save_sweep_npz(path, sweep_out):
+    """np.savez of a sweep_over_betas result under the key names the reference's `run=False` reload path reads
+    (`save_dict['means']`, ..., `save_dict['ps_kwargs'].item()`, sweep_beta.py:933-950)."""
+    ps = {k: v for k, v in dict(sweep_out.get("ps_kwargs", {})).items() if not callable(v)}
+    payload = {k: sweep_out[k] for k in NPZ_KEYS if k in sweep_out and k not in ("ps_kwargs", "outs")}
+    payload["ps_kwargs"] = np.array(ps, dtype=object)
+    payload["outs"] = np.array(sweep_out.get("outs", []), dtype=object)
+    np.savez(path, **payload)
+    return path
+
+
+def load_sweep_npz(path):
+    """The reference's reload (`data = np.load(..., allow_pickle=True); save_dict = dict(data)`)."""
+    data = np.load(path, allow_pickle=True)
+    d = dict(data)
+    d["ps_kwargs"] = d["ps_kwargs"].item()
+    return d

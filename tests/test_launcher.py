@@ -194,3 +194,16 @@ def test_double_sweep_grid():
         assert out[N]["means"].shape == (2,) and np.isfinite(out[N]["block_means"]).all()
     # denser systems block more (exclusion): blocking probability grows with N
     assert out[50]["block_means"].mean() > out[10]["block_means"].mean()
+
+
+def test_npz_cache_uses_the_reference_key_names(tmp_path):
+    out = _sweep(betas=(0.5, 2.0), runs=3)
+    p = la.save_sweep_npz(str(tmp_path / "CHANGES_simulation_out_sweep.npz"), out)
+    # the reference's reload path, sweep_beta.py:933-950
+    data = np.load(p, allow_pickle=True)
+    save_dict = dict(data)
+    for k in ["beta_values", "means", "stds", "ses", "D_means", "D_ses", "m_means", "m_stds", "m_ses", "rho_means", "rho_ses",
+              "block_means", "block_ses"]:
+        assert np.array_equal(save_dict[k], out[k], equal_nan=True), k
+    assert save_dict["ps_kwargs"].item()["L"] == 64 and "outs" in save_dict
+    assert la.load_sweep_npz(p)["ps_kwargs"]["site_capacity"] == 1
