@@ -271,13 +271,14 @@ def main():
         sm_mhz = (clocks.get("sm_max_mhz") or 1965)
         peak = 148 * 128 * sm_mhz * 1e6 / 1e9
         achieved = bytes_per_event * events_per_launch / (k1_avg_ms * 1e-3) / 1e9
-        roofline = dict(bound="smem", kernel="aps::k1_kernel<64,true>", achieved=achieved, peak=peak, unit="GB/s",
+        roofline = dict(bound="smem", kernel="aps::k1_fast_kernel<32,true,21,512,1056>", achieved=achieved, peak=peak, unit="GB/s",
                         frac=achieved / peak, traffic=None,
                         peak_source="computed 148 SM x 128 B/clk x clocks.max.sm (shared-memory bandwidth is not in "
                                     "MEASURED_PEAKS.json); HBM traffic of K1 is only the observation rows",
                         algorithmic_bytes_per_event=bytes_per_event, events_per_launch=events_per_launch,
                         kernel_ms=k1_avg_ms, kernel_share_of_step=k1_avg_ms * args.steps / total_ms,
-                        ncu="profiles/: issue-slot and shared-memory utilisation of the same kernel")
+                        ncu=(json.load(open(os.path.join(ROOT, "profiles", "k1_ncu_summary.json")))
+                             if os.path.exists(os.path.join(ROOT, "profiles", "k1_ncu_summary.json")) else None))
         cpu_baseline = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
