@@ -271,8 +271,13 @@ def main():
         sm_mhz = (clocks.get("sm_max_mhz") or 1965)
         peak = 148 * 128 * sm_mhz * 1e6 / 1e9
         achieved = bytes_per_event * events_per_launch / (k1_avg_ms * 1e-3) / 1e9
+        ncu_file = os.path.join(ROOT, "profiles", "k1_ncu_summary.json")
+        ncu_k1 = json.load(open(ncu_file)) if os.path.exists(ncu_file) else {}
+        smem_traffic = ncu_k1.get("smem_bytes_per_event_at_128B_per_wavefront")
         roofline = dict(bound="smem", kernel="aps::k1_fast_kernel<32,true,21,512,1056>", achieved=achieved, peak=peak, unit="GB/s",
-                        frac=achieved / peak, traffic=None,
+                        frac=achieved / peak,
+                        traffic=(smem_traffic * events_per_launch if smem_traffic else None),
+                        traffic_note="shared-memory wavefronts x 128 B per launch from the ncu capture (DRAM traffic of K1 is ~0.1 GB per launch)",
                         peak_source="computed 148 SM x 128 B/clk x clocks.max.sm (shared-memory bandwidth is not in "
                                     "MEASURED_PEAKS.json); HBM traffic of K1 is only the observation rows",
                         algorithmic_bytes_per_event=bytes_per_event, events_per_launch=events_per_launch,
