@@ -33,6 +33,15 @@ _FIELDS = {
     "sigma_end": "int8",
     "trace": "int32",
     "m_field_in": "float64",
+    "anchor_mask": "uint8",
+    "bound0": "int8",
+    "n_end": "int32",
+    "bound_end": "int8",
+    "obs_n": "int32",
+    "obs_bound": "int8",
+    "exit_t": "float64",
+    "exit_pos": "int32",
+    "n_exit": "int32",
 }
 
 
@@ -52,17 +61,19 @@ def _contig(a) -> bool:
     return a.flags["C_CONTIGUOUS"]
 
 
-def make_params(L, K, radius, D, lam, T, flags=0) -> ApsParams:
-    return ApsParams(int(L), int(K), int(radius), int(flags), float(D), float(lam), float(T))
+def make_params(L, K, radius, D, lam, T, flags=0, k_on=0.0, k_off=0.0, k_exit=0.0) -> ApsParams:
+    return ApsParams(int(L), int(K), int(radius), int(flags), float(D), float(lam), float(T), float(k_on), float(k_off),
+                     float(k_exit))
 
 
-def make_batch(n_replicas, n_max, M, record=0, max_events=0, trace_cap=0, spec_from=-1, **arrays):
+def make_batch(n_replicas, n_max, M, record=0, max_events=0, trace_cap=0, spec_from=-1, exit_cap=0, **arrays):
     """Returns (ApsBatch, keepalive list).  uint64 seeds may be passed as int64 torch tensors
     (torch has limited uint64 support); the bit pattern is what matters."""
     b = ApsBatch()
     b.n_replicas, b.n_max, b.M = int(n_replicas), int(n_max), int(M)
     b.record, b.max_events, b.trace_cap = int(record), int(max_events), int(trace_cap)
     b.spec_from = int(spec_from)
+    b.exit_cap = int(exit_cap)
     keep = []
     for name, arr in arrays.items():
         if name not in _FIELDS:

@@ -17,9 +17,10 @@ LIB_PATH = os.path.join(PKG_DIR, "csrc", "libaps_b200.so")
 APS_OK = 0
 APS_ERR_INVALID, APS_ERR_NO_DEVICE, APS_ERR_CUDA, APS_ERR_CAPACITY = 1, 2, 3, 4
 APS_RUN_DONE, APS_RUN_EMPTY, APS_RUN_DRAWS_EXHAUSTED, APS_RUN_MAX_EVENTS = 0, 1, 2, 3
-APS_FLAG_CROWDING = 1
+APS_FLAG_CROWDING, APS_FLAG_SUPPRESS_FLIP_BOUND, APS_FLAG_IMMOBILIZE = 1, 2, 4
 APS_REC_COUNTS, APS_REC_POS, APS_REC_MLOCAL = 1, 2, 4
 APS_EV_DIFF_LEFT, APS_EV_DIFF_RIGHT, APS_EV_ACTIVE, APS_EV_FLIP = 0, 1, 2, 3
+APS_EV_BIND, APS_EV_UNBIND, APS_EV_EXIT = 4, 5, 6
 
 
 class ApsParams(C.Structure):
@@ -31,6 +32,9 @@ class ApsParams(C.Structure):
         ("rate_diffusion", C.c_double),
         ("rate_active", C.c_double),
         ("T", C.c_double),
+        ("k_on", C.c_double),
+        ("k_off", C.c_double),
+        ("k_exit", C.c_double),
     ]
 
 
@@ -70,6 +74,16 @@ class ApsBatch(C.Structure):
         ("sigma_end", C.c_void_p),
         ("trace", C.c_void_p),
         ("m_field_in", C.c_void_p),
+        ("anchor_mask", C.c_void_p),
+        ("bound0", C.c_void_p),
+        ("n_end", C.c_void_p),
+        ("bound_end", C.c_void_p),
+        ("obs_n", C.c_void_p),
+        ("obs_bound", C.c_void_p),
+        ("exit_t", C.c_void_p),
+        ("exit_pos", C.c_void_p),
+        ("n_exit", C.c_void_p),
+        ("exit_cap", C.c_int64),
     ]
 
 
@@ -85,7 +99,7 @@ class ApsExpandArgs(C.Structure):
     _fields_ = [("n_replicas", C.c_int32), ("M", C.c_int32), ("L", C.c_int32), ("reserved", C.c_int32),
                 ("dx", C.c_double), ("n", C.c_void_p), ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p),
                 ("obs_cm", C.c_void_p), ("rho_p", C.c_void_p), ("rho_m", C.c_void_p), ("total", C.c_void_p),
-                ("var", C.c_void_p)]
+                ("var", C.c_void_p), ("obs_n", C.c_void_p)]
 
 
 APS_RED_V_EFF, APS_RED_D_EFF, APS_RED_M_MEAN, APS_RED_RHO_EFF, APS_RED_BLOCK = 0, 1, 2, 3, 4
@@ -177,7 +191,7 @@ def load(path: str | None = None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.aps_abi_version() != 1:
+    if lib.aps_abi_version() != 2:
         raise ApsError("libaps_b200.so ABI version mismatch")
     if path is None:
         _lib = lib

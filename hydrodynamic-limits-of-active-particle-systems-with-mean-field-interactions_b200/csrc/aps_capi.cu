@@ -117,7 +117,7 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     a.only_retry = 0; a.reserved = 0;
     // specialised kernel for K = 1 with a local field (every shipped sweep configuration)
     const bool fast_ok = g_use_fast && p->K == 1 && p->radius >= 0 && p->radius < p->L && !(p->flags & APS_FLAG_CROWDING) &&
-                         !b->m_field_in && b->n_max <= 1024 && b->status != nullptr;
+                         !b->m_field_in && !b->anchor_mask && b->n_max <= 1024 && b->status != nullptr;
     if (fast_ok) {
         int launched = 0;
         // single-warp CTAs (no block barriers) win for narrow update windows; wide windows (r > 30) use two warps
@@ -214,6 +214,18 @@ int run_host(const aps_params* p, const aps_batch* hb, bool philox) {
     TRY(s.out(hb->sigma_end, R * NM, (void**)&d.sigma_end));
     TRY(s.out(hb->trace_cap > 0 ? hb->trace : nullptr, R * (size_t)hb->trace_cap * 12, (void**)&d.trace));
     if (hb->trace_cap <= 0) d.trace = nullptr;
+    TRY(s.in(hb->m_field_in, R * L * 8, (const void**)&d.m_field_in));
+    TRY(s.in(hb->anchor_mask, L, (const void**)&d.anchor_mask));
+    TRY(s.in(hb->bound0, R * NM, (const void**)&d.bound0));
+    TRY(s.out(hb->n_end, R * 4, (void**)&d.n_end, false));
+    TRY(s.out(hb->bound_end, R * NM, (void**)&d.bound_end));
+    TRY(s.out(hb->obs_n, R * M * 4, (void**)&d.obs_n));
+    TRY(s.out(hb->obs_bound, R * M * NM, (void**)&d.obs_bound));
+    const size_t EC = hb->exit_cap > 0 ? (size_t)hb->exit_cap : 0;
+    TRY(s.out(EC ? hb->exit_t : nullptr, R * EC * 8, (void**)&d.exit_t));
+    TRY(s.out(EC ? hb->exit_pos : nullptr, R * EC * 4, (void**)&d.exit_pos));
+    TRY(s.out(hb->n_exit, R * 4, (void**)&d.n_exit));
+    if (!EC) { d.exit_t = nullptr; d.exit_pos = nullptr; }
     TRY(run_device(p, &d, nullptr, philox));
     return s.finish();
 }

@@ -74,6 +74,8 @@ __host__ __device__ inline size_t k1_smem_bytes(int L, int n_max, int radius, in
     if (use_lut) bytes += (((size_t)(L + 2 * pad) + 1) / 2) * 4;  // per-site codes
     bytes += (((size_t)n_max + 1) / 2) * 4;          // pos (uint16)
     bytes += (((size_t)n_max + 3) / 4) * 4;          // sigma (int8)
+    bytes += (((size_t)n_max + 3) / 4) * 4;          // bound flags (int8)
+    bytes += (((size_t)L + 3) / 4) * 4;              // anchor mask (uint8)
     return bytes;
 }
 
@@ -82,6 +84,8 @@ struct Smem {
     double* rates; double* w; double* node_val; double* wtot; double* misc;
     int32_t* node_a; int32_t* node_b; int32_t* node_kind; int32_t* desc;
     uint16_t* pk; uint16_t* code; uint16_t* pos; int8_t* sigma;
+    int8_t* bound;        // bound flags (anchors only; all zero otherwise)
+    uint8_t* anchor;      // is_anchor_site, or nullptr when the batch has no anchors
     const double* m_in;   // optional injected field (global memory), see aps_batch.m_field_in
 };
 
@@ -105,12 +109,14 @@ __device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int
     s.pk = reinterpret_cast<uint16_t*>(q); q += ((L + 2 * pad) + 1) / 2;
     s.code = reinterpret_cast<uint16_t*>(q); if (use_lut) q += ((L + 2 * pad) + 1) / 2;
     s.pos = reinterpret_cast<uint16_t*>(q); q += (n_max + 1) / 2;
-    s.sigma = reinterpret_cast<int8_t*>(q);
+    s.sigma = reinterpret_cast<int8_t*>(q); q += (n_max + 3) / 4;
+    s.bound = reinterpret_cast<int8_t*>(q); q += (n_max + 3) / 4;
+    s.anchor = reinterpret_cast<uint8_t*>(q);
     return s;
 }
 
 // desc[] slots
-enum { D_SEQ = 0, D_PART, D_KIND, D_OLD, D_NEW, D_STOP, D_EXACT, D_NCROSS, D_END, D_AVAIL, D_NNODES, D_BADR };
+enum { D_SEQ = 0, D_PART, D_KIND, D_OLD, D_NEW, D_STOP, D_EXACT, D_NCROSS, D_END, D_AVAIL, D_NNODES, D_BADR, D_R12, D_R13, D_SG };
 // misc[] slots
 enum { X_TNEW = 0, X_R };
 
@@ -166,6 +172,27 @@ __device__ __forceinline__ void hop_rates(const uint16_t* pk, int pad, int L, in
     }
 }
 
+// Every additive part of rates[i] (CLASS.py:259-351): hop parts, bind / unbind / exit (anchors) and whether
+// the flip term is suppressed.  Without anchors the last three are +0.0 and the sum is unchanged.
+struct RateParts { double rl, rr, rdiff, ract, rbind, runbind, rexit; bool no_flip; };
+
+__device__ __forceinline__ RateParts rate_parts(const Smem& s, const aps_params& P, int pad, bool crowd, int i, int p, int sg) {
+    RateParts r;
+    hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, r.rl, r.rr, r.ract);
+    r.rbind = 0.0; r.runbind = 0.0; r.rexit = 0.0; r.no_flip = false;
+    r.rdiff = APS_ADD(r.rl, r.rr);
+    if (s.anchor) {
+        const bool bnd = s.bound[i] != 0, on_anchor = s.anchor[p] != 0;
+        if ((P.flags & APS_FLAG_IMMOBILIZE) && sg == -1 && on_anchor && bnd) {    // anchored: immobile, may exit (:307-312,338-340)
+            r.rdiff = 0.0; r.ract = 0.0; r.rexit = P.k_exit;
+        }
+        r.no_flip = (P.flags & APS_FLAG_SUPPRESS_FLIP_BOUND) && bnd;                 // :266-267
+        if (!bnd && sg == -1 && on_anchor && occ_of(s.pk[pad + p]) < P.K) r.rbind = P.k_on;   // :343-345
+        if (bnd) r.runbind = P.k_off;                                                // :347-348
+    }
+    return r;
+}
+
 // Local magnetisation at site p: the two Gaussian filters of CLASS.py:229-245 evaluated at one
 // output in scipy's symmetric-correlate order.
 __device__ __forceinline__ double local_m(const uint16_t* pk, const double* w, int pad, int r, int p) {
@@ -214,13 +241,16 @@ __device__ __forceinline__ double site_m(const Smem& s, const aps_params& P, int
     return lut ? local_m_lut(s.code, s.lut, pad, P.radius, b2, p) : local_m(s.pk, s.w, pad, P.radius, p);
 }
 __device__ __forceinline__ double particle_rate(const Smem& s, const aps_params& P, int pad, bool crowd, double beta,
-                                                double m_global, int p, int sg, bool lut, int b2) {
-    double rl, rr, ra;
-    hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, rl, rr, ra);
-    double m = s.m_in ? s.m_in[p] : ((P.radius < 0) ? m_global : site_m(s, P, pad, lut, b2, p));
-    double arg = APS_MUL(APS_MUL(-beta, (double)sg), m);
-    double cv = aps_exp(arg);
-    return APS_ADD(APS_ADD(APS_ADD(rl, rr), ra), cv);
+                                                double m_global, int i, int p, int sg, bool lut, int b2) {
+    const RateParts r = rate_parts(s, P, pad, crowd, i, p, sg);
+    double cv = 0.0;
+    if (!r.no_flip) {
+        double m = s.m_in ? s.m_in[p] : ((P.radius < 0) ? m_global : site_m(s, P, pad, lut, b2, p));
+        cv = aps_exp(APS_MUL(APS_MUL(-beta, (double)sg), m));
+    }
+    double rate = APS_ADD(APS_ADD(r.rdiff, r.ract), cv);
+    if (s.anchor) rate = APS_ADD(APS_ADD(APS_ADD(rate, r.rbind), r.runbind), r.rexit);
+    return rate;
 }
 
 // numpy pairwise-sum tree for n elements, built once per replica by one thread.
@@ -256,7 +286,11 @@ __device__ inline int build_sum_tree(int n, int32_t* na, int32_t* nb, int32_t* n
 // Apply one event to the shared-memory state.
 __device__ __forceinline__ void apply_event(const Smem& s, int L, int pad, int i, int kind, int oldp, int newp, int sg,
                                             int bcode, bool lut) {
-    if (kind == APS_EV_FLIP) {
+    if (kind == APS_EV_BIND) s.bound[i] = 1;
+    else if (kind == APS_EV_UNBIND) s.bound[i] = 0;
+    else if (kind == APS_EV_EXIT) {                     // lattice only; the particle arrays are compacted by the whole CTA
+        pk_add(s, L, pad, oldp, sg == 1 ? -1 : 0, sg == 1 ? 0 : -1, bcode, lut);
+    } else if (kind == APS_EV_FLIP) {
         s.sigma[i] = (int8_t)(-sg);
         pk_add(s, L, pad, oldp, -sg, sg, bcode, lut);   // c_plus-1,c_minus+1  or the reverse
     } else {
@@ -269,7 +303,10 @@ __device__ __forceinline__ void apply_event(const Smem& s, int L, int pad, int i
 // Exact inverse of apply_event on the lattice arrays only (used to expose the pre-event field).
 __device__ __forceinline__ void lattice_delta(const Smem& s, int L, int pad, int kind, int oldp, int newp, int sg_old,
                                               int sign, int bcode, bool lut) {
-    if (kind == APS_EV_FLIP) {
+    if (kind == APS_EV_BIND || kind == APS_EV_UNBIND) return;
+    if (kind == APS_EV_EXIT) {
+        pk_add(s, L, pad, oldp, sg_old == 1 ? -sign : 0, sg_old == 1 ? 0 : -sign, bcode, lut);
+    } else if (kind == APS_EV_FLIP) {
         pk_add(s, L, pad, oldp, -sign * sg_old, sign * sg_old, bcode, lut);
     } else {
         const int dp = sg_old == 1 ? 1 : 0, dm = 1 - dp;
@@ -283,11 +320,14 @@ __device__ __forceinline__ void lattice_delta(const Smem& s, int L, int pad, int
 __device__ __forceinline__ bool decode_and_apply(const Smem& s, const aps_params& P, int pad, bool crowd, int sel,
                                                  double ue, double ud, int avail, int seq, int bcode, bool lut) {
     int p = s.pos[sel], sg = s.sigma[sel];
-    double rl, rr, ra;
-    hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, rl, rr, ra);
+    const RateParts rp = rate_parts(s, P, pad, crowd, sel, p, sg);
+    const double rl = rp.rl, rr = rp.rr;
     double v = APS_MUL(ue, s.rates[sel]);
-    double diff_thresh = APS_ADD(rl, rr);
-    double act_thresh = APS_ADD(diff_thresh, ra);
+    double diff_thresh = rp.rdiff;
+    double act_thresh = APS_ADD(diff_thresh, rp.ract);
+    double bind_thresh = APS_ADD(act_thresh, rp.rbind);          // :365-367
+    double unbind_thresh = APS_ADD(bind_thresh, rp.runbind);
+    double exit_thresh = APS_ADD(unbind_thresh, rp.rexit);
     int kind, newp = p;
     if (v < diff_thresh) {
         if (avail < 4) { s.desc[D_STOP] = 1; s.desc[D_SEQ] = seq; return false; }
@@ -295,9 +335,12 @@ __device__ __forceinline__ bool decode_and_apply(const Smem& s, const aps_params
         else { kind = APS_EV_DIFF_RIGHT; newp = clampi(p + 1, 0, P.L - 1); }
     } else if (v < act_thresh) {
         kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, P.L - 1);
-    } else kind = APS_EV_FLIP;
+    } else if (v < bind_thresh) kind = APS_EV_BIND;
+    else if (v < unbind_thresh) kind = APS_EV_UNBIND;
+    else if (v < exit_thresh) kind = APS_EV_EXIT;
+    else kind = APS_EV_FLIP;
     apply_event(s, P.L, pad, sel, kind, p, newp, sg, bcode, lut);
-    s.desc[D_PART] = sel; s.desc[D_KIND] = kind; s.desc[D_OLD] = p; s.desc[D_NEW] = newp;
+    s.desc[D_PART] = sel; s.desc[D_KIND] = kind; s.desc[D_OLD] = p; s.desc[D_NEW] = newp; s.desc[D_SG] = sg;
     s.desc[D_STOP] = 0; s.desc[D_SEQ] = seq;
     return true;
 }
@@ -321,10 +364,12 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
     const bool global_m = r < 0;
     bool lut = A.use_lut != 0;
     const int bcode = A.bcode, b2 = A.bcode * A.bcode;
-    const int n = B.n[rep];
+    int n = B.n[rep];
     const double beta = B.beta[rep], T = P.T;
     Smem s = carve(smem_raw, L, n_max, pad, A.max_nodes, NW, A.use_lut, P.K, r);
     s.m_in = B.m_field_in ? B.m_field_in + (size_t)rep * (size_t)L : nullptr;
+    if (B.anchor_mask) { for (int l = tid; l < L; l += NT) s.anchor[l] = B.anchor_mask[l]; } else s.anchor = nullptr;
+    for (int i = tid; i < n_max; i += NT) s.bound[i] = (B.bound0 && i < n) ? B.bound0[(size_t)rep * n_max + i] : 0;
 
     // ---------------- prologue: stage the replica into shared memory ----------------
     {
@@ -385,7 +430,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
         if (tid == 0) s.desc[D_NNODES] = (n > 0) ? build_sum_tree(n, s.node_a, s.node_b, s.node_kind, A.max_nodes) : 0;
     }
     bsync<NT>();
-    const int nnodes = s.desc[D_NNODES];
+    int nnodes = s.desc[D_NNODES];
+    int n_exit = (B.n_exit && B.ev_start) ? B.n_exit[rep] : 0;
 
     int64_t n_done = 0;
     const int64_t ev_base = B.ev_start ? B.ev_start[rep] : 0;
@@ -411,6 +457,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
                 for (int i = tid; i < n; i += NT) op[i] = (int32_t)s.pos[i];
             }
             if (B.obs_sigma_sum && tid == 0) B.obs_sigma_sum[row] = S;
+            if (B.obs_n && tid == 0) B.obs_n[row] = n;
+            if (B.obs_bound) { int8_t* ob = B.obs_bound + row * (size_t)n_max; for (int i = tid; i < n; i += NT) ob[i] = s.bound[i]; }
         }
     };
     auto write_field = [&](int first, int count) {
@@ -427,15 +475,16 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
     } else {
         // initial rates (every particle) and observation row 0
         for (int i = tid; i < n; i += NT)
-            s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, s.pos[i], s.sigma[i], lut, b2);
+            s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, i, s.pos[i], s.sigma[i], lut, b2);
         if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
         bsync<NT>();
         double next_obs = (obs_idx < M) ? B.times_obs[obs_idx] : 0.0;
-        const double guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
-        const int chunk = (n + NT - 1) / NT;
+        double guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
+        int chunk = (n + NT - 1) / NT;
 
         while (true) {
             if (!(t < T)) { status = APS_RUN_DONE; break; }
+            if (n == 0) { status = APS_RUN_EMPTY; break; }          // every particle has exited (CLASS.py:256-257)
             if (B.max_events > 0 && n_done >= B.max_events) { status = APS_RUN_MAX_EVENTS; break; }
 
             // ---- variates of this event from the shared-memory ring (refilled by a whole warp) ----
@@ -572,12 +621,36 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
             const double tnew = s.misc[X_TNEW];
             if (B.trace && tid == 0 && n_done < B.trace_cap) {
                 int32_t* tr = B.trace + ((size_t)rep * (size_t)B.trace_cap + (size_t)n_done) * 3;
-                tr[0] = part; tr[1] = kind; tr[2] = (kind == APS_EV_FLIP) ? -1 : newp;
+                tr[0] = part; tr[1] = kind; tr[2] = (kind <= APS_EV_ACTIVE) ? newp : (kind == APS_EV_EXIT ? oldp : -1);
             }
             ++n_done;
             cursor += 3 + (kind < 2 ? 1 : 0);
-            int sg_old = s.sigma[part];
-            if (kind == APS_EV_FLIP) { S += 2 * sg_old; sg_old = -sg_old; }   // sigma[] already holds the new sign
+            const int sg_old = s.desc[D_SG];                        // sign of the particle before the event
+            if (kind == APS_EV_FLIP) S -= 2 * sg_old;
+            if (kind == APS_EV_EXIT) {
+                // np.delete(pos/sigma/bound, i) (CLASS.py:434-436): compact the particle arrays (and their rates)
+                if (tid == 0 && B.exit_t && n_exit < B.exit_cap) {
+                    B.exit_t[(size_t)rep * (size_t)B.exit_cap + n_exit] = t;          // clock before this step's tau (:425)
+                    B.exit_pos[(size_t)rep * (size_t)B.exit_cap + n_exit] = oldp;
+                }
+                ++n_exit;
+                S -= sg_old;
+                for (int base = part; base < n - 1; base += NT) {
+                    const int i = base + tid;
+                    const bool ok = i < n - 1;
+                    uint16_t vp = 0; int8_t vs = 0, vb = 0; double vr = 0.0;
+                    if (ok) { vp = s.pos[i + 1]; vs = s.sigma[i + 1]; vb = s.bound[i + 1]; vr = s.rates[i + 1]; }
+                    bsync<NT>();
+                    if (ok) { s.pos[i] = vp; s.sigma[i] = vs; s.bound[i] = vb; s.rates[i] = vr; }
+                    bsync<NT>();
+                }
+                --n;
+                if (tid == 0) s.desc[D_NNODES] = (n > 0) ? build_sum_tree(n, s.node_a, s.node_b, s.node_kind, A.max_nodes) : 0;
+                bsync<NT>();
+                nnodes = s.desc[D_NNODES];
+                chunk = (n + NT - 1) / NT;
+                guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
+            }
             t = tnew;
             if (endflag) { status = APS_RUN_DONE; break; }
             if (ncross > 0) {
@@ -600,15 +673,17 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
             // ---- B: refresh the rates the event can have changed ----
             int wlo, whi;
             if (global_m) {
-                if (kind == APS_EV_FLIP) { m_glob = APS_DIV((double)S, (double)n); wlo = 0; whi = L - 1; }
-                else { wlo = (oldp < newp ? oldp : newp) - 1; whi = (oldp < newp ? newp : oldp) + 1; }
+                if (kind == APS_EV_FLIP || kind == APS_EV_EXIT) {      // sum(sigma) or n changed: every flip rate changes
+                    if (n > 0) m_glob = APS_DIV((double)S, (double)n);
+                    wlo = 0; whi = L - 1;
+                } else { wlo = (oldp < newp ? oldp : newp) - 1; whi = (oldp < newp ? newp : oldp) + 1; }
             } else {
                 const int reach = r > 1 ? r : 1;
                 wlo = (oldp < newp ? oldp : newp) - reach; whi = (oldp < newp ? newp : oldp) + reach;
             }
             for (int i = tid; i < n; i += NT) {
                 int p = s.pos[i];
-                if (p >= wlo && p <= whi) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, p, s.sigma[i], lut, b2);
+                if (p >= wlo && p <= whi) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, i, p, s.sigma[i], lut, b2);
             }
             bsync<NT>();  // BAR3
         }
@@ -622,8 +697,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
         if (B.status) B.status[rep] = status;
         if (B.n_guard) B.n_guard[rep] = n_guard;
         if (B.draws_used) B.draws_used[rep] = PHILOX ? 0 : cursor;
+        if (B.n_end) B.n_end[rep] = n;
+        if (B.n_exit) B.n_exit[rep] = n_exit;
     }
     bsync<NT>();
+    if (B.bound_end) for (int i = tid; i < n; i += NT) B.bound_end[(size_t)rep * n_max + i] = s.bound[i];
     if (B.pos_end) for (int i = tid; i < n; i += NT) B.pos_end[(size_t)rep * n_max + i] = (int32_t)s.pos[i];
     if (B.sigma_end) for (int i = tid; i < n; i += NT) B.sigma_end[(size_t)rep * n_max + i] = s.sigma[i];
 }

@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
                 if (B.t_end) B.t_end[rep] = B.t_start ? B.t_start[rep] : 0.0;
                 if (B.n_guard) B.n_guard[rep] = 0;
                 if (B.draws_used) B.draws_used[rep] = 0;
+                if (B.n_end) B.n_end[rep] = 0;
+                if (B.n_exit && !B.ev_start) B.n_exit[rep] = 0;
                 B.status[rep] = APS_RUN_EMPTY;
             } else B.status[rep] = APS_RUN_RETRY_GENERIC;
         }
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
                 for (int i = tid; i < n; i += NT) op[i] = (int32_t)pos[i];
             }
             if (B.obs_sigma_sum && tid == 0) B.obs_sigma_sum[row] = S;
+            if (B.obs_n && tid == 0) B.obs_n[row] = n;
+            if (B.obs_bound) { int8_t* ob = B.obs_bound + row * (size_t)n_max; for (int i = tid; i < n; i += NT) ob[i] = 0; }
         }
     };
     auto write_field = [&](int first, int count) {
@@ -522,8 +526,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
         B.status[rep] = status;
         if (B.n_guard) B.n_guard[rep] = n_guard;
         if (B.draws_used) B.draws_used[rep] = PHILOX ? 0 : cursor;
+        if (B.n_end) B.n_end[rep] = n;
+        if (B.n_exit && !B.ev_start) B.n_exit[rep] = 0;
     }
     bsync<NT>();
+    if (B.bound_end) for (int i = tid; i < n; i += NT) B.bound_end[(size_t)rep * n_max + i] = 0;
     if (B.pos_end) for (int i = tid; i < n; i += NT) B.pos_end[(size_t)rep * n_max + i] = (int32_t)pos[i];
     if (B.sigma_end) for (int i = tid; i < n; i += NT) B.sigma_end[(size_t)rep * n_max + i] = sigma[i];
 }

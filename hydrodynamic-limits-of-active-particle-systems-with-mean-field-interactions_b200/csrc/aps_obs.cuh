@@ -61,7 +61,7 @@ __global__ void expand_kernel(aps_expand_args a) {
     const size_t row = (size_t)rep * a.M + m;
     const int8_t* cp = a.obs_cp + row * L;
     const int8_t* cm = a.obs_cm + row * L;
-    const int n = a.n[rep];
+    const int n = a.obs_n ? a.obs_n[row] : a.n[rep];
     const double denom = APS_MUL((double)(n > 1 ? n : 1), a.dx);
     for (int l = threadIdx.x; l < L; l += blockDim.x) {
         double rp = APS_DIV((double)cp[l], denom), rm = APS_DIV((double)cm[l], denom);

@@ -43,13 +43,19 @@ def _stream():
 
 class ReplicaBatch:
     def __init__(self, *, L, K, radius, weights, D, lam, T, times_obs, betas, n, pos0, sigma0, seeds=None,
-                 record=APS_REC_COUNTS | APS_REC_POS, crowding=False, device=None, dx=None):
+                 record=APS_REC_COUNTS | APS_REC_POS, crowding=False, device=None, dx=None, anchor_mask=None,
+                 k_on=0.0, k_off=0.0, k_exit=0.0, suppress_flip_when_bound=True, immobilize_when_anchored=True,
+                 exit_cap=None):
         self.lib = capi.load()
         self.dev = _dev(device)
         self.L, self.K, self.radius = int(L), int(K), int(radius)
         self.dx = float(dx) if dx is not None else 1.0 / self.L
         self.T = float(T)
-        self.params = make_params(L, K, radius, D, lam, T, capi.APS_FLAG_CROWDING if crowding else 0)
+        flags = capi.APS_FLAG_CROWDING if crowding else 0
+        if anchor_mask is not None:
+            flags |= (capi.APS_FLAG_SUPPRESS_FLIP_BOUND if suppress_flip_when_bound else 0)
+            flags |= (capi.APS_FLAG_IMMOBILIZE if immobilize_when_anchored else 0)
+        self.params = make_params(L, K, radius, D, lam, T, flags, k_on=k_on, k_off=k_off, k_exit=k_exit)
         t = lambda a, dt: torch.as_tensor(np.array(a, dtype=dt, order="C", copy=True)).to(self.dev, non_blocking=True)
         self.times_obs = t(times_obs, np.float64)
         self.M = int(self.times_obs.numel())
@@ -80,12 +86,28 @@ class ReplicaBatch:
         self.draws_used = z((R,), torch.int64)
         self.pos_end = z((R, nm), torch.int32)
         self.sigma_end = z((R, nm), torch.int8)
+        self.n_end = z((R,), torch.int32)
+        self.obs_n = z((R, M), torch.int32)
+        # anchors / binding / exit (only allocated when the batch has anchors)
+        self.anchor_mask = None
+        self.bound0 = self.bound_end = self.obs_bound = self.exit_t = self.exit_pos = self.n_exit = None
+        self.exit_cap = 0
+        if anchor_mask is not None:
+            self.anchor_mask = t(np.asarray(anchor_mask, dtype=np.uint8), np.uint8)
+            self.bound_end = z((R, nm), torch.int8)
+            self.obs_bound = z((R, M, nm), torch.int8)
+            self.exit_cap = int(exit_cap if exit_cap is not None else nm)
+            self.exit_t = z((R, max(1, self.exit_cap)), torch.float64)
+            self.exit_pos = z((R, max(1, self.exit_cap)), torch.int32)
+            self.n_exit = z((R,), torch.int32)
 
     # -- K1 ---------------------------------------------------------------------------------
     def _batch(self, **extra):
         return make_batch(
             self.R, self.n_max, self.M, record=self.record, max_events=extra.pop("max_events", 0),
-            spec_from=extra.pop("spec_from", -1),
+            spec_from=extra.pop("spec_from", -1), exit_cap=self.exit_cap, n_end=self.n_end, obs_n=self.obs_n,
+            anchor_mask=self.anchor_mask, bound0=self.bound0, bound_end=self.bound_end, obs_bound=self.obs_bound,
+            exit_t=self.exit_t, exit_pos=self.exit_pos, n_exit=self.n_exit,
             times_obs=self.times_obs, weights=self.weights, beta=self.beta, n=self.n, pos0=self.pos0,
             sigma0=self.sigma0, obs_cp=self.obs_cp, obs_cm=self.obs_cm, obs_pos=self.obs_pos,
             obs_sigma_sum=self.obs_sigma_sum, obs_m_local=self.obs_m_local, n_obs=self.n_obs,
@@ -121,7 +143,7 @@ class ReplicaBatch:
         var = z((R, M)) if want_var else None
         a = ApsExpandArgs(R, M, L, 0, self.dx, self.n.data_ptr(), self.n_obs.data_ptr(), self.obs_cp.data_ptr(),
                           self.obs_cm.data_ptr(), rho_p.data_ptr(), rho_m.data_ptr(), total.data_ptr(),
-                          var.data_ptr() if want_var else None)
+                          var.data_ptr() if want_var else None, self.obs_n.data_ptr())
         capi.check(self.lib.aps_expand_obs_device(a, _stream()), "aps_expand_obs_device")
         return rho_p, rho_m, total, var
 

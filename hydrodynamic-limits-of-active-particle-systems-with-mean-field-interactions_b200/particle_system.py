@@ -12,8 +12,9 @@ Random numbers, two modes selected by the `rng=` argument (the reference's injec
     diffusive hop (:378) is handled by speculative chunks with rewind of the bit generator.
   * `PhiloxRNG(seed)` or `rng=None`: NATIVE mode, in-kernel counter-based Philox4x32-10.
 
-Not supported (raise NotImplementedError; all disabled in every shipped driver):
-custom `flip_rate_fn`, `periodic=True` with a local kernel, `anchor_positions`.
+Anchors / binding / unbinding / exit (`anchor_positions`, `k_on`, `k_off`, `k_exit`, CLASS.py:307-348,418-436) are supported
+(generic K1 kernel).  Not supported (raise NotImplementedError; disabled in every shipped driver):
+custom `flip_rate_fn`, `periodic=True`.
 """
 from __future__ import annotations
 
@@ -80,11 +81,21 @@ class ParticleSystem:
         self.minus_anchor = minus_anchor
         self._sigma_grid = self.local_kernel_sigma / self.dx
         self.anchor_radius = anchor_radius
-        if anchor_positions is not None:
-            raise NotImplementedError("anchors / binding / exit are outside the accelerated path")
-        self.anchor_positions = None
-        self.anchor_idxs = np.array([], dtype=int)
+        # anchor sites: positions -> lattice indices within anchor_radius (CLASS.py:88-104)
         self.is_anchor_site = np.zeros(self.L, dtype=bool)
+        if anchor_positions is None:
+            self.anchor_positions = None
+            self.anchor_idxs = np.array([], dtype=int)
+        else:
+            ap = np.asarray(anchor_positions, dtype=float)
+            self.anchor_idxs = np.unique(np.round((ap / self.xlim) * (self.L - 1)).astype(int))
+            r_idx = int(np.ceil(anchor_radius / self.dx))
+            sites = set()
+            for a in self.anchor_idxs:
+                sites.update(range(max(0, a - r_idx), min(self.L - 1, a + r_idx) + 1))
+            self.anchor_idx_array = np.array(sorted(sites), dtype=int)
+            self.is_anchor_site[self.anchor_idx_array] = True
+        self._has_anchors = anchor_positions is not None
         if self.periodic:
             raise NotImplementedError("periodic=True is outside the accelerated path (no shipped driver uses it)")
         self._kernel = None
@@ -160,7 +171,10 @@ class ParticleSystem:
                             lam=self.rate_active, T=T, times_obs=times_obs, betas=[float(self.beta)], n=[n],
                             pos0=np.asarray(pos, dtype=np.int32).reshape(1, -1) if n else np.zeros((1, 1), np.int32),
                             sigma0=np.asarray(sigma, dtype=np.int8).reshape(1, -1) if n else np.ones((1, 1), np.int8),
-                            seeds=seeds, record=record, crowding=self.crowding_suppresses_rates, dx=self.dx)
+                            seeds=seeds, record=record, crowding=self.crowding_suppresses_rates, dx=self.dx,
+                            anchor_mask=self.is_anchor_site if self._has_anchors else None, k_on=self.k_on, k_off=self.k_off,
+                            k_exit=self.k_exit, suppress_flip_when_bound=self.suppress_flip_when_bound,
+                            immobilize_when_anchored=self.immobilize_when_anchored)
 
     def run(self, T=10.0, obs_dt=0.01, record_fft=False, record_var=False):
         import torch
@@ -187,8 +201,11 @@ class ParticleSystem:
         rho_p, rho_m, total, var = rb.expand(want_var=record_fft and record_var)
         out_pos = rb.obs_pos[0].cpu().numpy()
         sig_sum = rb.obs_sigma_sum[0].cpu().numpy()
+        counts = rb.obs_n[0].cpu().numpy()                        # particles per row (exits shrink the system)
+        bounds = rb.obs_bound[0].cpu().numpy().astype(bool) if rb.obs_bound is not None else None
         m_global = np.zeros(M, dtype=float)
-        m_global[:n_obs] = sig_sum[:n_obs] / float(n)
+        m_global[:n_obs] = sig_sum[:n_obs] / counts[:n_obs].astype(float)
+        n_exit = int(rb.n_exit.item()) if rb.n_exit is not None else 0
         rho_hat = fft_amp = None
         if record_fft:
             hat = torch.fft.fft(total[0], dim=-1)
@@ -202,19 +219,20 @@ class ParticleSystem:
                                   mode="philox" if native else "replay")
         return {
             "times_obs": times_obs,
-            "pos_list": [out_pos[m, :n].astype(np.int64) if m < n_obs else None for m in range(M)],
+            "pos_list": [out_pos[m, :counts[m]].astype(np.int64) if m < n_obs else None for m in range(M)],
             "rho_p_list": rho_p[0].cpu().numpy(),
             "rho_m_list": rho_m[0].cpu().numpy(),
             "total_list": total[0].cpu().numpy(),
-            "particle_count_list": [n if m < n_obs else None for m in range(M)],
-            "bound_list": [np.zeros(n, dtype=bool) if m < n_obs else None for m in range(M)],
+            "particle_count_list": [int(counts[m]) if m < n_obs else None for m in range(M)],
+            "bound_list": [(bounds[m, :counts[m]].copy() if bounds is not None else np.zeros(counts[m], dtype=bool))
+                           if m < n_obs else None for m in range(M)],
             "m_local_list": rb.obs_m_local[0].cpu().numpy(),
             "m_global": m_global,
             "rho_hat_complex": rho_hat,
             "fft_amp_list": fft_amp,
             "var_list": var_list,
-            "exit_times": [],
-            "exit_positions": [],
+            "exit_times": rb.exit_t[0, :n_exit].cpu().numpy().tolist() if n_exit else [],
+            "exit_positions": rb.exit_pos[0, :n_exit].cpu().numpy().astype(np.int64).tolist() if n_exit else [],
         }
 
     # per event the reference calls rng.exponential(1/R), rng.choice(n, p=...), rng.random() and, for a
@@ -239,6 +257,9 @@ class ParticleSystem:
         rb.pos_end.copy_(rb.pos0)
         rb.sigma_end.copy_(rb.sigma0)
         rb.pos0, rb.sigma0 = rb.pos_end, rb.sigma_end          # in-place state: each launch resumes
+        rb.n_end.copy_(rb.n)
+        rb.n = rb.n_end                                        # exits shrink n between launches
+        rb.bound0 = rb.bound_end                               # None without anchors
         resume = dict(t_start=rb.t_end, obs_start=rb.n_obs, ev_start=rb.n_events)
         off = torch.tensor([0, 0], dtype=torch.int64, device=rb.dev)
         prefix = np.empty(0, dtype=np.float64)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APS_ABI_VERSION 1
+#define APS_ABI_VERSION 2
 
 typedef enum aps_status {
     APS_OK = 0,
@@ -51,6 +51,8 @@ typedef enum aps_status {
 
 /* aps_params.flags */
 #define APS_FLAG_CROWDING 1u    /* crowding_suppresses_rates=True (CLASS.py:322-336)              */
+#define APS_FLAG_SUPPRESS_FLIP_BOUND 2u  /* suppress_flip_when_bound=True (CLASS.py:266-267)      */
+#define APS_FLAG_IMMOBILIZE 4u  /* immobilize_when_anchored=True (CLASS.py:307-312,338-340)       */
 
 /* aps_batch.record */
 #define APS_REC_COUNTS 1u       /* obs_cp / obs_cm                                                */
@@ -62,6 +64,9 @@ typedef enum aps_status {
 #define APS_EV_DIFF_RIGHT 1
 #define APS_EV_ACTIVE 2
 #define APS_EV_FLIP 3
+#define APS_EV_BIND 4           /* anchors only: bound[i] = True   (CLASS.py:418-419)             */
+#define APS_EV_UNBIND 5         /* bound[i] = False                (CLASS.py:421-422)             */
+#define APS_EV_EXIT 6           /* particle leaves the system      (CLASS.py:424-436)             */
 
 /* Model parameters shared by every replica of one launch (constructor arguments of
  * ParticleSystem after the optional dx-rescaling, CLASS.py:41-50,84). */
@@ -74,6 +79,9 @@ typedef struct aps_params {
     double rate_diffusion;  /* D                                                                  */
     double rate_active;     /* lambda (sigma=+1 particles hop right only, CLASS.py:276,317-319)   */
     double T;               /* run(T=...)                                                         */
+    double k_on;            /* binding rate at anchor sites (only used when aps_batch.anchor_mask) */
+    double k_off;           /* unbinding rate                                                     */
+    double k_exit;          /* exit rate of bound '-' particles on anchor sites                   */
 } aps_params;
 
 /* One launch = n_replicas independent ParticleSystem.run() calls.  Optional pointers may be NULL. */
@@ -128,6 +136,17 @@ typedef struct aps_batch {
     /* optional: use this magnetisation field instead of computing it (step_gillespie takes m_field
      * as an argument, CLASS.py:254,261); only meaningful with max_events = 1 */
     const double* m_field_in;   /* [n_replicas][L]                                                */
+    /* anchors / binding / exit (CLASS.py:88-104,307-312,343-348,418-436); all NULL = no anchors         */
+    const uint8_t* anchor_mask; /* [L] is_anchor_site, shared by all replicas                     */
+    const int8_t* bound0;       /* [n_replicas][n_max] optional initial bound flags (resume)      */
+    int32_t* n_end;             /* [n_replicas] particle count at the end (exits shrink it)       */
+    int8_t* bound_end;          /* [n_replicas][n_max]                                            */
+    int32_t* obs_n;             /* [n_replicas][M] particle count at each observation             */
+    int8_t* obs_bound;          /* [n_replicas][M][n_max] bound flags at each observation         */
+    double* exit_t;             /* [n_replicas][exit_cap] clock at the start of the exit step     */
+    int32_t* exit_pos;          /* [n_replicas][exit_cap] site the particle left from             */
+    int32_t* n_exit;            /* [n_replicas] exits recorded (in: previous count when resuming) */
+    int64_t exit_cap;
 } aps_batch;
 
 int aps_abi_version(void);
@@ -186,6 +205,7 @@ typedef struct aps_expand_args {
     double* rho_m;              /* optional                                                       */
     double* total;              /* optional                                                       */
     double* var;                /* [n_replicas][M] optional: np.var(total row), numpy's order     */
+    const int32_t* obs_n;       /* [n_replicas][M] optional per-row particle count (exits); else n */
 } aps_expand_args;
 int aps_expand_obs_device(const aps_expand_args* a, void* stream);
 

@@ -94,9 +94,11 @@ typedef struct work {
     int L, r;
     double *s, *tot, *pad, *sconv, *tconv, *m;
     double *r_left, *r_right, *r_diff, *r_act, *cvec, *rates, *cdf;
+    double *r_bind, *r_unbind, *r_exit;
     int32_t *cp, *cm;
     int64_t* pos;
     int8_t* sigma;
+    int8_t* bound;
 } work;
 
 static int work_alloc(work* w, int L, int r, int n_max) {
@@ -109,14 +111,16 @@ static int work_alloc(work* w, int L, int r, int n_max) {
     w->r_left = malloc(8 * np); w->r_right = malloc(8 * np); w->r_diff = malloc(8 * np);
     w->r_act = malloc(8 * np); w->cvec = malloc(8 * np); w->rates = malloc(8 * np); w->cdf = malloc(8 * np);
     w->cp = malloc(4 * nl); w->cm = malloc(4 * nl);
-    w->pos = malloc(8 * np); w->sigma = malloc(np);
-    return (w->s && w->tot && w->pad && w->sconv && w->tconv && w->m && w->r_left && w->r_right &&
+    w->pos = malloc(8 * np); w->sigma = malloc(np); w->bound = calloc(np, 1);
+    w->r_bind = malloc(8 * np); w->r_unbind = malloc(8 * np); w->r_exit = malloc(8 * np);
+    return (w->bound && w->r_bind && w->r_unbind && w->r_exit && w->s && w->tot && w->pad && w->sconv && w->tconv && w->m && w->r_left && w->r_right &&
             w->r_diff && w->r_act && w->cvec && w->rates && w->cdf && w->cp && w->cm && w->pos && w->sigma) ? 0 : -1;
 }
 static void work_free(work* w) {
     free(w->s); free(w->tot); free(w->pad); free(w->sconv); free(w->tconv); free(w->m);
     free(w->r_left); free(w->r_right); free(w->r_diff); free(w->r_act); free(w->cvec); free(w->rates);
     free(w->cdf); free(w->cp); free(w->cm); free(w->pos); free(w->sigma);
+    free(w->bound); free(w->r_bind); free(w->r_unbind); free(w->r_exit);
 }
 
 /* compute_local_m_field, CLASS.py:216-246 */
@@ -164,8 +168,9 @@ typedef struct draw_src {
 } draw_src;
 
 /* per-particle rates, CLASS.py:259-351 restricted to anchors=None (bind/unbind/exit rates are 0) */
-static double build_rates(work* w, const aps_params* P, int n, double beta) {
+static double build_rates(work* w, const aps_params* P, int n, double beta, const uint8_t* anchor) {
     const int L = P->L, K = P->K;
+    const int suppress = (P->flags & APS_FLAG_SUPPRESS_FLIP_BOUND) != 0, immob = (P->flags & APS_FLAG_IMMOBILIZE) != 0;
     const double D = P->rate_diffusion, lam = P->rate_active;
     const int crowd = (P->flags & APS_FLAG_CROWDING) != 0;
     for (int i = 0; i < n; ++i) {
@@ -180,6 +185,10 @@ static double build_rates(work* w, const aps_params* P, int n, double beta) {
         int r_free = (occ_r < K) && (rt != p);
         double rl = D * (double)l_free, rr = D * (double)r_free;
         double ra = (sg == 1 && f_free) ? lam : 0.0;
+        const int bnd = anchor ? w->bound[i] : 0, on_anchor = anchor ? anchor[p] : 0;
+        const int anchored = immob && sg == -1 && on_anchor && bnd;        /* :308 */
+        double rex = 0.0;
+        if (anchored) { ra = 0.0; rl = 0.0; rr = 0.0; rex = P->k_exit; }   /* :309-312 */
         if (crowd) {
             double ff = 1.0 - ((double)occ_f / (double)K);
             ff = ff < 0.0 ? 0.0 : (ff > 1.0 ? 1.0 : ff);
@@ -191,12 +200,16 @@ static double build_rates(work* w, const aps_params* P, int n, double beta) {
             rr = (D * (double)r_free) * rf;
         }
         w->r_left[i] = rl; w->r_right[i] = rr;
-        w->r_diff[i] = rl + rr;
-        w->r_act[i] = ra;
+        w->r_diff[i] = anchored ? 0.0 : rl + rr;                           /* :315,336,339 */
+        w->r_act[i] = anchored ? 0.0 : ra;                                 /* :340 */
         /* flip_rate_fn default: np.exp(-beta * sigma * m), CLASS.py:60 */
         double arg = ((-beta) * (double)sg) * w->m[p];
-        w->cvec[i] = aps_exp(arg);
-        w->rates[i] = ((((w->r_diff[i] + w->r_act[i]) + w->cvec[i]) + 0.0) + 0.0) + 0.0;
+        w->cvec[i] = (suppress && bnd) ? 0.0 : aps_exp(arg);               /* :266-267 */
+        int occ_here = w->cp[p] + w->cm[p];
+        w->r_bind[i] = (anchor && !bnd && sg == -1 && on_anchor && occ_here < K) ? P->k_on : 0.0;   /* :343-345 */
+        w->r_unbind[i] = bnd ? P->k_off : 0.0;                             /* :347-348 */
+        w->r_exit[i] = rex;
+        w->rates[i] = ((((w->r_diff[i] + w->r_act[i]) + w->cvec[i]) + w->r_bind[i]) + w->r_unbind[i]) + w->r_exit[i];
     }
     return pairwise_sum(w->rates, n);
 }
@@ -221,11 +234,16 @@ static void record_obs(const aps_params* P, const aps_batch* B, int rep, int m, 
         B->obs_sigma_sum[row] = s;
     }
     if ((B->record & APS_REC_MLOCAL) && B->obs_m_local) memcpy(B->obs_m_local + row * L, mfield_pre, 8 * L);
+    if (B->obs_n) B->obs_n[row] = n;
+    if (B->obs_bound) for (int i = 0; i < n; ++i) B->obs_bound[row * (size_t)B->n_max + i] = w->bound[i];
 }
 
 /* one ParticleSystem.run(), CLASS.py:450-558 */
 static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, work* w) {
-    const int L = P->L, n = B->n[rep], M = B->M;
+    const int L = P->L, M = B->M;
+    int n = B->n[rep];
+    const uint8_t* anchor = B->anchor_mask;
+    int n_exit = (B->n_exit && B->ev_start) ? B->n_exit[rep] : 0;
     const double beta = B->beta[rep], T = P->T;
     int64_t n_events = B->ev_start ? B->ev_start[rep] : 0;
     const int64_t ev_base = n_events;
@@ -243,6 +261,7 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
     for (int i = 0; i < n; ++i) {
         w->pos[i] = B->pos0[(size_t)rep * B->n_max + i];
         w->sigma[i] = B->sigma0[(size_t)rep * B->n_max + i];
+        w->bound[i] = B->bound0 ? B->bound0[(size_t)rep * B->n_max + i] : 0;
         if (w->sigma[i] == 1) w->cp[w->pos[i]]++; else w->cm[w->pos[i]]++;
     }
     if (n == 0) { status = APS_RUN_EMPTY; goto done; }
@@ -255,7 +274,8 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
         if (B->max_events > 0 && n_events - ev_base >= B->max_events) { status = APS_RUN_MAX_EVENTS; break; }
         if (B->m_field_in) memcpy(w->m, B->m_field_in + (size_t)rep * (size_t)L, 8 * (size_t)L);
         else m_field(w, P, B->weights);                                  /* :512 */
-        double R = build_rates(w, P, n, beta);                           /* :259-352 */
+        if (n == 0) { status = APS_RUN_EMPTY; break; }                   /* :256-257 (every particle has exited) */
+        double R = build_rates(w, P, n, beta, anchor);                   /* :259-352 */
         if (!(R > 0)) { status = APS_RUN_EMPTY; break; }                 /* :353-355 */
         double e, u_choice, u_event;
         if (mode == 0) {
@@ -280,6 +300,9 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
         double v = u_event * w->rates[sel];                              /* :362 */
         double diff_thresh = w->r_diff[sel];
         double act_thresh = diff_thresh + w->r_act[sel];
+        double bind_thresh = act_thresh + w->r_bind[sel];                /* :365-367 */
+        double unbind_thresh = bind_thresh + w->r_unbind[sel];
+        double exit_thresh = unbind_thresh + w->r_exit[sel];
         int old_pos = (int)w->pos[sel], new_pos = old_pos, kind;
         if (v < diff_thresh) {                                           /* :371-398 */
             double rl = w->r_left[sel], rr = w->r_right[sel];
@@ -293,8 +316,22 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
             else { new_pos = clipi((int64_t)old_pos + 1, 0, L - 1); kind = APS_EV_DIFF_RIGHT; }
         } else if (v < act_thresh) {                                     /* :400-416 */
             new_pos = clipi((int64_t)old_pos + (w->sigma[sel] == 1), 0, L - 1); kind = APS_EV_ACTIVE;
-        } else kind = APS_EV_FLIP;                                       /* :438-446 */
-        if (kind == APS_EV_FLIP) {
+        } else if (v < bind_thresh) kind = APS_EV_BIND;                  /* :418-419 */
+        else if (v < unbind_thresh) kind = APS_EV_UNBIND;                /* :421-422 */
+        else if (v < exit_thresh) kind = APS_EV_EXIT;                    /* :424-436 */
+        else kind = APS_EV_FLIP;                                         /* :438-446 */
+        if (kind == APS_EV_BIND) w->bound[sel] = 1;
+        else if (kind == APS_EV_UNBIND) w->bound[sel] = 0;
+        else if (kind == APS_EV_EXIT) {
+            if (B->exit_t && n_exit < B->exit_cap) {
+                B->exit_t[(size_t)rep * (size_t)B->exit_cap + n_exit] = t;               /* clock BEFORE this step's tau */
+                B->exit_pos[(size_t)rep * (size_t)B->exit_cap + n_exit] = old_pos;
+            }
+            n_exit++;
+            if (w->sigma[sel] == 1) w->cp[old_pos]--; else w->cm[old_pos]--;
+            for (int i = sel; i + 1 < n; ++i) { w->pos[i] = w->pos[i + 1]; w->sigma[i] = w->sigma[i + 1]; w->bound[i] = w->bound[i + 1]; }
+            n--;                                                                          /* np.delete, :434-436 */
+        } else if (kind == APS_EV_FLIP) {
             if (w->sigma[sel] == 1) { w->sigma[sel] = -1; w->cp[old_pos]--; w->cm[old_pos]++; }
             else { w->sigma[sel] = 1; w->cm[old_pos]--; w->cp[old_pos]++; }
         } else {
@@ -305,7 +342,7 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
         if (mode == 0) { ds.d += 3; ds.left -= 3; }
         if (B->trace && n_events - ev_base < B->trace_cap) {
             int32_t* tr = B->trace + ((size_t)rep * (size_t)B->trace_cap + (size_t)(n_events - ev_base)) * 3;
-            tr[0] = sel; tr[1] = kind; tr[2] = (kind == APS_EV_FLIP) ? -1 : new_pos;
+            tr[0] = sel; tr[1] = kind; tr[2] = (kind <= APS_EV_ACTIVE) ? new_pos : (kind == APS_EV_EXIT ? old_pos : -1);
         }
         n_events++;
         t += tau;                                                        /* :514 */
@@ -325,6 +362,9 @@ done:
     if (B->draws_used) B->draws_used[rep] = (mode == 0 && draws_begin) ? (int64_t)(ds.d - draws_begin) : 0;
     if (B->pos_end) for (int i = 0; i < n; ++i) B->pos_end[(size_t)rep * B->n_max + i] = (int32_t)w->pos[i];
     if (B->sigma_end) for (int i = 0; i < n; ++i) B->sigma_end[(size_t)rep * B->n_max + i] = w->sigma[i];
+    if (B->bound_end) for (int i = 0; i < n; ++i) B->bound_end[(size_t)rep * B->n_max + i] = w->bound[i];
+    if (B->n_end) B->n_end[rep] = n;
+    if (B->n_exit) B->n_exit[rep] = n_exit;
 }
 
 typedef struct targ { const aps_params* P; const aps_batch* B; int mode; int tid, nthreads; int rc; } targ;

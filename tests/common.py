@@ -28,15 +28,19 @@ def load_case(name):
 def params_from_case(c, T=None):
     m = c["meta"]
     flags = capi.APS_FLAG_CROWDING if m["ps"].get("crowding_suppresses_rates") else 0
+    if m.get("anchors"):
+        flags |= (capi.APS_FLAG_SUPPRESS_FLIP_BOUND if m["suppress"] else 0) | (capi.APS_FLAG_IMMOBILIZE if m["immobilize"] else 0)
     return make_params(m["L"], m["K"], m["radius"], m["rate_diffusion"], m["rate_active"],
-                       m["run"]["T"] if T is None else T, flags)
+                       m["run"]["T"] if T is None else T, flags, k_on=m.get("k_on", 0.0), k_off=m.get("k_off", 0.0),
+                       k_exit=m.get("k_exit", 0.0))
 
 
 class HostRun:
     """Host-side buffers for one batch; `.batch` is the aps_batch pointing at them."""
 
     def __init__(self, L, n_max, M, n, pos0, sigma0, beta, times_obs, weights, draws=None, draw_off=None,
-                 seeds=None, record=7, trace_cap=0, max_events=0, t_start=None, obs_start=None, ev_start=None):
+                 seeds=None, record=7, trace_cap=0, max_events=0, t_start=None, obs_start=None, ev_start=None,
+                 anchor_mask=None, bound0=None, exit_cap=0):
         R = len(n)
         self.R, self.L, self.n_max, self.M = R, L, n_max, M
         self.n = np.ascontiguousarray(n, dtype=np.int32)
@@ -66,8 +70,19 @@ class HostRun:
         self.pos_end = np.full((R, n_max), -1, np.int32)
         self.sigma_end = np.zeros((R, n_max), np.int8)
         self.trace = np.full((R, max(trace_cap, 1), 3), -5, np.int32) if trace_cap else None
+        self.anchor_mask = None if anchor_mask is None else np.ascontiguousarray(anchor_mask, dtype=np.uint8)
+        self.bound0 = None if bound0 is None else np.ascontiguousarray(bound0, dtype=np.int8).reshape(R, n_max)
+        self.n_end = np.full(R, -1, np.int32)
+        self.bound_end = np.zeros((R, n_max), np.int8)
+        self.obs_n = np.full((R, Mr), -1, np.int32)
+        self.obs_bound = np.zeros((R, Mr, n_max), np.int8)
+        self.exit_t = np.full((R, max(exit_cap, 1)), np.nan, np.float64)
+        self.exit_pos = np.full((R, max(exit_cap, 1)), -1, np.int32)
+        self.n_exit = np.zeros(R, np.int32)
         self.batch, self._keep = make_batch(
-            R, n_max, M, record=record, max_events=max_events, trace_cap=trace_cap,
+            R, n_max, M, record=record, max_events=max_events, trace_cap=trace_cap, exit_cap=exit_cap,
+            anchor_mask=self.anchor_mask, bound0=self.bound0, n_end=self.n_end, bound_end=self.bound_end, obs_n=self.obs_n,
+            obs_bound=self.obs_bound, exit_t=self.exit_t, exit_pos=self.exit_pos, n_exit=self.n_exit,
             times_obs=self.times_obs, weights=self.weights, beta=self.beta, n=self.n, pos0=self.pos0,
             sigma0=self.sigma0, draws=self.draws, draw_off=self.draw_off, seeds=self.seeds,
             t_start=self.t_start, obs_start=self.obs_start, ev_start=self.ev_start,
@@ -77,7 +92,8 @@ class HostRun:
             sigma_end=self.sigma_end, trace=self.trace)
 
     OUT_FIELDS = ["obs_cp", "obs_cm", "obs_pos", "obs_sigma_sum", "obs_m_local", "n_obs", "n_events", "t_end",
-                  "status", "draws_used", "pos_end", "sigma_end", "trace"]
+                  "status", "draws_used", "pos_end", "sigma_end", "trace", "n_end", "bound_end", "obs_n", "obs_bound",
+                  "exit_t", "exit_pos", "n_exit"]
 
 
 def hostrun_from_case(c, trace=True, **kw):
@@ -85,7 +101,9 @@ def hostrun_from_case(c, trace=True, **kw):
     n = m["n"]
     return HostRun(m["L"], max(n, 1), len(c["times_obs"]), [n], c["pos0"], c["sigma0"], [m["ps"]["beta"]],
                    c["times_obs"], c["weights"], draws=c["draws"], draw_off=[0, len(c["draws"])],
-                   trace_cap=(len(c["trace"]) + 4) if trace else 0, **kw)
+                   trace_cap=(len(c["trace"]) + 4) if trace else 0,
+                   anchor_mask=c["anchor_mask"] if m.get("anchors") else None,
+                   exit_cap=(len(c["exit_times"]) + 4) if m.get("anchors") else 0, **kw)
 
 
 def run_oracle(params, hr, mode=0, threads=1):
@@ -121,14 +139,28 @@ def assert_matches_reference(c, hr: HostRun, rep=0):
     assert hr.draws_used[rep] == len(c["draws"])
     if hr.trace is not None:
         assert np.array_equal(hr.trace[rep, :n_ev], c["trace"]), "event trace differs from the reference"
-    denom = float(max(1, n)) * m["dx"]
+    n_t = hr.obs_n[rep, :n_obs].astype(np.int64)                  # particle count per row (exits shrink it)
+    if "count_obs" in c:
+        assert np.array_equal(n_t, c["count_obs"][:n_obs])
+    else:
+        assert (n_t == n).all()
+    denom = np.maximum(1, n_t).astype(float)[:, None] * m["dx"]
     rho_p = hr.obs_cp[rep, :n_obs].astype(np.int64) / denom      # CLASS.py:205-213
     rho_m = hr.obs_cm[rep, :n_obs].astype(np.int64) / denom
     assert np.array_equal(rho_p, c["rho_p_list"][:n_obs])
     assert np.array_equal(rho_m, c["rho_m_list"][:n_obs])
     assert np.array_equal(rho_p + rho_m, c["total_list"][:n_obs])
-    assert np.array_equal(hr.obs_pos[rep, :n_obs, :n], c["pos_obs"][:n_obs])
-    assert np.array_equal(hr.obs_sigma_sum[rep, :n_obs] / float(n), c["m_global"][:n_obs])
+    for row in range(n_obs):
+        k = int(n_t[row])
+        assert np.array_equal(hr.obs_pos[rep, row, :k], c["pos_obs"][row, :k])
+        if "bound_obs" in c:
+            assert np.array_equal(hr.obs_bound[rep, row, :k], c["bound_obs"][row, :k])
+    assert np.array_equal(hr.obs_sigma_sum[rep, :n_obs] / n_t.astype(float), c["m_global"][:n_obs])
+    if "exit_times" in c:
+        ne = len(c["exit_times"])
+        assert hr.n_exit[rep] == ne and hr.n_end[rep] == n - ne
+        assert np.array_equal(hr.exit_pos[rep, :ne], c["exit_positions"])
+        np.testing.assert_allclose(hr.exit_t[rep, :ne], c["exit_times"], rtol=1e-13)   # clock: exp/log differ by <= 1 ulp
     got, want = hr.obs_m_local[rep, :n_obs], c["m_local_list"][:n_obs]
     assert np.array_equal(got, want), f"m_local differs: max abs {np.abs(got - want).max()}"
     # rows never reached stay zero in the reference (CLASS.py:466-472)

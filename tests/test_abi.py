@@ -33,13 +33,13 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, n), f"{n} declared in include/aps.h but not exported"
         assert n in capi.SYMBOLS, f"{n} has no ctypes prototype in capi.py"
     assert sorted(capi.SYMBOLS) == names
-    assert lib.aps_abi_version() == 1
+    assert lib.aps_abi_version() == 2
 
 
 def test_struct_layout_matches_header(lib):
-    # sizes the C compiler gives the two descriptors (x86-64 SysV): 4 int32 + 3 double; 4 int32 + 3 int64 + 27 pointers
-    assert C.sizeof(capi.ApsParams) == 40
-    assert C.sizeof(capi.ApsBatch) == 16 + 24 + 27 * 8
+    # sizes the C compiler gives the two descriptors (x86-64 SysV): 4 int32 + 6 double; 4 int32 + 3 int64 + 36 pointers + exit_cap
+    assert C.sizeof(capi.ApsParams) == 64
+    assert C.sizeof(capi.ApsBatch) == 16 + 24 + 36 * 8 + 8
 
 
 def test_invalid_arguments_are_rejected(lib):

@@ -53,8 +53,11 @@ def test_same_seed_same_output_dict(name):
         assert np.array_equal(out[k], c[k]), k
     for mm in range(len(c["times_obs"])):
         if mm < n_obs:
-            assert out["pos_list"][mm].dtype == np.int64 and np.array_equal(out["pos_list"][mm], c["pos_obs"][mm])
-            assert out["particle_count_list"][mm] == m["n"] and out["bound_list"][mm].dtype == bool
+            k = int(c["count_obs"][mm]) if "count_obs" in c else m["n"]          # exits shrink the system
+            assert out["pos_list"][mm].dtype == np.int64 and np.array_equal(out["pos_list"][mm], c["pos_obs"][mm][:k])
+            assert out["particle_count_list"][mm] == k and out["bound_list"][mm].dtype == bool
+            if "bound_obs" in c:
+                assert np.array_equal(out["bound_list"][mm], c["bound_obs"][mm][:k].astype(bool))
         else:
             assert out["pos_list"][mm] is None and out["particle_count_list"][mm] is None
     if m["run"]["record_fft"]:
@@ -64,6 +67,9 @@ def test_same_seed_same_output_dict(name):
         assert np.abs(out["rho_hat_complex"][:, :32] - c["rho_hat_head"]).max() <= 1e-9 * scale
     else:
         assert out["rho_hat_complex"] is None and out["fft_amp_list"] is None
+    if "exit_times" in c:
+        assert out["exit_positions"] == c["exit_positions"].tolist()
+        np.testing.assert_allclose(out["exit_times"], c["exit_times"], rtol=1e-13)
     # the generator is left exactly where the reference leaves it
     ref_rng = np.random.default_rng(m["seed"])
     # (consumption of init + events is replayed implicitly: next variate must match a fresh replay)

@@ -29,18 +29,26 @@ class OracleBackedBatch:
         self.dev = "cpu"
         self.P = params_from_case(c)
         self.hr = HostRun(m["L"], n, len(c["times_obs"]), [n], pos.astype(np.int32), sigma, [m["ps"]["beta"]],
-                          c["times_obs"], c["weights"], draws=np.zeros(4), draw_off=[0, 4])
+                          c["times_obs"], c["weights"], draws=np.zeros(4), draw_off=[0, 4],
+                          anchor_mask=c["anchor_mask"] if m.get("anchors") else None, exit_cap=n)
+        if m.get("anchors"):
+            self.hr_anchor = True
         hr = self.hr
         self.pos0, self.sigma0, self.pos_end, self.sigma_end = _T(hr.pos0), _T(hr.sigma0), _T(hr.pos_end), _T(hr.sigma_end)
         self.t_end, self.n_obs, self.n_events = _T(hr.t_end), _T(hr.n_obs), _T(hr.n_events)
         self.status, self.draws_used = _T(hr.status), _T(hr.draws_used)
+        self.n, self.n_end, self.bound_end, self.bound0 = _T(hr.n), _T(hr.n_end), None, None
         self.launches = []
 
     def run_replay(self, d, off, resume=None, max_events=0, spec_from=-1):
         hr = self.hr
         dr = np.ascontiguousarray(d.numpy()); of = np.ascontiguousarray(off.numpy())
-        b, keep = make_batch(1, hr.n_max, hr.M, record=7, spec_from=spec_from, max_events=max_events,
-                             times_obs=hr.times_obs, weights=hr.weights, beta=hr.beta, n=hr.n, pos0=self.pos0.a,
+        anch = hr.anchor_mask is not None
+        b, keep = make_batch(1, hr.n_max, hr.M, record=7, spec_from=spec_from, max_events=max_events, exit_cap=hr.n_max if anch else 0,
+                             anchor_mask=hr.anchor_mask, bound0=hr.bound_end if anch else None, bound_end=hr.bound_end if anch else None,
+                             obs_bound=hr.obs_bound if anch else None, exit_t=hr.exit_t if anch else None,
+                             exit_pos=hr.exit_pos if anch else None, n_exit=hr.n_exit if anch else None, n_end=hr.n_end, obs_n=hr.obs_n,
+                             times_obs=hr.times_obs, weights=hr.weights, beta=hr.beta, n=self.n.a, pos0=self.pos0.a,
                              sigma0=self.sigma0.a, draws=dr, draw_off=of, t_start=hr.t_end, obs_start=hr.n_obs,
                              ev_start=hr.n_events, obs_cp=hr.obs_cp, obs_cm=hr.obs_cm, obs_pos=hr.obs_pos,
                              obs_sigma_sum=hr.obs_sigma_sum, obs_m_local=hr.obs_m_local, n_obs=hr.n_obs,
@@ -55,7 +63,8 @@ def build(c, rng):
     return T.build(c, rng)
 
 
-@pytest.mark.parametrize("name", ["c2_sweep_b0", "tiny_diffusive", "k1_dense", "crowding", "c1_exclusion"])
+@pytest.mark.parametrize("name", ["c2_sweep_b0", "tiny_diffusive", "k1_dense", "crowding", "c1_exclusion", "anchors_k3",
+                                  "anchors_crowding_global"])
 def test_chunked_replay_with_rewind(name, monkeypatch):
     c = load_case(name)
     m = c["meta"]

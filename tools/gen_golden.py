@@ -75,7 +75,8 @@ class RecordingRNG:
             self.log.append(u)
             cdf = np.asarray(p).cumsum()
             cdf /= cdf[-1]
-            return int(cdf.searchsorted(u, side="right"))
+            self.last_choice = int(cdf.searchsorted(u, side="right"))
+            return self.last_choice
         return self.gen.choice(a, size=size, replace=replace, p=p)
 
     def random(self):
@@ -159,6 +160,18 @@ def cases():
         c[f"sparse_events_{k}"] = dict(ps=dict(L=8, xlim=1, rate_diffusion=0.1, rate_active=0.1, beta=0.0, init="fixed", N=2,
                                                scale_rates=False, local_kernel_sigma=0.2, site_capacity=1),
                                        run=dict(T=1.0, obs_dt=0.9, record_fft=False, record_var=False), seed=seed)
+    anch = dict(anchor_positions=[0.25, 0.60, 0.80], anchor_radius=0.01, k_on=10, k_off=5, k_exit=5)
+    c["anchors_k3"] = dict(ps=dict(L=200, xlim=1, rate_diffusion=0.5, rate_active=3, beta=1.0, init="fixed", N=150,
+                                   scale_rates=False, local_kernel_sigma=0.02, site_capacity=3, **anch),
+                           run=dict(T=2.0, obs_dt=0.25, record_fft=False, record_var=False), seed=1515)
+    c["anchors_free_flip"] = dict(ps=dict(L=120, xlim=1, rate_diffusion=0.3, rate_active=2, beta=0.5, init="fixed", N=90,
+                                          scale_rates=False, local_kernel_sigma=0.03, site_capacity=2,
+                                          immobilize_when_anchored=False, suppress_flip_when_bound=False, **anch),
+                                  run=dict(T=2.0, obs_dt=0.25, record_fft=False, record_var=False), seed=1616)
+    c["anchors_crowding_global"] = dict(ps=dict(L=100, xlim=1, rate_diffusion=0.4, rate_active=2, beta=1.5, init="fixed", N=120,
+                                                scale_rates=False, local_kernel_sigma=0.0, site_capacity=3,
+                                                crowding_suppresses_rates=True, **dict(anch, k_exit=20)),
+                                        run=dict(T=3.0, obs_dt=0.25, record_fft=False, record_var=False), seed=1717)
     c["poisson_k2"] = dict(ps=dict(L=200, xlim=1, rate_diffusion=0.3, rate_active=4, beta=1.8, init="poisson", N=260,
                                    scale_rates=False, local_kernel_sigma=0.01, site_capacity=2),
                            profile=dict(L=200, N=260, frac_plus=0.6, decay_plus=0.5),
@@ -202,20 +215,24 @@ def run_case(PS, name, spec):
     orig_step = ps.step_gillespie
 
     def step_hook(pos, sigma, bound, *a):
-        p0, s0, nlog = pos.copy(), sigma.copy(), len(rec.log)
+        p0, s0, b0, nlog = pos.copy(), sigma.copy(), bound.copy(), len(rec.log)
         res = orig_step(pos, sigma, bound, *a)
         used = len(rec.log) - nlog
-        dp = np.nonzero(res[0] != p0)[0]
-        dsg = np.nonzero(res[1] != s0)[0]
-        if dsg.size == 1 and dp.size == 0:
-            trace.append((int(dsg[0]), 3, -1))
-        elif dp.size == 1 and dsg.size == 0:
-            i = int(dp[0])
+        i = rec.last_choice                       # the particle rng.choice picked (CLASS.py:360)
+        if res[0].size < p0.size:
+            assert np.array_equal(res[0], np.delete(p0, i)) and np.array_equal(res[1], np.delete(s0, i))
+            trace.append((i, 6, int(p0[i])))
+        elif res[2][i] != b0[i]:
+            trace.append((i, 4 if res[2][i] else 5, -1))
+        elif res[1][i] != s0[i]:
+            trace.append((i, 3, -1))
+        elif res[0][i] != p0[i]:
             step = int(res[0][i] - p0[i])
             kind = (0 if step < 0 else 1) if used == 4 else 2
             trace.append((i, kind, int(res[0][i])))
         else:
-            raise RuntimeError("event did not change exactly one particle")
+            raise RuntimeError("event did not change the selected particle")
+        assert (res[0] != p0[:res[0].size]).sum() <= (res[0].size if res[0].size < p0.size else 1)
         return res
 
     ps.step_gillespie = step_hook
@@ -230,8 +247,13 @@ def run_case(PS, name, spec):
 
     n = captured["pos0"].size
     pos_obs = np.full((len(out["pos_list"]), n), -1, dtype=np.int32)
+    bound_obs = np.zeros((len(out["pos_list"]), n), dtype=np.int8)
+    count_obs = np.zeros(len(out["pos_list"]), dtype=np.int32)
     for m in range(n_obs):
-        pos_obs[m] = out["pos_list"][m]
+        k = out["pos_list"][m].size
+        pos_obs[m, :k] = out["pos_list"][m]
+        bound_obs[m, :k] = out["bound_list"][m]
+        count_obs[m] = out["particle_count_list"][m]
     radius = -1
     weights = np.zeros(0)
     if ps.local_kernel_sigma > 0:
@@ -241,6 +263,8 @@ def run_case(PS, name, spec):
     meta = dict(name=name, ps=spec["ps"], run=spec["run"], seed=seed, profile=spec.get("profile"),
                 dx=ps.dx, rate_diffusion=ps.rate_diffusion, rate_active=ps.rate_active, K=ps.K, L=ps.L,
                 radius=radius, n=int(n), n_obs=int(n_obs), n_events=len(trace),
+                anchors=bool(ps.is_anchor_site.any()), k_on=float(ps.k_on), k_off=float(ps.k_off), k_exit=float(ps.k_exit),
+                suppress=bool(ps.suppress_flip_when_bound), immobilize=bool(ps.immobilize_when_anchored),
                 numpy=np.__version__, scipy=__import__("scipy").__version__)
     save = dict(
         meta=np.array(json.dumps(meta)),
@@ -252,6 +276,8 @@ def run_case(PS, name, spec):
         trace=np.asarray(trace, dtype=np.int32).reshape(-1, 3),
         rho_p_list=out["rho_p_list"], rho_m_list=out["rho_m_list"], total_list=out["total_list"],
         m_local_list=out["m_local_list"], m_global=out["m_global"], pos_obs=pos_obs,
+        bound_obs=bound_obs, count_obs=count_obs, anchor_mask=ps.is_anchor_site.astype(np.uint8),
+        exit_times=np.asarray(out["exit_times"], dtype=np.float64), exit_positions=np.asarray(out["exit_positions"], dtype=np.int32),
     )
     if out["var_list"] is not None:
         save["var_list"] = out["var_list"]
