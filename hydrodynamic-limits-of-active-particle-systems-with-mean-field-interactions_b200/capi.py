@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(PKG_DIR, "csrc", "libaps_b200.so")
 APS_OK = 0
 APS_ERR_INVALID, APS_ERR_NO_DEVICE, APS_ERR_CUDA, APS_ERR_CAPACITY = 1, 2, 3, 4
 APS_RUN_DONE, APS_RUN_EMPTY, APS_RUN_DRAWS_EXHAUSTED, APS_RUN_MAX_EVENTS = 0, 1, 2, 3
-APS_FLAG_CROWDING, APS_FLAG_SUPPRESS_FLIP_BOUND, APS_FLAG_IMMOBILIZE = 1, 2, 4
+APS_FLAG_CROWDING, APS_FLAG_SUPPRESS_FLIP_BOUND, APS_FLAG_IMMOBILIZE, APS_FLAG_PERIODIC = 1, 2, 4, 8
 APS_REC_COUNTS, APS_REC_POS, APS_REC_MLOCAL = 1, 2, 4
 APS_EV_DIFF_LEFT, APS_EV_DIFF_RIGHT, APS_EV_ACTIVE, APS_EV_FLIP = 0, 1, 2, 3
 APS_EV_BIND, APS_EV_UNBIND, APS_EV_EXIT = 4, 5, 6

@@ -70,6 +70,8 @@ int validate(const aps_params* p, const aps_batch* b, bool philox) {
     if (b->M < 1) return fail(APS_ERR_INVALID, "need at least one observation time (M >= 1)");
     if (!b->times_obs || !b->beta || !b->n || !b->pos0 || !b->sigma0) return fail(APS_ERR_INVALID, "missing required input pointer");
     if (p->radius >= 0 && !b->weights) return fail(APS_ERR_INVALID, "weights required when radius >= 0");
+    if ((p->flags & APS_FLAG_PERIODIC) && p->radius >= 0 && 2 * (int64_t)p->radius + 1 > p->L)
+        return fail(APS_ERR_INVALID, "periodic field needs 2*radius+1 <= L (truncate the ring kernel)");
     if (philox && !b->seeds) return fail(APS_ERR_INVALID, "seeds required in native (Philox) mode");
     if (!philox && (!b->draws || !b->draw_off)) return fail(APS_ERR_INVALID, "draws/draw_off required in replay mode");
     return APS_OK;
@@ -116,7 +118,7 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     cudaStream_t st = (cudaStream_t)stream;
     a.only_retry = 0; a.reserved = 0;
     // specialised kernel for K = 1 with a local field (every shipped sweep configuration)
-    const bool fast_ok = g_use_fast && p->K == 1 && p->radius >= 0 && p->radius < p->L && !(p->flags & APS_FLAG_CROWDING) &&
+    const bool fast_ok = g_use_fast && p->K == 1 && p->radius >= 0 && p->radius < p->L && !(p->flags & (APS_FLAG_CROWDING | APS_FLAG_PERIODIC)) &&
                          !b->m_field_in && !b->anchor_mask && b->n_max <= 1024 && b->status != nullptr;
     if (fast_ok) {
         int launched = 0;
@@ -275,6 +277,8 @@ int aps_init_particles_device(const aps_init_args* a, void* stream) {
 int aps_m_field_host(const aps_params* p, const double* weights, const int32_t* cp, const int32_t* cm, double* out) {
     if (!p || !cp || !cm || !out || p->L < 1 || p->L > 65535 || (p->radius >= 0 && !weights))
         return fail(APS_ERR_INVALID, "aps_m_field_host: bad argument");
+    if ((p->flags & APS_FLAG_PERIODIC) && p->radius >= 0 && 2 * (int64_t)p->radius + 1 > p->L)
+        return fail(APS_ERR_INVALID, "periodic field needs 2*radius+1 <= L (truncate the ring kernel)");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
     const int pad = p->radius > 0 ? p->radius : 0;
     const size_t L = (size_t)p->L, smem = (size_t)(pad + 1) * 8 + (L + 2 * (size_t)pad) * 2 + 16;

@@ -87,6 +87,7 @@ struct Smem {
     int8_t* bound;        // bound flags (anchors only; all zero otherwise)
     uint8_t* anchor;      // is_anchor_site, or nullptr when the batch has no anchors
     const double* m_in;   // optional injected field (global memory), see aps_batch.m_field_in
+    int periodic;         // APS_FLAG_PERIODIC: the halo holds wrapped images and hops wrap
 };
 
 __device__ __forceinline__ Smem carve(unsigned char* base, int L, int n_max, int pad, int max_nodes, int nwarps,
@@ -121,10 +122,19 @@ enum { D_SEQ = 0, D_PART, D_KIND, D_OLD, D_NEW, D_STOP, D_EXACT, D_NCROSS, D_END
 enum { X_TNEW = 0, X_R };
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// target of a hop by d = -1, 0, +1 from p: reflecting walls clamp, a ring wraps (CLASS.py:278-288)
+__device__ __forceinline__ int hop_target(int p, int d, int L, bool per) {
+    int q = p + d;
+    return per ? (q < 0 ? q + L : (q >= L ? q - L : q)) : clampi(q, 0, L - 1);
+}
 
-// Add `delta` to the cell of site x and to every reflect image inside the halo.
-__device__ __forceinline__ void cell_add(uint16_t* pk, int L, int pad, int x, int delta) {
-    if (pad < L) {
+// Add `delta` to the cell of site x and to every reflect (or, on a ring, wrapped) image inside the halo.
+__device__ __forceinline__ void cell_add(uint16_t* pk, int L, int pad, int x, int delta, bool per) {
+    if (per) {                           // pad <= L/2 on a ring (validated at the boundary)
+        pk[pad + x] = (uint16_t)(pk[pad + x] + delta);
+        if (x < pad) pk[pad + L + x] = (uint16_t)(pk[pad + L + x] + delta);
+        if (x >= L - pad) pk[pad + x - L] = (uint16_t)(pk[pad + x - L] + delta);
+    } else if (pad < L) {
         pk[pad + x] = (uint16_t)(pk[pad + x] + delta);
         if (x < pad) pk[pad - 1 - x] = (uint16_t)(pk[pad - 1 - x] + delta);
         if (x >= L - pad) pk[pad + 2 * L - 1 - x] = (uint16_t)(pk[pad + 2 * L - 1 - x] + delta);
@@ -141,16 +151,16 @@ __device__ __forceinline__ void cell_add(uint16_t* pk, int L, int pad, int x, in
 
 // packed counts (c_plus | c_minus<<8) and, when the product table is in use, the radix code
 __device__ __forceinline__ void pk_add(const Smem& s, int L, int pad, int x, int dplus, int dminus, int bcode, bool lut) {
-    cell_add(s.pk, L, pad, x, dplus + 256 * dminus);
-    if (lut) cell_add(s.code, L, pad, x, dplus + bcode * dminus);
+    cell_add(s.pk, L, pad, x, dplus + 256 * dminus, s.periodic != 0);
+    if (lut) cell_add(s.code, L, pad, x, dplus + bcode * dminus, s.periodic != 0);
 }
 
 __device__ __forceinline__ int occ_of(uint16_t v) { return (v & 0xff) + (v >> 8); }
 
 // Hop rates of one particle, CLASS.py:276-336 (anchors absent).
-__device__ __forceinline__ void hop_rates(const uint16_t* pk, int pad, int L, int K, double D, double lam, bool crowd,
+__device__ __forceinline__ void hop_rates(const uint16_t* pk, int pad, int L, int K, double D, double lam, bool crowd, bool per,
                                           int p, int sg, double& rl, double& rr, double& ra) {
-    int fwd = clampi(p + (sg == 1), 0, L - 1), lt = clampi(p - 1, 0, L - 1), rt = clampi(p + 1, 0, L - 1);
+    int fwd = hop_target(p, sg == 1, L, per), lt = hop_target(p, -1, L, per), rt = hop_target(p, 1, L, per);
     int occ_l = occ_of(pk[pad + lt]), occ_r = occ_of(pk[pad + rt]);
     int occ_f = (fwd == rt) ? occ_r : occ_of(pk[pad + fwd]);
     bool f_free = (occ_f < K) && (fwd != p);
@@ -178,7 +188,7 @@ struct RateParts { double rl, rr, rdiff, ract, rbind, runbind, rexit; bool no_fl
 
 __device__ __forceinline__ RateParts rate_parts(const Smem& s, const aps_params& P, int pad, bool crowd, int i, int p, int sg) {
     RateParts r;
-    hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, p, sg, r.rl, r.rr, r.ract);
+    hop_rates(s.pk, pad, P.L, P.K, P.rate_diffusion, P.rate_active, crowd, s.periodic != 0, p, sg, r.rl, r.rr, r.ract);
     r.rbind = 0.0; r.runbind = 0.0; r.rexit = 0.0; r.no_flip = false;
     r.rdiff = APS_ADD(r.rl, r.rr);
     if (s.anchor) {
@@ -331,10 +341,10 @@ __device__ __forceinline__ bool decode_and_apply(const Smem& s, const aps_params
     int kind, newp = p;
     if (v < diff_thresh) {
         if (avail < 4) { s.desc[D_STOP] = 1; s.desc[D_SEQ] = seq; return false; }
-        if (ud < APS_DIV(rl, APS_ADD(rl, rr))) { kind = APS_EV_DIFF_LEFT; newp = clampi(p - 1, 0, P.L - 1); }
-        else { kind = APS_EV_DIFF_RIGHT; newp = clampi(p + 1, 0, P.L - 1); }
+        if (ud < APS_DIV(rl, APS_ADD(rl, rr))) { kind = APS_EV_DIFF_LEFT; newp = hop_target(p, -1, P.L, s.periodic != 0); }
+        else { kind = APS_EV_DIFF_RIGHT; newp = hop_target(p, 1, P.L, s.periodic != 0); }
     } else if (v < act_thresh) {
-        kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, P.L - 1);
+        kind = APS_EV_ACTIVE; newp = hop_target(p, sg == 1, P.L, s.periodic != 0);
     } else if (v < bind_thresh) kind = APS_EV_BIND;
     else if (v < unbind_thresh) kind = APS_EV_UNBIND;
     else if (v < exit_thresh) kind = APS_EV_EXIT;
@@ -367,6 +377,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
     int n = B.n[rep];
     const double beta = B.beta[rep], T = P.T;
     Smem s = carve(smem_raw, L, n_max, pad, A.max_nodes, NW, A.use_lut, P.K, r);
+    const bool periodic = (P.flags & APS_FLAG_PERIODIC) != 0;
+    s.periodic = periodic ? 1 : 0;
     s.m_in = B.m_field_in ? B.m_field_in + (size_t)rep * (size_t)L : nullptr;
     if (B.anchor_mask) { for (int l = tid; l < L; l += NT) s.anchor[l] = B.anchor_mask[l]; } else s.anchor = nullptr;
     for (int i = tid; i < n_max; i += NT) s.bound[i] = (B.bound0 && i < n) ? B.bound0[(size_t)rep * n_max + i] : 0;
@@ -401,9 +413,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
             part += sg;
             const uint32_t d = sg == 1 ? 1u : 256u, dc = sg == 1 ? 1u : (uint32_t)bcode;
             // every reflect image of p inside the halo (atomic: several particles may share a word)
-            const int twoL = 2 * L, kmax = (pad + L) / twoL + 1;
+            const int twoL = 2 * L, kmax = periodic ? 1 : (pad + L) / twoL + 1;
             for (int k = -kmax; k <= kmax; ++k) {
-                int i1 = k * twoL + p, i2 = k * twoL - 1 - p;
+                // reflect images: p + 2kL and -1 - p + 2kL; ring images: p + kL (i2 unused)
+                int i1 = periodic ? k * L + p : k * twoL + p, i2 = periodic ? -pad - 1 : k * twoL - 1 - p;
                 if (i1 >= -pad && i1 < L + pad) {
                     int q = pad + i1; atomicAdd(&pk32[q >> 1], d << (16 * (q & 1)));
                     if (lut) atomicAdd(&cd32[q >> 1], dc << (16 * (q & 1)));
@@ -681,9 +694,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
                 const int reach = r > 1 ? r : 1;
                 wlo = (oldp < newp ? oldp : newp) - reach; whi = (oldp < newp ? newp : oldp) + reach;
             }
+            if (periodic && (newp - oldp > 1 || oldp - newp > 1)) { wlo = 0; whi = L - 1; }   // a hop across the seam
             for (int i = tid; i < n; i += NT) {
                 int p = s.pos[i];
-                if (p >= wlo && p <= whi) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, i, p, s.sigma[i], lut, b2);
+                if ((p >= wlo && p <= whi) || (periodic && (p + L <= whi || p - L >= wlo))) s.rates[i] = particle_rate(s, P, pad, crowd, beta, m_glob, i, p, s.sigma[i], lut, b2);
             }
             bsync<NT>();  // BAR3
         }
@@ -717,6 +731,7 @@ static __global__ void field_kernel(aps_params P, const double* __restrict__ wei
     for (int i = threadIdx.x; i < L + 2 * pad; i += blockDim.x) {
         long long q = (long long)i - pad, per = 2LL * L;
         long long m = q % per; if (m < 0) m += per; if (m >= L) m = per - 1 - m;
+        if (P.flags & APS_FLAG_PERIODIC) { m = q % L; if (m < 0) m += L; }
         pk[i] = (uint16_t)((cp[m] & 0xff) | ((cm[m] & 0xff) << 8));
     }
     __syncthreads();

@@ -31,6 +31,21 @@ def gaussian_weights(sigma_grid: float):
     return radius, phi[::-1].copy()
 
 
+def periodic_weights(L: int, dx: float, sigma: float, tail: float = 1e-22):
+    """Taps of the reference's ring kernel (CLASS.py:111-121: exp(-0.5*(min(j, L-j)*dx/sigma)^2), normalised over the
+    ring), truncated at the smallest radius whose discarded mass is below `tail`.  The reference applies the kernel
+    by FFT (:224-227); the direct sum over the kept taps differs from it only by rounding (~1e-16) plus `tail`."""
+    j = np.arange(L)
+    kernel = np.exp(-0.5 * (np.minimum(j, L - j) * dx / sigma) ** 2)
+    kernel = kernel / kernel.sum()
+    half = (L - 1) // 2
+    for r in range(0, half + 1):
+        if kernel[r + 1:L - r].sum() <= tail:
+            return r, np.concatenate([kernel[r:0:-1], kernel[:r + 1]]).copy()
+    raise NotImplementedError("periodic=True: the kernel does not decay within half the ring "
+                              "(local_kernel_sigma too large for this L)")
+
+
 def _dev(device=None):
     if not torch.cuda.is_available():
         raise capi.ApsError("no CUDA device: the B200 stepper has no CPU path")
@@ -45,13 +60,14 @@ class ReplicaBatch:
     def __init__(self, *, L, K, radius, weights, D, lam, T, times_obs, betas, n, pos0, sigma0, seeds=None,
                  record=APS_REC_COUNTS | APS_REC_POS, crowding=False, device=None, dx=None, anchor_mask=None,
                  k_on=0.0, k_off=0.0, k_exit=0.0, suppress_flip_when_bound=True, immobilize_when_anchored=True,
-                 exit_cap=None):
+                 exit_cap=None, periodic=False):
         self.lib = capi.load()
         self.dev = _dev(device)
         self.L, self.K, self.radius = int(L), int(K), int(radius)
         self.dx = float(dx) if dx is not None else 1.0 / self.L
         self.T = float(T)
         flags = capi.APS_FLAG_CROWDING if crowding else 0
+        flags |= capi.APS_FLAG_PERIODIC if periodic else 0
         if anchor_mask is not None:
             flags |= (capi.APS_FLAG_SUPPRESS_FLIP_BOUND if suppress_flip_when_bound else 0)
             flags |= (capi.APS_FLAG_IMMOBILIZE if immobilize_when_anchored else 0)

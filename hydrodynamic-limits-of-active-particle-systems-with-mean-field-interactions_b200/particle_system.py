@@ -13,8 +13,10 @@ Random numbers, two modes selected by the `rng=` argument (the reference's injec
   * `PhiloxRNG(seed)` or `rng=None`: NATIVE mode, in-kernel counter-based Philox4x32-10.
 
 Anchors / binding / unbinding / exit (`anchor_positions`, `k_on`, `k_off`, `k_exit`, CLASS.py:307-348,418-436) are supported
-(generic K1 kernel).  Not supported (raise NotImplementedError; disabled in every shipped driver):
-custom `flip_rate_fn`, `periodic=True`.
+(generic K1 kernel).  `periodic=True` (ring: hops wrap, :278-288) is supported too; its local field is the reference's ring
+kernel (:111-121) applied as a truncated direct sum instead of the FFT of :224-227, so trajectories match the reference for
+a given seed and `m_local_list` agrees to 1e-13 rather than bit for bit.
+Not supported (raises NotImplementedError; disabled in every shipped driver): a custom `flip_rate_fn`.
 """
 from __future__ import annotations
 
@@ -96,12 +98,13 @@ class ParticleSystem:
             self.anchor_idx_array = np.array(sorted(sites), dtype=int)
             self.is_anchor_site[self.anchor_idx_array] = True
         self._has_anchors = anchor_positions is not None
-        if self.periodic:
-            raise NotImplementedError("periodic=True is outside the accelerated path (no shipped driver uses it)")
         self._kernel = None
         self._fft_kernel = None
-        from .engine import gaussian_weights
-        if self.local_kernel_sigma > 0:
+        from .engine import gaussian_weights, periodic_weights
+        if self.local_kernel_sigma > 0 and self.periodic:
+            # ring kernel of CLASS.py:111-121, applied as a truncated direct sum instead of the FFT of :224-227
+            self._radius, self._weights = periodic_weights(self.L, self.dx, self.local_kernel_sigma)
+        elif self.local_kernel_sigma > 0:
             self._radius, self._weights = gaussian_weights(self._sigma_grid)
         else:
             self._radius, self._weights = -1, np.zeros(1)
@@ -157,7 +160,8 @@ class ParticleSystem:
         cm = np.ascontiguousarray(counts_m, dtype=np.int32)
         out = np.zeros(self.L, dtype=np.float64)
         from .batch import make_params
-        p = make_params(self.L, self.K, self._radius, self.rate_diffusion, self.rate_active, 0.0)
+        p = make_params(self.L, self.K, self._radius, self.rate_diffusion, self.rate_active, 0.0,
+                        capi.APS_FLAG_PERIODIC if self.periodic else 0)
         w = np.ascontiguousarray(self._weights, dtype=np.float64)
         capi.check(lib.aps_m_field_host(p, w.ctypes.data, cp.ctypes.data, cm.ctypes.data, out.ctypes.data),
                    "aps_m_field_host")
@@ -174,7 +178,7 @@ class ParticleSystem:
                             seeds=seeds, record=record, crowding=self.crowding_suppresses_rates, dx=self.dx,
                             anchor_mask=self.is_anchor_site if self._has_anchors else None, k_on=self.k_on, k_off=self.k_off,
                             k_exit=self.k_exit, suppress_flip_when_bound=self.suppress_flip_when_bound,
-                            immobilize_when_anchored=self.immobilize_when_anchored)
+                            immobilize_when_anchored=self.immobilize_when_anchored, periodic=self.periodic)
 
     def run(self, T=10.0, obs_dt=0.01, record_fft=False, record_var=False):
         import torch
@@ -305,7 +309,7 @@ class ParticleSystem:
         rb = ReplicaBatch(L=self.L, K=self.K, radius=self._radius, weights=self._weights, D=self.rate_diffusion,
                           lam=self.rate_active, T=np.inf, times_obs=[0.0], betas=[float(self.beta)], n=[n],
                           pos0=np.asarray(pos, np.int32).reshape(1, -1), sigma0=np.asarray(sigma, np.int8).reshape(1, -1),
-                          record=0, crowding=self.crowding_suppresses_rates, dx=self.dx)
+                          record=0, crowding=self.crowding_suppresses_rates, dx=self.dx, periodic=self.periodic)
         mf = torch.from_numpy(np.ascontiguousarray(m_field, dtype=np.float64)).to(rb.dev)
         one = torch.ones(1, dtype=torch.int32, device=rb.dev)
         draws = self._draw_triples(1)

@@ -53,6 +53,9 @@ typedef enum aps_status {
 #define APS_FLAG_CROWDING 1u    /* crowding_suppresses_rates=True (CLASS.py:322-336)              */
 #define APS_FLAG_SUPPRESS_FLIP_BOUND 2u  /* suppress_flip_when_bound=True (CLASS.py:266-267)      */
 #define APS_FLAG_IMMOBILIZE 4u  /* immobilize_when_anchored=True (CLASS.py:307-312,338-340)       */
+#define APS_FLAG_PERIODIC 8u    /* periodic=True: hops wrap (CLASS.py:278-288), the field is the   */
+                                /* circular convolution with `weights` (truncated periodic kernel,  */
+                                /* :108-122,224-227; needs 2*radius+1 <= L)                         */
 
 /* aps_batch.record */
 #define APS_REC_COUNTS 1u       /* obs_cp / obs_cm                                                */

@@ -74,8 +74,11 @@ static inline int reflect_index(int64_t i, int L) {
 /* scipy.ndimage.correlate1d, symmetric branch (ni_filters.c), with mode='reflect':
  *   out[l] = x[l]*w[r];  for j = -r..-1: out[l] += (x[l+j] + x[l-j]) * w[r+j]   (no FMA)      */
 static void gaussian_filter_reflect(const double* x, int L, int r, const double* w,
-                                    double* pad, double* out) {
-    for (int i = 0; i < L + 2 * r; ++i) pad[i] = x[reflect_index((int64_t)i - r, L)];
+                                    double* pad, double* out, int periodic) {
+    for (int i = 0; i < L + 2 * r; ++i) {
+        int64_t q = (int64_t)i - r;
+        pad[i] = periodic ? x[((q % L) + L) % L] : x[reflect_index(q, L)];
+    }
     const double wc = w[r];
     for (int l = 0; l < L; ++l) out[l] = pad[l + r] * wc;
     for (int jj = -r; jj < 0; ++jj) {
@@ -135,8 +138,9 @@ static void m_field(work* w, const aps_params* P, const double* weights) {
         for (int l = 0; l < L; ++l) w->m[l] = mg;
         return;
     }
-    gaussian_filter_reflect(w->s, L, P->radius, weights, w->pad, w->sconv);
-    gaussian_filter_reflect(w->tot, L, P->radius, weights, w->pad, w->tconv);
+    const int periodic = (P->flags & APS_FLAG_PERIODIC) != 0;   /* circular convolution, same tap order */
+    gaussian_filter_reflect(w->s, L, P->radius, weights, w->pad, w->sconv, periodic);
+    gaussian_filter_reflect(w->tot, L, P->radius, weights, w->pad, w->tconv, periodic);
     for (int l = 0; l < L; ++l) {
         double m = 0.0;
         if (w->tconv[l] > 0) m = w->sconv[l] / w->tconv[l];
@@ -173,12 +177,13 @@ static double build_rates(work* w, const aps_params* P, int n, double beta, cons
     const int suppress = (P->flags & APS_FLAG_SUPPRESS_FLIP_BOUND) != 0, immob = (P->flags & APS_FLAG_IMMOBILIZE) != 0;
     const double D = P->rate_diffusion, lam = P->rate_active;
     const int crowd = (P->flags & APS_FLAG_CROWDING) != 0;
+    const int periodic = (P->flags & APS_FLAG_PERIODIC) != 0;
     for (int i = 0; i < n; ++i) {
         int p = (int)w->pos[i];
         int sg = w->sigma[i];
-        int fwd = clipi((int64_t)p + (sg == 1), 0, L - 1);
-        int lt = clipi((int64_t)p - 1, 0, L - 1);
-        int rt = clipi((int64_t)p + 1, 0, L - 1);
+        int fwd = periodic ? (p + (sg == 1)) % L : clipi((int64_t)p + (sg == 1), 0, L - 1);   /* :278-291 */
+        int lt = periodic ? (p - 1 + L) % L : clipi((int64_t)p - 1, 0, L - 1);
+        int rt = periodic ? (p + 1) % L : clipi((int64_t)p + 1, 0, L - 1);
         int occ_f = w->cp[fwd] + w->cm[fwd], occ_l = w->cp[lt] + w->cm[lt], occ_r = w->cp[rt] + w->cm[rt];
         int f_free = (occ_f < K) && (fwd != p);
         int l_free = (occ_l < K) && (lt != p);
@@ -312,10 +317,13 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
                 if (ds.left < 4 || (B->spec_from >= 0 && at >= B->spec_from)) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
                 u_dir = ds.d[3]; ds.d += 1; ds.left -= 1;
             } else u_dir = ds.b_dir;
-            if (u_dir < rl / (rl + rr)) { new_pos = clipi((int64_t)old_pos - 1, 0, L - 1); kind = APS_EV_DIFF_LEFT; }
-            else { new_pos = clipi((int64_t)old_pos + 1, 0, L - 1); kind = APS_EV_DIFF_RIGHT; }
+            const int per = (P->flags & APS_FLAG_PERIODIC) != 0;
+            if (u_dir < rl / (rl + rr)) { new_pos = per ? (old_pos - 1 + L) % L : clipi((int64_t)old_pos - 1, 0, L - 1); kind = APS_EV_DIFF_LEFT; }
+            else { new_pos = per ? (old_pos + 1) % L : clipi((int64_t)old_pos + 1, 0, L - 1); kind = APS_EV_DIFF_RIGHT; }
         } else if (v < act_thresh) {                                     /* :400-416 */
-            new_pos = clipi((int64_t)old_pos + (w->sigma[sel] == 1), 0, L - 1); kind = APS_EV_ACTIVE;
+            const int per = (P->flags & APS_FLAG_PERIODIC) != 0;
+            new_pos = per ? (old_pos + (w->sigma[sel] == 1)) % L : clipi((int64_t)old_pos + (w->sigma[sel] == 1), 0, L - 1);
+            kind = APS_EV_ACTIVE;
         } else if (v < bind_thresh) kind = APS_EV_BIND;                  /* :418-419 */
         else if (v < unbind_thresh) kind = APS_EV_UNBIND;                /* :421-422 */
         else if (v < exit_thresh) kind = APS_EV_EXIT;                    /* :424-436 */

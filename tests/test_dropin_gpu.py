@@ -1,6 +1,7 @@
 """The drop-in `ParticleSystem` (host mirror + K1/K4 kernels) against the unmodified reference:
 same constructor keywords, same seeded numpy Generator -> same returned dict.
-Integer / density / field / magnetisation arrays: bit-exact.  FFT arrays: |diff| <= 1e-9 * max|x|
+Integer / density / field / magnetisation arrays: bit-exact (periodic=True local field: |diff| <= 1e-13, the
+reference convolves by FFT there).  FFT arrays: |diff| <= 1e-9 * max|x|
 (cuFFT vs numpy pocketfft rounding; the reference's FFT is plain post-processing of total_list)."""
 import json
 import os
@@ -49,7 +50,11 @@ def test_same_seed_same_output_dict(name):
                         "bound_list", "m_local_list", "m_global", "rho_hat_complex", "fft_amp_list", "var_list",
                         "exit_times", "exit_positions"}
     assert np.array_equal(out["times_obs"], c["times_obs"])
+    fft_field = m.get("periodic") and m["radius"] >= 0     # reference field by FFT (CLASS.py:224-227): rounding-level parity
     for k in ["rho_p_list", "rho_m_list", "total_list", "m_local_list", "m_global"]:
+        if k == "m_local_list" and fft_field:
+            np.testing.assert_allclose(out[k], c[k], rtol=0, atol=1e-13)
+            continue
         assert np.array_equal(out[k], c[k]), k
     for mm in range(len(c["times_obs"])):
         if mm < n_obs:
@@ -186,3 +191,27 @@ def test_device_reducers_match_reference_functions():
         np.testing.assert_allclose(prof[0], c["rho_p_list"][si:ei].mean(0), rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(prof[1], c["rho_m_list"][si:ei].mean(0), rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(prof[2], c["rho_p_list"][si:ei].mean(0) ** 2, rtol=1e-12, atol=1e-15)
+
+
+def test_periodic_field_matches_the_fft_convolution():
+    """periodic=True: compute_local_m_field (truncated direct ring sum) against the reference's formula
+    real(ifft(fft(x) * fft(kernel))) (CLASS.py:111-121,224-227), evaluated here with numpy; |diff| <= 1e-13."""
+    c = load_case("periodic_k1")
+    m = c["meta"]
+    ps = build(c, np.random.default_rng(3))
+    L = ps.L
+    g = np.random.default_rng(11)
+    cp = (g.random(L) < 0.4).astype(int)
+    cm = ((g.random(L) < 0.3) & (cp == 0)).astype(int)
+    j = np.arange(L)
+    kern = np.exp(-0.5 * (np.minimum(j, L - j) * ps.dx / ps.local_kernel_sigma) ** 2)
+    kern /= kern.sum()
+    fk = np.fft.fft(kern)
+    s_conv = np.real(np.fft.ifft(np.fft.fft((cp - cm).astype(float)) * fk))
+    t_conv = np.real(np.fft.ifft(np.fft.fft((cp + cm).astype(float)) * fk))
+    want = np.clip(np.where(t_conv > 0, s_conv / np.where(t_conv > 0, t_conv, 1.0), 0.0), -1, 1)
+    got = ps.compute_local_m_field(cp, cm)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-13)
+    # the ring has no walls: shifting the configuration shifts the field
+    got2 = ps.compute_local_m_field(np.roll(cp, 17), np.roll(cm, 17))
+    assert np.array_equal(np.roll(got, 17), got2)

@@ -207,3 +207,17 @@ def test_npz_cache_uses_the_reference_key_names(tmp_path):
         assert np.array_equal(save_dict[k], out[k], equal_nan=True), k
     assert save_dict["ps_kwargs"].item()["L"] == 64 and "outs" in save_dict
     assert la.load_sweep_npz(p)["ps_kwargs"]["site_capacity"] == 1
+
+
+def test_periodic_weights_truncation():
+    """Ring kernel taps (CLASS.py:111-121): symmetric, discarded mass <= 1e-22, refuses a kernel wider than the ring."""
+    from aps_b200.engine import periodic_weights
+    L, dx, s = 200, 1.0 / 200, 0.02
+    r, w = periodic_weights(L, dx, s)
+    assert w.size == 2 * r + 1 and 2 * r + 1 <= L and np.array_equal(w, w[::-1])
+    j = np.arange(L)
+    k = np.exp(-0.5 * (np.minimum(j, L - j) * dx / s) ** 2); k /= k.sum()
+    assert w[r] == k[0] and w[r + 3] == k[3] and abs(1.0 - w.sum()) < 1e-15
+    assert k[r + 1:L - r].sum() <= 1e-22 and (r == 0 or k[r:L - r + 1].sum() > 1e-22)
+    with pytest.raises(NotImplementedError):
+        periodic_weights(64, 1.0 / 64, 0.5)

@@ -172,6 +172,17 @@ def cases():
                                                 scale_rates=False, local_kernel_sigma=0.0, site_capacity=3,
                                                 crowding_suppresses_rates=True, **dict(anch, k_exit=20)),
                                         run=dict(T=3.0, obs_dt=0.25, record_fft=False, record_var=False), seed=1717)
+    # periodic=True (ring): the reference applies the kernel by FFT (CLASS.py:224-227); hops wrap (:278-288)
+    c["periodic_k1"] = dict(ps=dict(L=200, xlim=1, rate_diffusion=0.4, rate_active=3, beta=1.5, init="fixed", N=120,
+                                    scale_rates=False, local_kernel_sigma=0.02, site_capacity=1, periodic=True),
+                            run=dict(T=2.0, obs_dt=0.25, record_fft=False, record_var=False), seed=1818)
+    c["periodic_k2_crowding"] = dict(ps=dict(L=64, xlim=1, rate_diffusion=0.8, rate_active=2, beta=0.8, init="fixed", N=70,
+                                             scale_rates=False, local_kernel_sigma=0.03, site_capacity=2, periodic=True,
+                                             crowding_suppresses_rates=True),
+                                     run=dict(T=2.0, obs_dt=0.25, record_fft=False, record_var=False), seed=1919)
+    c["periodic_global"] = dict(ps=dict(L=50, xlim=1, rate_diffusion=0.6, rate_active=2, beta=1.2, init="fixed", N=30,
+                                        scale_rates=False, local_kernel_sigma=0.0, site_capacity=1, periodic=True),
+                                run=dict(T=3.0, obs_dt=0.5, record_fft=False, record_var=False), seed=2020)
     c["poisson_k2"] = dict(ps=dict(L=200, xlim=1, rate_diffusion=0.3, rate_active=4, beta=1.8, init="poisson", N=260,
                                    scale_rates=False, local_kernel_sigma=0.01, site_capacity=2),
                            profile=dict(L=200, N=260, frac_plus=0.6, decay_plus=0.5),
@@ -256,14 +267,19 @@ def run_case(PS, name, spec):
         count_obs[m] = out["particle_count_list"][m]
     radius = -1
     weights = np.zeros(0)
-    if ps.local_kernel_sigma > 0:
+    if ps.local_kernel_sigma > 0 and ps.periodic:
+        # the reference's own ring kernel (ps._kernel, CLASS.py:111-121), truncated where the discarded mass <= 1e-22
+        kern = ps._kernel
+        radius = next(r for r in range((ps.L - 1) // 2 + 1) if kern[r + 1:ps.L - r].sum() <= 1e-22)
+        weights = np.concatenate([kern[radius:0:-1], kern[:radius + 1]]).copy()
+    elif ps.local_kernel_sigma > 0:
         sd = float(ps._sigma_grid)
         radius = int(4.0 * sd + 0.5)
         weights = _filters._gaussian_kernel1d(sd, 0, radius)[::-1].copy()
     meta = dict(name=name, ps=spec["ps"], run=spec["run"], seed=seed, profile=spec.get("profile"),
                 dx=ps.dx, rate_diffusion=ps.rate_diffusion, rate_active=ps.rate_active, K=ps.K, L=ps.L,
                 radius=radius, n=int(n), n_obs=int(n_obs), n_events=len(trace),
-                anchors=bool(ps.is_anchor_site.any()), k_on=float(ps.k_on), k_off=float(ps.k_off), k_exit=float(ps.k_exit),
+                periodic=bool(ps.periodic), anchors=bool(ps.is_anchor_site.any()), k_on=float(ps.k_on), k_off=float(ps.k_off), k_exit=float(ps.k_exit),
                 suppress=bool(ps.suppress_flip_when_bound), immobilize=bool(ps.immobilize_when_anchored),
                 numpy=np.__version__, scipy=__import__("scipy").__version__)
     save = dict(
