@@ -122,7 +122,8 @@ def measure_k2(torch, logL=30, passes=30):
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
     for name, sigma, dt in [("global field, dt=0.0025", None, 0.0025), ("global field, dt=0.005", None, 0.005),
                             ("global field, dt=0.02", None, 0.02), ("local Gaussian field sigma=5 sites, dt=0.005", 5.0, 0.005)]:
-        lat = SublatticeLattice(1 << logL, D=0.02, lam=5.0, beta=2.0, dt=dt, sigma_sites=sigma, seed=0)
+        lat = SublatticeLattice(1 << logL, D=0.02, lam=5.0, beta=2.0, dt=dt, sigma_sites=sigma, seed=0,
+                                single_rank=True)     # the K2 roofline is a one-GPU measurement on rank 0 at every N
         lat.init_random(0.5, 0.5)
         lat.run_passes(6)
         torch.cuda.synchronize()
@@ -198,6 +199,8 @@ def main():
     # ---------------- device-resident arm (value) ----------------
     spec = la.build_beta_sweep_spec(betas, reps, PS_KWARGS, ik, run_kwargs, base_seed=1)
     lo, hi = la.shard_bounds(len(spec.betas), rank, world)
+    if world > 1:      # same strided assignment as launcher.run_ensemble: every rank gets 64 replicas of every beta
+        spec = la.permute_spec(spec, la.balanced_order(len(spec.betas), world))
     ens = la.DeviceEnsemble(spec, lo, hi)
     for _ in range(max(3, args.warmup)):
         ens.step()

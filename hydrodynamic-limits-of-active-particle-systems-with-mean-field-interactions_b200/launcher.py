@@ -25,7 +25,7 @@ import torch
 
 from . import capi
 from .capi import APS_REC_COUNTS, APS_REC_POS, APS_RED_N, ApsInitArgs
-from .engine import ReplicaBatch, _dev, _stream, gaussian_weights
+from .engine import ReplicaBatch, _dev, _stream, gaussian_weights, periodic_weights
 
 
 def make_exp_gradient(L, N, frac_plus, decay_length, anchor_positions=(0.25, 0.60), anchor_peak_width=0.01,
@@ -62,6 +62,21 @@ def shard_bounds(n_items: int, rank: int, world: int):
     base, rem = divmod(n_items, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def balanced_order(n_items: int, world: int) -> np.ndarray:
+    """Replica order whose contiguous shard_bounds blocks are the strided sets {r, r+world, ...}: a sweep lists its
+    replicas parameter-major and the event rate depends on the parameter (flip rate exp(-beta*sigma*m)), so contiguous
+    blocks would give the ranks unequal work; strided blocks give every rank the same mix of sweep points."""
+    return np.concatenate([np.arange(r, n_items, world) for r in range(world)]) if world > 1 else np.arange(n_items)
+
+
+def permute_spec(spec: "EnsembleSpec", order: np.ndarray) -> "EnsembleSpec":
+    """The same ensemble with its per-replica arrays reordered (seeds travel with their replica, so results do not change)."""
+    from dataclasses import replace
+    pick = lambda a: None if a is None else np.asarray(a)[order]
+    return replace(spec, betas=pick(spec.betas), point_of=pick(spec.point_of), seeds=pick(spec.seeds),
+                   profile_of=pick(spec.profile_of), N_of=pick(spec.N_of))
 
 
 def expected_poisson_particles(rho_p, rho_m, K):
@@ -112,15 +127,18 @@ def _model_params(ps_kwargs):
     if ps_kwargs.get("scale_rates", True):
         D, lam = D / dx ** 2, lam / dx
     sigma = float(ps_kwargs.get("local_kernel_sigma", 0.005))
-    if sigma > 0:
+    periodic = bool(ps_kwargs.get("periodic", False))
+    if sigma > 0 and periodic:
+        radius, weights = periodic_weights(L, dx, sigma)      # ring kernel, CLASS.py:111-121
+    elif sigma > 0:
         radius, weights = gaussian_weights(sigma / dx)
     else:
         radius, weights = -1, np.zeros(1)
-    for key, bad in [("flip_rate_fn", lambda v: v is not None), ("periodic", bool), ("anchor_positions", lambda v: v is not None)]:
+    for key, bad in [("flip_rate_fn", lambda v: v is not None), ("anchor_positions", lambda v: v is not None)]:
         if bad(ps_kwargs.get(key)):
             raise NotImplementedError(f"{key} is outside the accelerated path")
     return dict(L=L, dx=dx, D=D, lam=lam, K=int(ps_kwargs.get("site_capacity", 1)), radius=radius, weights=weights,
-                crowding=bool(ps_kwargs.get("crowding_suppresses_rates", False)), init=ps_kwargs.get("init", "fixed"),
+                crowding=bool(ps_kwargs.get("crowding_suppresses_rates", False)), periodic=periodic, init=ps_kwargs.get("init", "fixed"),
                 N=int(ps_kwargs.get("N", 1000)))
 
 
@@ -165,7 +183,7 @@ class DeviceEnsemble:
         self.rb = ReplicaBatch(L=mp["L"], K=mp["K"], radius=mp["radius"], weights=mp["weights"], D=mp["D"], lam=mp["lam"],
                                T=T, times_obs=self.times_obs, betas=self.betas_h, n=self.n, pos0=self.pos0,
                                sigma0=self.sigma0, seeds=self.seeds, record=spec.record, crowding=mp["crowding"],
-                               device=self.dev.index, dx=mp["dx"])
+                               device=self.dev.index, dx=mp["dx"], periodic=mp["periodic"])
         self.h2d_bytes += (self.rb.times_obs.numel() + self.rb.beta.numel() + (self.rb.weights.numel() if self.rb.weights is not None else 0)) * 8
         self.point_local = torch.as_tensor(np.asarray(spec.point_of[sl], dtype=np.int64)).to(self.dev)
         self.n_points = int(spec.point_of.max()) + 1 if len(spec.point_of) else 0
@@ -207,7 +225,8 @@ def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_c
     rank, world = dist_info()
     Rtot = len(spec.betas)
     lo, hi = shard_bounds(Rtot, rank, world)
-    ens = (ensemble_cls or DeviceEnsemble)(spec, lo, hi, device=device)
+    order = balanced_order(Rtot, world)            # rank r runs replicas r, r+world, ... (equal mix of sweep points)
+    ens = (ensemble_cls or DeviceEnsemble)(permute_spec(spec, order) if world > 1 else spec, lo, hi, device=device)
     ens.step(want_profiles=want_profiles)
     scal = ens.pack_scalars()
     prof = ens.prof
@@ -223,6 +242,7 @@ def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_c
             a, b = shard_bounds(Rtot, r, world)
             parts.append(gathered[r][: b - a])
         scal = torch.cat(parts, dim=0)
+        scal = torch.empty_like(scal).index_copy_(0, torch.as_tensor(order, device=scal.device), scal)   # original replica order
         if prof is not None:
             torch.distributed.all_reduce(prof, op=torch.distributed.ReduceOp.SUM)
     scal_h = scal.cpu().numpy()

@@ -58,7 +58,7 @@ class OracleEnsemble:
         hr = HostRun(mp["L"], self.n_max, len(self.times_obs), n, pos0, sg0, spec.betas[sl], self.times_obs,
                      mp["weights"], seeds=seeds, record=3)
         P = make_params(mp["L"], mp["K"], mp["radius"], mp["D"], mp["lam"], self.T,
-                        capi.APS_FLAG_CROWDING if mp["crowding"] else 0)
+                        (capi.APS_FLAG_CROWDING if mp["crowding"] else 0) | (capi.APS_FLAG_PERIODIC if mp.get("periodic") else 0))
         assert oracle.load().aps_oracle_run(P, hr.batch, 1, threads) == 0
         self.hr = hr
         red = np.zeros((self.R, capi.APS_RED_N))

@@ -103,6 +103,12 @@ def test_gpu_launcher_matches_oracle_ensemble():
     b = la.sweep_over_betas([0.3, 1.7], 4, ps, {}, RUN, base_seed=9, ensemble_cls=OracleEnsemble)
     assert np.array_equal(a["n_events"], b["n_events"])
     np.testing.assert_allclose(a["means"], b["means"], rtol=1e-9, atol=1e-13)
+    # periodic ring (generic K1 kernel, truncated ring kernel)
+    ps = dict(PS, init="fixed", N=20, periodic=True)
+    a = la.sweep_over_betas([0.5, 2.0], 3, ps, {}, RUN, base_seed=11)
+    b = la.sweep_over_betas([0.5, 2.0], 3, ps, {}, RUN, base_seed=11, ensemble_cls=OracleEnsemble)
+    assert np.array_equal(a["n_events"], b["n_events"]) and a["n_events"].min() > 0
+    np.testing.assert_allclose(a["means"], b["means"], rtol=1e-9, atol=1e-13)
 
 
 @pytest.mark.gpu
@@ -221,3 +227,20 @@ def test_periodic_weights_truncation():
     assert k[r + 1:L - r].sum() <= 1e-22 and (r == 0 or k[r:L - r + 1].sum() > 1e-22)
     with pytest.raises(NotImplementedError):
         periodic_weights(64, 1.0 / 64, 0.5)
+
+
+def test_balanced_order_gives_every_rank_every_sweep_point():
+    """Strided assignment: with replicas listed beta-major, each rank's contiguous block of the permuted spec holds
+    the same number of replicas of every beta, and the permutation is a bijection that carries seeds with replicas."""
+    nb, reps, world = 6, 8, 4
+    spec = la.build_beta_sweep_spec(np.linspace(0, 3, nb), reps, dict(L=64, rate_diffusion=0.1, rate_active=1.0, N=10,
+                                                                         scale_rates=False, init="fixed"), {}, dict(T=1.0))
+    order = la.balanced_order(len(spec.betas), world)
+    assert sorted(order.tolist()) == list(range(nb * reps))
+    ps = la.permute_spec(spec, order)
+    assert np.array_equal(ps.seeds, spec.seeds[order]) and np.array_equal(ps.betas, spec.betas[order])
+    for r in range(world):
+        lo, hi = la.shard_bounds(len(spec.betas), r, world)
+        assert np.array_equal(order[lo:hi], np.arange(r, nb * reps, world))
+        assert np.array_equal(np.bincount(ps.point_of[lo:hi], minlength=nb), np.full(nb, reps // world))
+    assert np.array_equal(la.balanced_order(5, 1), np.arange(5))
