@@ -388,40 +388,30 @@ def double_sweep(n_part_values, beta_values, n_runs, ps_kwargs, run_kwargs, **kw
 
 
 # ---- structure observables: PARTICLE_solver_BIOLOGY_local_structure.py:55-193 -----------------------
-def structure_observables(rb: ReplicaBatch, start_fraction=0.5, k_max=None):
-    """extract_structure_observables_from_out (local_structure.py:55-103) for every replica of a batch, on
-    the device: density rows and np.var by the K4 expansion kernel, |FFT| by cuFFT (torch.fft), the row
-    statistics by torch reductions.  Returns a dict of device tensors with a leading replica axis."""
-    rho_p, rho_m, total, var = rb.expand(want_var=True)
-    M = rb.M
-    s = int(start_fraction * M)
-    amp = torch.fft.fft(total, dim=-1).abs()                          # [R][M][L]
-    if k_max is not None:
-        amp = amp[:, :, :k_max]
-    fft_mean = amp[:, s:].mean(dim=1)
-    fft_std = amp[:, s:].std(dim=1, unbiased=True)
-    k_cut = min(25, fft_mean.shape[1])
-    out = dict(var_mean=var[:, s:].mean(dim=1), var_std=var[:, s:].std(dim=1, unbiased=True), fft_mean=fft_mean,
-               fft_std=fft_std, dominant_k=fft_mean[:, 1:].argmax(dim=1) + 1, low_k_power=fft_mean[:, 1:k_cut].sum(dim=1),
-               lowk_variance=(amp[:, s:, 1:k_cut] ** 2).sum(dim=2).mean(dim=1))
-    if rb.obs_m_local is not None:
-        ml = rb.obs_m_local[:, s:].reshape(rb.R, -1)
-        out["m_local_var"] = ml.var(dim=1, unbiased=False)
-    return out
+from .structure import structure_observables, fft_amplitudes      # noqa: E402  (device-side analyses live in structure.py)
 
 
 def sweep_betas_for_structures(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, start_fraction=0.5,
-                               k_max=None, base_seed=0):
-    """Drop-in for local_structure.py:167-193 (dict keyed by beta, same ensemble keys, no 'raw' outs).
-    Single rank; shard beta values over ranks by calling it with different beta subsets."""
+                               k_max=None, base_seed=0, keep_raw=True, k_keep=64):
+    """Drop-in for local_structure.py:167-193: dict keyed by beta with the ensemble keys of
+    sweep_beta_structure_ensemble (:105-165).  `raw` holds one entry per run with the per-run observables and a light
+    `out` dict (`times_obs`, `fft_amp_list` restricted to the first `k_keep` modes, `var_list`, `m_global`) — enough
+    for the driver's time-series analyses (time_to_pattern, lowk_variance_time, extract_growth_rate; k <= 25 there)
+    without downloading the (M, L) arrays.  Single rank; shard beta values over ranks by calling it with subsets."""
     from .capi import APS_REC_MLOCAL
     spec = build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, base_seed=base_seed)
     spec.record = APS_REC_COUNTS | APS_REC_POS | APS_REC_MLOCAL
     ens = DeviceEnsemble(spec, 0, len(spec.betas))
     ens.init_particles()
     ens.rb.run_philox()
-    obs = {k: v.cpu().numpy() for k, v in structure_observables(ens.rb, start_fraction, k_max).items()}
+    amp, total, var = fft_amplitudes(ens.rb)
+    obs = {k: v.cpu().numpy() for k, v in structure_observables(ens.rb, start_fraction, k_max, amp=amp, var=var).items()}
     nb, nr = len(beta_values), n_runs_per_beta
+    if keep_raw:
+        amp_h = amp[:, :, :k_keep].cpu().numpy()
+        var_h = var.cpu().numpy()
+        n_h = np.maximum(1, ens.n.cpu().numpy()).astype(float)
+        mg_h = ens.rb.obs_sigma_sum.cpu().numpy() / n_h[:, None]
     results = {}
     for b, beta in enumerate(beta_values):
         sl = slice(b * nr, (b + 1) * nr)
@@ -436,6 +426,32 @@ def sweep_betas_for_structures(beta_values, n_runs_per_beta, ps_kwargs, init_kwa
             "lowk_var_mean": obs["lowk_variance"][sl].mean(), "lowk_var_se": se(obs["lowk_variance"][sl]),
             "n_events": ens.rb.n_events[sl].cpu().numpy(),
         }
+        if keep_raw:
+            results[beta]["raw"] = [
+                dict({k: (obs[k][r] if obs[k].ndim > 1 else obs[k][r].item()) for k in obs},
+                     out=dict(times_obs=ens.times_obs, fft_amp_list=amp_h[r], var_list=var_h[r], m_global=mg_h[r]))
+                for r in range(b * nr, (b + 1) * nr)]
+    return results
+
+
+def sweep_over_sigmas(sigma_values, beta_values, n_runs_per_beta=5, ps_kwargs=None, init_kwargs=None, run_kwargs=None,
+                      base_seed=0, save_dir=None):
+    """Drop-in for sweep_beta_2.py:1030-1075: one beta sweep per interaction width sigma (each sigma is its own launch
+    group: the filter radius differs), results keyed by sigma with the reference's keys; with `save_dir` every sigma
+    is also written to `v_eff_vs_beta_sigma_<sigma>.npz` under the reference's key names (:1059-1067)."""
+    import os
+    results = {}
+    for sigma in sigma_values:
+        ps = dict(ps_kwargs or {}, local_kernel_sigma=float(sigma))
+        sd = sweep_over_betas(beta_values, n_runs_per_beta, ps, init_kwargs, run_kwargs, base_seed=base_seed,
+                              want_profiles=False)
+        results[sigma] = {"beta": np.asarray(beta_values, dtype=float), "v_mean": sd["means"], "v_se": sd["ses"],
+                          "D_mean": sd["D_means"], "D_se": sd["D_ses"], "ps_kwargs": sd["ps_kwargs"]}
+        if save_dir is not None:
+            keep = {k: v for k, v in sd["ps_kwargs"].items() if not callable(v)}
+            np.savez(os.path.join(save_dir, f"v_eff_vs_beta_sigma_{sigma:.4g}.npz"), beta=results[sigma]["beta"],
+                     v_mean=sd["means"], v_se=sd["ses"], D_mean=sd["D_means"], D_se=sd["D_ses"],
+                     ps_kwargs=np.array(keep, dtype=object))
     return results
 
 

@@ -244,3 +244,26 @@ def test_balanced_order_gives_every_rank_every_sweep_point():
         assert np.array_equal(order[lo:hi], np.arange(r, nb * reps, world))
         assert np.array_equal(np.bincount(ps.point_of[lo:hi], minlength=nb), np.full(nb, reps // world))
     assert np.array_equal(la.balanced_order(5, 1), np.arange(5))
+
+
+@pytest.mark.gpu
+def test_sweep_over_sigmas_and_raw_structure_series(tmp_path):
+    """sweep_beta_2.py:1030-1075 (results keyed by sigma, npz key names) and the light per-run `raw` entries of
+    sweep_betas_for_structures that feed the driver's time-series analyses."""
+    ps = dict(PS, init="fixed", N=30)
+    res = la.sweep_over_sigmas([0.0, 0.03], [0.5, 2.0], 3, ps, {}, RUN, base_seed=3, save_dir=str(tmp_path))
+    assert list(res) == [0.0, 0.03]
+    for sigma in res:
+        one = la.sweep_over_betas([0.5, 2.0], 3, dict(ps, local_kernel_sigma=sigma), {}, RUN, base_seed=3, want_profiles=False)
+        assert np.array_equal(res[sigma]["v_mean"], one["means"]) and np.array_equal(res[sigma]["D_se"], one["D_ses"])
+        z = np.load(tmp_path / f"v_eff_vs_beta_sigma_{sigma:.4g}.npz", allow_pickle=True)
+        assert set(z.files) == {"beta", "v_mean", "v_se", "D_mean", "D_se", "ps_kwargs"}
+        assert z["ps_kwargs"].item()["local_kernel_sigma"] == sigma
+    assert not np.array_equal(res[0.0]["v_mean"], res[0.03]["v_mean"])
+    st_res = la.sweep_betas_for_structures([0.5], 4, dict(ps, local_kernel_sigma=0.03), {}, dict(T=4.0, obs_dt=0.25), k_keep=16)
+    raw = st_res[0.5]["raw"]
+    assert len(raw) == 4 and raw[0]["out"]["fft_amp_list"].shape == (16, 16) and raw[0]["out"]["var_list"].shape == (16,)
+    assert np.mean([r["var_mean"] for r in raw]) == pytest.approx(st_res[0.5]["var_mean"], rel=1e-12)
+    from aps_b200 import structure as st
+    lk = st.lowk_variance_time(torch.from_numpy(raw[0]["out"]["fft_amp_list"])[None], k_cut=10)
+    assert lk.shape == (1, 16) and float(lk[0, 8:].mean()) > 0

@@ -310,6 +310,14 @@ def run_case(PS, name, spec):
     return ps, out
 
 
+def cases_reducers():
+    return {tag: dict(ps=dict(L=1000, xlim=1, rate_diffusion=0.02, rate_active=5, beta=beta, init="poisson", N=500,
+                              scale_rates=False, local_kernel_sigma=0.005, site_capacity=1),
+                      profile=dict(L=1000, N=500, frac_plus=0.75, decay_plus=0.35),
+                      run=dict(T=3.0, obs_dt=0.1, record_fft=True, record_var=True), seed=seed)
+            for tag, beta, seed in [("b0", 0.5, 77), ("b2", 2.0, 78)]}
+
+
 def reducer_golden(PS):
     """Golden outputs of the sweep driver's per-run reducers on a short sweep_beta-like run."""
     names = ["compute_v_eff_and_window", "compute_rho_eff", "compute_blocking_probability",
@@ -321,11 +329,7 @@ def reducer_golden(PS):
     assert np.array_equal(r[2], rp) and np.array_equal(r[3], rm)
     assert all(r[0](i / 1000) == rp[i] and r[1](i / 1000) == rm[i] for i in range(1000))
     res = {}
-    for tag, beta, seed in [("b0", 0.5, 77), ("b2", 2.0, 78)]:
-        spec = dict(ps=dict(L=1000, xlim=1, rate_diffusion=0.02, rate_active=5, beta=beta, init="poisson", N=500,
-                            scale_rates=False, local_kernel_sigma=0.005, site_capacity=1),
-                    profile=dict(L=1000, N=500, frac_plus=0.75, decay_plus=0.35),
-                    run=dict(T=3.0, obs_dt=0.1, record_fft=True, record_var=True), seed=seed)
+    for tag, spec in cases_reducers().items():
         ps, out = run_case(PS, f"reducers_{tag}", spec)
         mean_v, v_eff, times, si, ei, frac_b = ns["compute_v_eff_and_window"](
             out, ps, boundary_xmin=0.99, max_buondary_fraction=0.06, min_window_fraction=0.10)
@@ -337,6 +341,45 @@ def reducer_golden(PS):
                         v_eff=v_eff.tolist(), frac_boundary=frac_b.tolist())
     json.dump(res, open(os.path.join(OUT, "reducers.json"), "w"), indent=1)
     print("reducers:", {k: {kk: vv for kk, vv in v.items() if not isinstance(vv, list)} for k, v in res.items()})
+
+
+def structure_golden(PS):
+    """Golden outputs of the local_structure driver's per-run analyses (local_structure.py:55-103,195-265) on the two
+    recorded reducer runs (record_fft=True), executed from the reference's own function definitions."""
+    names = ["extract_structure_observables_from_out", "time_to_pattern", "ensemble_time_to_pattern",
+             "cluster_size_distribution", "temporal_autocorrelation", "lowk_variance_time", "spectral_entropy",
+             "mode_competition_ratio", "extract_growth_rate"]
+    ns = extract_functions(os.path.join(REF, "PARTICLE_solver_BIOLOGY_local_structure.py"), names)
+    cases = cases_reducers()
+    res, outs = {}, []
+    for tag in ["b0", "b2"]:
+        ps, out = run_case(PS, f"reducers_{tag}", cases[tag])
+        outs.append(out)
+        obs = ns["extract_structure_observables_from_out"](out, start_fraction=0.5, k_max=None)
+        thr_k = {k: float(np.sort(out["fft_amp_list"][:, k])[-3:-1].mean()) for k in (1, 2, 3, 5)}   # exceeded by two rows only
+        thr = thr_k[2]
+        d = {k: (float(v) if np.isscalar(v) or np.ndim(v) == 0 else None) for k, v in obs.items()}
+        d.update(fft_mean_head=obs["fft_mean"][:40].tolist(), fft_std_head=obs["fft_std"][:40].tolist(),
+                 dominant_k=int(obs["dominant_k"]), threshold=thr,
+                 thresholds={str(k): v for k, v in thr_k.items()},
+                 time_to_pattern={str(k): float(ns["time_to_pattern"](out, threshold=v, k=k)) for k, v in thr_k.items()},
+                 time_to_pattern_never=float(ns["time_to_pattern"](out, threshold=1e9, k=2)),
+                 lowk_variance_time=ns["lowk_variance_time"](out, k_cut=25).tolist(),
+                 autocorr_lag1=float(ns["temporal_autocorrelation"](out, lag=1)),
+                 autocorr_lag3=float(ns["temporal_autocorrelation"](out, lag=3)),
+                 growth_rate=float(ns["extract_growth_rate"](out, k=1, t_min=0.5, t_max=2.5, amp_min=1e-4)),
+                 growth_rate_k3=float(ns["extract_growth_rate"](out, k=3, t_min=0.0, t_max=None, amp_min=1e-4)),
+                 growth_rate_nan=float(ns["extract_growth_rate"](out, k=1, t_min=2.85, t_max=None, amp_min=1e-4)),
+                 spectral_entropy=float(ns["spectral_entropy"](obs["fft_mean"], k_max=25)),
+                 spectral_entropy_full=float(ns["spectral_entropy"](obs["fft_mean"])),
+                 mode_competition=float(ns["mode_competition_ratio"](obs["fft_mean"])),
+                 clusters=ns["cluster_size_distribution"](out["total_list"][-1], 0.5 * out["total_list"][-1].max()).tolist())
+        res[tag] = d
+    thr = min(res["b0"]["threshold"], res["b2"]["threshold"])
+    mean_t, se_t = ns["ensemble_time_to_pattern"](outs, k=2, threshold=thr)
+    res["ensemble"] = dict(threshold=thr, mean=float(mean_t), se=float(se_t))
+    json.dump(res, open(os.path.join(OUT, "structure.json"), "w"), indent=1)
+    print("structure:", {k: {kk: vv for kk, vv in v.items() if not isinstance(vv, list)} for k, v in res.items()})
 
 
 STAT_PS = dict(L=100, xlim=1, rate_diffusion=0.3, rate_active=3, init="fixed", N=40, scale_rates=False,
@@ -415,6 +458,8 @@ def main():
         run_case(PS, name, spec)
     if not want or "reducers" in want:
         reducer_golden(PS)
+    if not want or "structure" in want:
+        structure_golden(PS)
     if not want or "stat" in want:
         stat_fixture(PS)
     if not want or "pde" in want:
