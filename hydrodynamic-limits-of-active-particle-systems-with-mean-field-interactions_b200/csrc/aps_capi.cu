@@ -25,6 +25,7 @@ int g_k1_threads = 0;  // 0 = heuristic
 int g_use_lut = 1;
 int g_use_fast = 1;
 int g_k2_ctas_per_sm = 6;
+int g_k2_stash_cap = 0;        // 0 = from the mean trial count (aps::k2_stash_cap)
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -345,11 +346,12 @@ int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates
     return APS_OK;
 }
 
-static size_t k2_smem(int radius) {
+static size_t k2_smem(int radius, int cap) {
     const size_t WB = aps::kK2Tile + 32;
     const size_t R16 = radius >= 0 ? (size_t)((radius + 15) & ~15) : 0;
-    const size_t stride = WB + (radius >= 0 ? WB + 2 * R16 : 0);
-    return 128 + (size_t)(radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal) * stride;
+    const size_t stride = WB + 2 * R16;              // local field: window + halo in one buffer per stage
+    return 128 + (size_t)(radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal) * stride +
+           (radius >= 0 ? aps::k2_scratch_bytes(radius, cap) + 16 : 0);
 }
 
 int aps_k2_flip_table(double beta, uint32_t* out) {
@@ -368,7 +370,8 @@ int aps_k2_pass_device(const aps_k2_args* a, void* stream) {
     if (a->radius >= 0 && (!a->w16 || !a->flip_tab)) return fail(APS_ERR_INVALID, "aps_k2_pass: local field needs w16 taps and flip_tab");
     if (a->radius < 0 && (!a->msum_in || a->n_particles < 1)) return fail(APS_ERR_INVALID, "aps_k2_pass: global field needs msum_in and n_particles");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
-    const size_t smem = k2_smem(a->radius);
+    const int cap = g_k2_stash_cap > 0 ? g_k2_stash_cap : aps::k2_stash_cap(a->rates.mu);
+    const size_t smem = k2_smem(a->radius, cap);
     if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_k2_pass: radius too large for the shared-memory ring");
     const int ntiles = (int)(a->L / aps::kK2Tile);
     static int n_sm = 0;
@@ -380,10 +383,10 @@ int aps_k2_pass_device(const aps_k2_args* a, void* stream) {
     if (grid > ntiles) grid = ntiles;
     if (a->radius >= 0) {
         CU(cudaFuncSetAttribute(aps::k2_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        aps::k2_pass_kernel<true><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a);
+        aps::k2_pass_kernel<true><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap);
     } else {
         CU(cudaFuncSetAttribute(aps::k2_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        aps::k2_pass_kernel<false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a);
+        aps::k2_pass_kernel<false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap);
     }
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
@@ -435,6 +438,7 @@ void aps_debug_set_guard_scale(double s) { g_guard_scale = s; }
 void aps_debug_set_k1_threads(int nt) { g_k1_threads = (nt == 32 || nt == 64 || nt == 128 || nt == 256) ? nt : 0; }
 void aps_debug_set_use_lut(int on) { g_use_lut = on ? 1 : 0; }
 void aps_debug_set_k2_ctas_per_sm(int n) { g_k2_ctas_per_sm = n > 0 ? n : 6; }
+void aps_debug_set_k2_stash_cap(int n) { g_k2_stash_cap = (n == 1 || n == 2 || n == 4 || n == 8 || n == 16 || n == 32) ? n : 0; }
 void aps_debug_set_use_fast(int on) { g_use_fast = on; }   // 0 generic only, 1 capacity classes, 2 run-time layout
 
 }  // extern "C"

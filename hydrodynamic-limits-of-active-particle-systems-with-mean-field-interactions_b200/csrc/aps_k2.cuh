@@ -2,14 +2,14 @@
 // Update rule: include/aps_k2_model.h (synchronous sublattice KMC; shared with the oracle).
 //
 // HBM design: one byte per site, one pass = one streamed read + one streamed write of the lattice
-// (2 B per site-visit).  A CTA owns a window of APS_K2_TILE sites whose borders sit in the middle of
-// the inactive halves of that parity (so no update ever crosses a window border), stages it into
-// shared memory with 16-byte vector loads, lets each of its 128 threads run the trials of one
-// 64-site segment (shared-memory layout padded by one word per segment -> conflict-free lanes),
-// and writes the window back with 16-byte vector stores to the ping-pong buffer.  The frozen copy
-// used by the local magnetisation (+-r halo) is a second shared-memory array.  Random bits are
-// spent per EVENT (Poisson number of trials per segment), not per site, which is what keeps the
-// kernel memory-bound at small rate*dt.
+// (2 B per site-visit).  A persistent CTA walks windows of APS_K2_TILE sites whose borders sit in the middle
+// of the inactive halves of that parity (so no update ever crosses a window border): a TMA bulk load
+// (mbarrier complete_tx) brings the window — for the local field together with its +-r halo — into a ring
+// of shared-memory stages, each of the 128 threads runs the trials of one 64-site segment in place, and a
+// TMA bulk store writes the window to the ping-pong buffer.  Random bits are spent per EVENT (Poisson
+// number of trials per segment), not per site, which is what keeps the kernel memory-bound at small
+// rate*dt.  The local magnetisation needs the state at the START of the pass: all fields of a
+// tile are evaluated before a block barrier and only then is the tile modified (see k2_pass_kernel).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -55,15 +55,67 @@ __device__ __forceinline__ void k2_tma_store(void* gdst, const void* ssrc, uint3
 }
 
 constexpr int kK2StagesGlobal = 4;   // global field: copy-bound, deep prefetch
-constexpr int kK2StagesLocal = 2;    // local field: compute-bound, favour resident CTAs over prefetch depth
+constexpr int kK2StagesLocal = 3;    // local field: window + halo per stage, plus one frozen copy per CTA
+
+// ---- local-field mode: per-CTA scratch for the three-phase tile update (see k2_pass_kernel) ----
+// Trials of a segment beyond the stash capacity (and flip candidates beyond the list capacity) are rare and are
+// replayed inline from the Philox counters, so the capacities only affect speed, never results.
+__host__ __device__ inline int k2_stash_cap(double mu) { return mu <= 2.6 ? 8 : (mu <= 8.0 ? 16 : 32); }
+__host__ __device__ inline bool k2_packed_taps(int radius) { return radius >= 1 && radius <= 127; }
+__host__ __device__ inline int k2_tap_words(int radius) { return (2 * radius + 7) / 4; }   // covers 2r+1 bytes at any alignment
+__host__ __device__ inline size_t k2_scratch_bytes(int radius, int cap) {
+    size_t b = k2_packed_taps(radius) ? (size_t)k2_tap_words(radius) * 4 * 8 : 0;   // taps[word][shift] (2 x u32)
+    b += (size_t)kK2Threads * cap * (4 + 4 + 2);     // per warp: acceptance words, candidate list, 16-bit trial codes
+    return (b + 15) & ~(size_t)15;
+}
+
+// sum of the integer taps over the '+' and '-' sites of the window centred at snap[c]: four sites per step with dp2a
+// (two 16-bit taps x two site bytes per instruction); taps[k*4 + s] holds the taps of word k for window alignment s.
+__device__ __forceinline__ void k2_field_packed(const unsigned char* snap, int c, int r, const uint2* taps, int nwords,
+                                                int& sw, int& tw) {
+    const int start = c - r, sft = start & 3;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(snap + (start - sft));
+    unsigned P = 0, Mi = 0;
+    for (int k = 0; k < nwords; ++k) {
+        const uint32_t w = wp[k];
+        const uint2 t = taps[k * 4 + sft];
+        const uint32_t pl = w & 0x01010101u, mi = (w >> 1) & 0x01010101u;
+        P = __dp2a_lo(t.x, pl, P); P = __dp2a_hi(t.y, pl, P);
+        Mi = __dp2a_lo(t.x, mi, Mi); Mi = __dp2a_hi(t.y, mi, Mi);
+    }
+    sw = (int)P - (int)Mi; tw = (int)(P + Mi);
+}
+__device__ __forceinline__ void k2_field_scalar(const unsigned char* snap, int c, int r, const int32_t* __restrict__ w16, int& sw, int& tw) {
+    sw = 0; tw = 0;
+    for (int k = 0; k <= 2 * r; ++k) {
+        const int cv = snap[c - r + k];
+        const int wj = w16[k < r ? r - k : k - r];
+        sw += wj * ((cv & 1) - (cv >> 1));
+        tw += wj * (cv != 0);
+    }
+}
 
 // One pass, persistent CTAs.  Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through a
 // kK2Stages-deep ring of shared-memory buffers: TMA bulk loads (mbarrier complete_tx) bring the window
 // (and, for the local field, a second read-only copy with the +-r halo) in, the 128 threads run the
 // trials of their segments in place, and a TMA bulk store writes the window to the ping-pong buffer.
 // LOCAL: Gaussian local field from the frozen copy; otherwise the global magnetisation.
+//
+// Global field: one thread walks the trials of its segment (Philox on the fly, two integer compares per trial).
+// Local field: the field of a flip trial costs 2r+1 taps and depends only on the FROZEN copy, so each warp splits
+// the update of its 32 segments into three warp-synchronous phases instead of letting one lane walk taps while
+// 31 wait:
+//   A  the trials are generated up front and stashed as 16 bits (site, rate slot) + the acceptance word; the flip
+//      candidates are compacted into a per-warp list with ballots;
+//   B  the list is evaluated densely, one candidate per lane (dp2a over the frozen bytes, four sites per step),
+//      and both acceptance bits (particle '+' / '-') are written back into the stash;
+//   -- block barrier: every field of the tile has been read from the still unmodified buffer, which therefore IS the
+//      frozen state (no second copy of the window in shared memory, one bulk load per tile incl. the +-r halo) --
+//   C  each lane replays its stashed trials in order against the live tile: no RNG, no taps, a few integer ops.
+// The decisions are the same function of (Philox words, state, frozen field) as in the oracle's serial loop;
+// trials beyond the stash capacity keep their two acceptance bits in register masks (Philox regenerated in C).
 template <bool LOCAL>
-__global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_constant__ aps_k2_args a) {
+__global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_constant__ aps_k2_args a, const int stash_cap) {
     extern __shared__ __align__(128) unsigned char k2_raw[];
     const int tid = threadIdx.x;
     const long long L = a.L;                         // sites held by this call (slab incl. ghosts)
@@ -74,12 +126,24 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     const int ntiles = (int)(L / kK2Tile);
     constexpr int WB = kK2Tile + 32;                 // largest window
     constexpr int kK2Stages = LOCAL ? kK2StagesLocal : kK2StagesGlobal;
-    const int stride = WB + (LOCAL ? WB + 2 * R16 : 0);
+    const int stride = WB + 2 * R16;                 // LOCAL: [lo - R16, hi + R16) in one buffer, the window at offset R16
     uint64_t* bars = reinterpret_cast<uint64_t*>(k2_raw);
     unsigned char* bufs = k2_raw + 128;
     __shared__ uint32_t thr_glob[2];
     const uint8_t* __restrict__ in = a.in;
     uint8_t* __restrict__ out = a.out;
+
+    // local-field scratch behind the ring: taps, then per warp [cap][32] acceptance words, candidate list, trial codes
+    const int cap = stash_cap;
+    const bool packed = LOCAL && k2_packed_taps(r) && a.w16[0] <= 65535;
+    const int nwords = k2_tap_words(r);
+    unsigned char* scr = bufs + (size_t)kK2Stages * stride;
+    uint2* taps = reinterpret_cast<uint2*>(scr);
+    uint32_t* base32 = reinterpret_cast<uint32_t*>(scr + (k2_packed_taps(r) ? (size_t)nwords * 32 : 0));
+    const int per = 32 * cap, wv = tid >> 5;
+    uint32_t* wb32 = base32 + wv * per;
+    uint32_t* list = base32 + (kK2Threads / 32) * per + wv * per;
+    uint16_t* code16 = reinterpret_cast<uint16_t*>(base32 + 2 * (kK2Threads / 32) * per) + wv * per;
 
     if (tid == 0) {
         for (int s2 = 0; s2 < kK2Stages; ++s2) k2_mbar_init(&bars[s2], 1);
@@ -88,6 +152,17 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             const double m = APS_DIV((double)(*a.msum_in), (double)a.n_particles);
             thr_glob[0] = aps_k2_flip_thr(a.rates.beta, +1, m, a.rates.inv_cmax);
             thr_glob[1] = aps_k2_flip_thr(a.rates.beta, -1, m, a.rates.inv_cmax);
+        }
+    }
+    if (LOCAL && packed) {
+        for (int e = tid; e < nwords * 4; e += kK2Threads) {
+            const int k = e >> 2, sft = e & 3;
+            uint32_t tw4[4];
+            for (int j = 0; j < 4; ++j) {
+                const int ti = 4 * k + j - sft;
+                tw4[j] = (ti >= 0 && ti <= 2 * r) ? (uint32_t)a.w16[ti < r ? r - ti : ti - r] : 0u;
+            }
+            taps[e] = make_uint2(tw4[0] | (tw4[1] << 16), tw4[2] | (tw4[3] << 16));
         }
     }
     __syncthreads();
@@ -99,14 +174,18 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     };
     auto issue_load = [&](int t, int s2) {          // thread 0 only
         long long lo, hi; window(t, lo, hi);
-        unsigned char* work = bufs + (size_t)s2 * stride;
+        unsigned char* work_b = bufs + (size_t)s2 * stride;
         uint32_t bytes = (uint32_t)(hi - lo);
         long long slo = lo - R16, shi = hi + R16;
         if (slo < 0) slo = 0;
         if (shi > L) shi = L;
-        k2_mbar_expect_tx(&bars[s2], bytes + (LOCAL ? (uint32_t)(shi - slo) : 0u));
-        k2_tma_load(work, in + lo, bytes, &bars[s2]);
-        if (LOCAL) k2_tma_load(work + WB + (slo - (lo - R16)), in + slo, (uint32_t)(shi - slo), &bars[s2]);
+        if (LOCAL) {       // window and +-R16 halo in one bulk copy
+            k2_mbar_expect_tx(&bars[s2], (uint32_t)(shi - slo));
+            k2_tma_load(work_b + (slo - (lo - R16)), in + slo, (uint32_t)(shi - slo), &bars[s2]);
+        } else {
+            k2_mbar_expect_tx(&bars[s2], bytes);
+            k2_tma_load(work_b, in + lo, bytes, &bars[s2]);
+        }
     };
 
     const int my_first = blockIdx.x, step_t = gridDim.x;
@@ -114,13 +193,16 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         for (int k = 0; k < kK2Stages - 1; ++k) { int t = my_first + k * step_t; if (t < ntiles) issue_load(t, k); }
     }
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const uint32_t t_left = a.rates.t_left, t_right = a.rates.t_right, t_active = a.rates.t_active;
     int dsig = 0;
     int it = 0;
     for (int t = my_first; t < ntiles; t += step_t, ++it) {
         const int s2 = it % kK2Stages;
         long long lo, hi; window(t, lo, hi);
-        unsigned char* work = bufs + (size_t)s2 * stride;
-        unsigned char* snap = work + WB;             // snap[i - (lo - R16)] = site i (LOCAL only)
+        unsigned char* work_b = bufs + (size_t)s2 * stride;
+        // LOCAL: work_b[i - (lo - R16)] = site i; every field is read in phase B, before the barrier that lets phase C
+        // modify the tile, so the live buffer IS the frozen state the model asks for
+        unsigned char* snap = work_b;
         k2_mbar_wait(&bars[s2], (uint32_t)((it / kK2Stages) & 1));
         if (LOCAL && (t == 0 || t == ntiles - 1)) {   // reflect padding at the ends of this slab
             for (int j = tid; j < r; j += kK2Threads) {
@@ -136,81 +218,112 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         const uint32_t c0 = (uint32_t)seg_global, c1 = (uint32_t)a.pass;
         const uint32_t chi = (uint32_t)(seg_global >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
         const long long abase = t0 + (long long)tid * APS_K2_SEG + qpar * APS_K2_HALF;     // first active site (slab index)
-        // The trial loop runs in warp lock-step up to the largest trial count of the warp so that the local
-        // field of any lane can be evaluated COOPERATIVELY: the 2r+1 integer taps are spread over the 32 lanes
-        // and summed with redux.sync, instead of one lane walking them while 31 wait.
         const bool seg_ok = abase + APS_K2_HALF <= L;
         aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
         int ntr = 0;
         if (seg_ok) while (ntr < (int)a.rates.n_cdf && w4.v[0] >= a.rates.cdf32[ntr]) ++ntr;
-        const int ntr_max = LOCAL ? __reduce_max_sync(0xffffffffu, ntr) : ntr;
-        int wreg0 = 0, wreg1 = 0;       // this lane's Gaussian taps (k = lane and lane + 32) when r <= 31
-        if (LOCAL && r <= 31) {
-            const int l2 = tid & 31;
-            if (l2 <= 2 * r) wreg0 = a.w16[l2 < r ? r - l2 : l2 - r];
-            if (l2 + 32 <= 2 * r) wreg1 = a.w16[l2 + 32 - r];
-        }
-        unsigned char* act = work + (abase - lo);
-        for (int tr = 0; tr < ntr_max; ++tr) {
-            const bool live = tr < ntr;
-            uint32_t wa = 0, wb = 0;
-            if (live) {
+        unsigned char* act = work_b + R16 + (abase - lo);
+
+        // one trial against the live tile; `acc` = acceptance of a flip for the particle found at the site
+        auto hop_or_flip = [&](int x, int cat, auto&& accept) {
+            const unsigned char v = act[x];
+            if (v == APS_K2_EMPTY) return;
+            const long long lx = abase + x;
+            if (cat == 0) {
+                if (lx > 0 && act[x - 1] == APS_K2_EMPTY) { act[x - 1] = v; act[x] = APS_K2_EMPTY; }
+            } else if (cat == 1 || (cat == 2 && v == APS_K2_PLUS)) {
+                if (lx < L - 1 && act[x + 1] == APS_K2_EMPTY) { act[x + 1] = v; act[x] = APS_K2_EMPTY; }
+            } else if (cat == 3) {
+                if (accept(v)) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= (v == APS_K2_PLUS) ? 2 : -2; }
+            }
+        };
+        auto category = [&](uint32_t slot) { return slot < t_left ? 0 : (slot < t_right ? 1 : (slot < t_active ? 2 : 3)); };
+
+        if (!LOCAL) {
+            for (int tr = 0; tr < ntr; ++tr) {
+                uint32_t wa, wb;
                 if (tr == 0) { wa = w4.v[2]; wb = w4.v[3]; }
                 else {
                     if (tr & 1) w4 = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
                     wa = (tr & 1) ? w4.v[0] : w4.v[2]; wb = (tr & 1) ? w4.v[1] : w4.v[3];
                 }
+                hop_or_flip((int)(wa >> 27), category(wa << 5), [&](unsigned char v) { return wb < thr_glob[v == APS_K2_PLUS ? 0 : 1]; });
             }
-            const int x = (int)(wa >> 27);
-            const uint32_t slot = wa << 5;
-            const long long lx = abase + x;
-            const unsigned char v = live ? act[x] : (unsigned char)APS_K2_EMPTY;
-            bool want_flip = false;
-            if (v != APS_K2_EMPTY) {
-                if (slot < a.rates.t_left) {
-                    if (lx > 0 && act[x - 1] == APS_K2_EMPTY) { act[x - 1] = v; act[x] = APS_K2_EMPTY; }
-                } else if (slot < a.rates.t_right || (slot < a.rates.t_active && v == APS_K2_PLUS)) {
-                    if (lx < L - 1 && act[x + 1] == APS_K2_EMPTY) { act[x + 1] = v; act[x] = APS_K2_EMPTY; }
-                } else if (slot >= a.rates.t_active) want_flip = true;
-            }
-            const int sg = (v == APS_K2_PLUS) ? 1 : -1;
-            uint32_t thr = 0;
-            if (LOCAL) {
-                int my_sw = 0, my_tw = 0;
-                unsigned need = __ballot_sync(0xffffffffu, want_flip);
-                const int lane = tid & 31;
-                const int centre = (int)(lx - lo) + R16;                  // snap index of this lane's site
-                while (need) {
-                    const int src = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int cidx = __shfl_sync(0xffffffffu, centre, src);
-                    int sw, tw;
-                    if (r <= 31) {          // at most two taps per lane, weights held in registers
-                        const int cv0 = snap[cidx - r + lane];
-                        const int cv1 = (lane + 32 <= 2 * r) ? snap[cidx - r + lane + 32] : 0;
-                        sw = wreg0 * ((cv0 & 1) - (cv0 >> 1)) + wreg1 * ((cv1 & 1) - (cv1 >> 1));
-                        tw = wreg0 * (cv0 != 0) + wreg1 * (cv1 != 0);
-                    } else {
-                        sw = 0; tw = 0;
-                        for (int k = lane; k <= 2 * r; k += 32) {
-                            const int cv = snap[cidx - r + k];
-                            const int wj = a.w16[k < r ? r - k : k - r];
-                            sw += wj * ((cv & 1) - (cv >> 1));
-                            tw += wj * (cv != 0);
-                        }
+        } else {
+            const int lane = tid & 31;
+            const int cbase = (int)(abase - lo) + R16;                     // snap index of this segment's first active site
+            auto field_thresholds = [&](int centre, uint32_t& thr_p, uint32_t& thr_m) {
+                int sw, tw;
+                if (packed) k2_field_packed(snap, centre, r, taps, nwords, sw, tw);
+                else k2_field_scalar(snap, centre, r, a.w16, sw, tw);
+                const int mq = aps_k2_mq_index(sw, tw);
+                thr_p = a.flip_tab[mq]; thr_m = a.flip_tab[2 * APS_K2_MQ + 1 + mq];
+            };
+            // ---- phase A: generate, stash ([trial][lane] layout) and compact the flip candidates ----
+            const int tmax = ntr < cap ? ntr : cap;
+            const int it_max = __reduce_max_sync(0xffffffffu, tmax);
+            int nl = 0;                                                    // warp-uniform length of the candidate list
+            for (int tr = 0; tr < it_max; ++tr) {
+                const bool live = tr < tmax;
+                uint32_t wa = 0, wb = 0;
+                if (live) {
+                    if (tr == 0) { wa = w4.v[2]; wb = w4.v[3]; }
+                    else {
+                        if (tr & 1) w4 = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
+                        wa = (tr & 1) ? w4.v[0] : w4.v[2]; wb = (tr & 1) ? w4.v[1] : w4.v[3];
                     }
-                    sw = __reduce_add_sync(0xffffffffu, sw);
-                    tw = __reduce_add_sync(0xffffffffu, tw);
-                    if (lane == src) { my_sw = sw; my_tw = tw; }
                 }
-                if (want_flip) thr = a.flip_tab[(sg == 1 ? 0 : (2 * APS_K2_MQ + 1)) + aps_k2_mq_index(my_sw, my_tw)];
-            } else if (want_flip) thr = thr_glob[sg == 1 ? 0 : 1];
-            if (want_flip && wb < thr) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
+                const int x = (int)(wa >> 27), cat = category(wa << 5), slot = tr * 32 + lane;
+                const bool cand = live && cat == 3;
+                const unsigned mask = __ballot_sync(0xffffffffu, cand);
+                if (live) code16[slot] = (uint16_t)((uint32_t)x | ((uint32_t)cat << 5));
+                if (cand) {
+                    wb32[slot] = wb;
+                    list[nl + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(cbase + x) | ((uint32_t)slot << 14);
+                }
+                nl += __popc(mask);
+            }
+            __syncwarp();
+            // ---- phase B: dense evaluation of the flip candidates, one per lane ----
+            for (int e = lane; e < nl; e += 32) {
+                const uint32_t ent = list[e];
+                const int slot = (int)(ent >> 14);
+                uint32_t thr_p, thr_m;
+                field_thresholds((int)(ent & 0x3fffu), thr_p, thr_m);
+                const uint32_t wb = wb32[slot];
+                code16[slot] = (uint16_t)(code16[slot] | (wb < thr_p ? 1u << 7 : 0u) | (wb < thr_m ? 1u << 8 : 0u));
+            }
+            // trials beyond the stash capacity (rare): acceptance bits into two register masks, still before the barrier
+            unsigned long long ov_p = 0ULL, ov_m = 0ULL;
+            for (int tr = cap; tr < ntr; ++tr) {
+                const aps_u32x4 wq = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
+                const uint32_t wa = (tr & 1) ? wq.v[0] : wq.v[2], wb = (tr & 1) ? wq.v[1] : wq.v[3];
+                if (category(wa << 5) == 3) {
+                    uint32_t thr_p, thr_m;
+                    field_thresholds(cbase + (int)(wa >> 27), thr_p, thr_m);
+                    ov_p |= (unsigned long long)(wb < thr_p) << (tr - cap);
+                    ov_m |= (unsigned long long)(wb < thr_m) << (tr - cap);
+                }
+            }
+            __syncthreads();                                               // every field of the tile has been read
+            // ---- phase C: replay the trials in order against the live tile ----
+            for (int tr = 0; tr < ntr; ++tr) {
+                if (tr < cap) {
+                    const uint32_t code = code16[tr * 32 + lane];
+                    hop_or_flip((int)(code & 31u), (int)((code >> 5) & 3u),
+                                [&](unsigned char v) { return (code >> (v == APS_K2_PLUS ? 7 : 8)) & 1u; });
+                } else {
+                    const aps_u32x4 wq = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
+                    const uint32_t wa = (tr & 1) ? wq.v[0] : wq.v[2];
+                    hop_or_flip((int)(wa >> 27), category(wa << 5),
+                                [&](unsigned char v) { return ((v == APS_K2_PLUS ? ov_p : ov_m) >> (tr - cap)) & 1ULL; });
+                }
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk store
         __syncthreads();
         if (tid == 0) {
-            k2_tma_store(out + lo, work, (uint32_t)(hi - lo));
+            k2_tma_store(out + lo, work_b + R16, (uint32_t)(hi - lo));
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             // the buffer used one iteration ago is free once its store has finished READING shared memory
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");

@@ -144,6 +144,28 @@ def test_gpu_pass_equals_oracle_bitwise(sigma, tiles):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cap", [1, 2, 32])
+@pytest.mark.parametrize("sigma", [0.1, 5.0])
+def test_gpu_local_field_capacities_do_not_change_results(cap, sigma):
+    """Local-field K2 stashes the trials of a tile and evaluates the flip candidates in a dense pass; trials beyond
+    the stash (and candidates beyond the list) are replayed inline.  Any capacity must give the oracle's bits
+    (cap = 1, 2: almost everything goes through the inline path and the candidate list overflows)."""
+    lib = capi.load()
+    kw = dict(sigma_sites=sigma, seed=7, D=0.3, lam=3.0, beta=1.2, dt=0.02)     # ~4.4 trials per half and pass
+    L = 2 * TILE
+    try:
+        lib.aps_debug_set_k2_stash_cap(cap)
+        g = SublatticeLattice(L, **kw)
+        o = oracle_lattice(L, **kw)
+        g.init_random(0.6, 0.5); o.init_random(0.6, 0.5)
+        for chunk in [1, 9]:
+            g.run_passes(chunk); o.run_passes(chunk)
+            assert np.array_equal(g.state.cpu().numpy(), o.state.numpy()), (cap, sigma, chunk)
+    finally:
+        lib.aps_debug_set_k2_stash_cap(0)
+
+
+@pytest.mark.gpu
 def test_gpu_large_lattice_invariants():
     """2^24 sites (16 MiB per buffer): conservation, exclusion and a flat interior profile at beta = 0."""
     L = 1 << 24
