@@ -121,7 +121,8 @@ def measure_k2(torch, logL=30, passes=30):
     traffic_file = os.path.join(ROOT, "profiles", "k2_ncu_traffic.json")
     traffic = json.load(open(traffic_file)) if os.path.exists(traffic_file) else {}
     for name, sigma, dt in [("global field, dt=0.0025", None, 0.0025), ("global field, dt=0.005", None, 0.005),
-                            ("global field, dt=0.02", None, 0.02), ("local Gaussian field sigma=5 sites, dt=0.005", 5.0, 0.005)]:
+                            ("global field, dt=0.02", None, 0.02), ("local Gaussian field sigma=5 sites, dt=0.005", 5.0, 0.005),
+                            ("local Gaussian field sigma=5 sites, dt=0.0025", 5.0, 0.0025)]:
         lat = SublatticeLattice(1 << logL, D=0.02, lam=5.0, beta=2.0, dt=dt, sigma_sites=sigma, seed=0,
                                 single_rank=True)     # the K2 roofline is a one-GPU measurement on rank 0 at every N
         lat.init_random(0.5, 0.5)
