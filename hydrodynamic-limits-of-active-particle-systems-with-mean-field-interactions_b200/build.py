@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OUT = os.path.join(CSRC, "libaps_b200.so")
-SOURCES = ["aps_capi.cu", "aps_fast.cu"]
+SOURCES = ["aps_capi.cu", "aps_fast.cu", "aps_pde.cu"]
+FMA_OK = {"aps_pde.cu"}          # tolerance-parity code (IMEX PDE stepper): contraction allowed
 
 
 def nvcc_path() -> str:
@@ -38,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         flags.insert(0, "-Xptxas=-v")
     objs = [os.path.join(CSRC, s[:-3] + ".o") for s in SOURCES]
-    procs = [subprocess.Popen([nvcc_path()] + flags + ["-c", os.path.join(CSRC, s), "-o", o], cwd=CSRC)
+    procs = [subprocess.Popen([nvcc_path()] + [f for f in flags if not (s in FMA_OK and f == "--fmad=false")] +
+                              ["-c", os.path.join(CSRC, s), "-o", o], cwd=CSRC)
              for s, o in zip(SOURCES, objs)]          # translation units compile in parallel
     if any(p.wait() != 0 for p in procs):
         raise subprocess.CalledProcessError(1, "nvcc -c")

@@ -137,7 +137,19 @@ class ApsK2Args(C.Structure):
                 ("msum_in", C.c_void_p), ("msum_out", C.c_void_p)]
 
 
-# every symbol include/aps.h declares: name -> (restype, argtypes)
+class ApsPdeArgs(C.Structure):          # include/aps_pde.h
+    _fields_ = [("L", C.c_int32), ("n_runs", C.c_int32), ("bc", C.c_int32), ("model", C.c_int32), ("field", C.c_int32),
+                ("snapshot_interval", C.c_int32), ("n_tracers", C.c_int32), ("window", C.c_int32), ("nsteps", C.c_int64),
+                ("dt", C.c_double), ("dx", C.c_double), ("xlim", C.c_double)] + \
+               [(k, C.c_void_p) for k in ["beta", "lam", "gamma", "kernel", "radius", "seeds", "rho_p", "rho_m", "m_series",
+                                          "var_series", "snapshots", "m_snapshots", "tracer_pos", "tracer_state",
+                                          "tracer_hist", "v_eff_series", "D_eff_series"]]
+
+
+APS_PDE_BC = {"periodic": 0, "neumann": 1}
+APS_PDE_MODEL = {"bidirectional": 0, "anchored_minus": 1}
+
+# every symbol include/aps.h and include/aps_pde.h declare: name -> (restype, argtypes)
 _P = C.POINTER
 SYMBOLS = {
     "aps_abi_version": (C.c_int, []),
@@ -161,6 +173,8 @@ SYMBOLS = {
     "aps_k2_run_device": (C.c_int, [_P(ApsK2Args), C.c_int, C.c_void_p]),
     "aps_k2_init_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_void_p]),
     "aps_k2_profile_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "aps_pde_solve_device": (C.c_int, [_P(ApsPdeArgs), C.c_void_p]),
+    "aps_pde_smem_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "aps_debug_set_guard_scale": (None, [C.c_double]),
     "aps_debug_set_k1_threads": (None, [C.c_int]),
     "aps_debug_set_use_lut": (None, [C.c_int]),

@@ -14,6 +14,11 @@
 #include "aps_init.cuh"
 #include "aps_k2.cuh"
 
+#include "../../include/aps_pde.h"
+namespace aps {
+size_t pde_smem_bytes(int L, int bc, int n_tracers);
+cudaError_t pde_launch(const aps_pde_args& a, cudaStream_t st);
+}
 namespace aps { cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched); }
 
 namespace {
@@ -429,6 +434,29 @@ int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset
     aps::k2_profile_kernel<<<(unsigned)((L + 4095) / 4096), 256, 0, (cudaStream_t)stream>>>(
         state, L, global_offset, L_global, nbins, (unsigned long long*)cnt_plus, (unsigned long long*)cnt_minus);
     CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+// ---- batched IMEX PDE stepper (include/aps_pde.h) ----
+int64_t aps_pde_smem_bytes(int32_t L, int32_t bc) { return (int64_t)aps::pde_smem_bytes(L, bc, 0); }
+
+int aps_pde_solve_device(const aps_pde_args* a, void* stream) {
+    if (!a || a->n_runs < 1 || a->nsteps < 0 || !(a->dt > 0) || !(a->dx > 0) || !(a->xlim > 0) || a->snapshot_interval < 1)
+        return fail(APS_ERR_INVALID, "aps_pde_solve: bad scalar argument");
+    if (a->bc != APS_PDE_BC_PERIODIC && a->bc != APS_PDE_BC_NEUMANN) return fail(APS_ERR_INVALID, "aps_pde_solve: bc");
+    if (a->model != APS_PDE_MODEL_BIDIRECTIONAL && a->model != APS_PDE_MODEL_ANCHORED_MINUS) return fail(APS_ERR_INVALID, "aps_pde_solve: model");
+    if (a->field != APS_PDE_FIELD_POINTWISE && a->field != APS_PDE_FIELD_KERNEL) return fail(APS_ERR_INVALID, "aps_pde_solve: field");
+    if (!a->beta || !a->lam || !a->gamma || !a->rho_p || !a->rho_m || !a->m_series || !a->var_series)
+        return fail(APS_ERR_INVALID, "aps_pde_solve: missing required pointer");
+    if (a->field == APS_PDE_FIELD_KERNEL && (!a->kernel || !a->radius)) return fail(APS_ERR_INVALID, "aps_pde_solve: kernel field needs kernel and radius");
+    if (a->n_tracers > 0 && (a->window < 1 || !a->seeds || !a->tracer_pos || !a->tracer_state || !a->tracer_hist || !a->v_eff_series || !a->D_eff_series))
+        return fail(APS_ERR_INVALID, "aps_pde_solve: tracers need window >= 1, seeds, state, ring and output series");
+    const size_t smem = aps::pde_smem_bytes(a->L, a->bc, a->n_tracers);
+    if (smem == 0) return fail(APS_ERR_CAPACITY, "aps_pde_solve: need 8 <= L <= 2048 and n_tracers <= 2048");
+    if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_pde_solve: instance does not fit in shared memory");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    CU(aps::pde_launch(*a, (cudaStream_t)stream));
     g_launches.fetch_add(1);
     return APS_OK;
 }

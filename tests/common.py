@@ -15,7 +15,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def case_names():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith("stat_")]
+    return [n for n in names if not n.startswith(("stat_", "pde_"))]
 
 
 def load_case(name):

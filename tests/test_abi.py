@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "aps.h")).read()
+    src = open(os.path.join(ROOT, "include", "aps.h")).read() + open(os.path.join(ROOT, "include", "aps_pde.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(aps_[a-z0-9_]+)\s*\(", src)))
 
@@ -40,6 +40,7 @@ def test_struct_layout_matches_header(lib):
     # sizes the C compiler gives the two descriptors (x86-64 SysV): 4 int32 + 6 double; 4 int32 + 3 int64 + 36 pointers + exit_cap
     assert C.sizeof(capi.ApsParams) == 64
     assert C.sizeof(capi.ApsBatch) == 16 + 24 + 36 * 8 + 8
+    assert C.sizeof(capi.ApsPdeArgs) == 8 * 4 + 8 + 3 * 8 + 17 * 8      # include/aps_pde.h
 
 
 def test_invalid_arguments_are_rejected(lib):

@@ -448,6 +448,56 @@ def pde_fixture():
           "std x", np.sqrt((tot * x * x).sum() / tot.sum() - ((tot * x).sum() / tot.sum()) ** 2))
 
 
+PDE_STEP_CASES = {
+    "pde_periodic_kernel": dict(ctor=dict(L=200, xlim=1.0, T=0.15, dt=5e-4, gamma=2e-3, lam=0.6, beta=2.0, bc="periodic",
+                                          active_model="bidirectional", gaussian_kernel=True, kernel_sigma=0.02,
+                                          snapshot_interval=50, seed=5),
+                                init=dict(mode="homogeneous", rho0=1.0, noise=0.3, n_tracers=64)),
+    "pde_full_ring_kernel": dict(ctor=dict(L=128, xlim=1.0, T=0.1, dt=5e-4, gamma=0.0, lam=0.6, beta=1.0, bc="periodic",
+                                           active_model="bidirectional", gaussian_kernel=True, kernel_sigma=1e5 - 10,
+                                           snapshot_interval=40, seed=6),
+                                 init=dict(mode="homogeneous", rho0=1.0, noise=0.3, n_tracers=32)),
+    "pde_neumann_pointwise": dict(ctor=dict(L=100, xlim=1.0, T=0.15, dt=5e-4, gamma=0.2, lam=0.6, beta=1.5, bc="neumann",
+                                            active_model="bidirectional", gaussian_kernel=False, kernel_sigma=0.02,
+                                            snapshot_interval=100, seed=7),
+                                  init=dict(mode="poisson", rho0=1.0, noise=0.05, n_tracers=16)),
+    "pde_anchored_minus": dict(ctor=dict(L=150, xlim=1.0, T=0.2, dt=1e-3, gamma=0.01, lam=0.8, beta=2.5, bc="periodic",
+                                         active_model="anchored_minus", gaussian_kernel=True, kernel_sigma=0.05,
+                                         snapshot_interval=25, seed=8),
+                               init=dict(mode="homogeneous", rho0=1.0, noise=0.2, n_tracers=16)),
+    "pde_neumann_anchored": dict(ctor=dict(L=96, xlim=1.0, T=0.1, dt=5e-4, gamma=0.05, lam=1.0, beta=0.7, bc="neumann",
+                                           active_model="anchored_minus", gaussian_kernel=True, kernel_sigma=0.03,
+                                           snapshot_interval=10, seed=9),
+                                 init=dict(mode="poisson", rho0=1.0, noise=0.0, n_tracers=8)),
+}
+
+
+def pde_step_fixtures():
+    """Short runs of the unmodified IMEXPDE (IMEX_PDE_solver_class.py; matplotlib stubbed) through its public API:
+    initial state as initialize() leaves it, final fields, per-step diagnostics and snapshots (the deterministic part of
+    solve(); tracer outputs depend on numpy's global stream inside the time loop and are compared statistically)."""
+    for m in ["matplotlib", "matplotlib.pyplot"]:
+        sys.modules.setdefault(m, MagicMock())
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from IMEX_PDE_solver_class import IMEXPDE  # type: ignore
+    for name, spec in PDE_STEP_CASES.items():
+        pde = IMEXPDE(outdir="/tmp/imex_fixture", **spec["ctor"])
+        pde.initialize(**spec["init"])
+        init = dict(rho_p0=pde.rho_p.copy(), rho_m0=pde.rho_m.copy(), tracers0=pde.tracers_unwrapped.copy(),
+                    tracer_state0=pde.tracer_state.astype(np.int8))
+        with np.errstate(all="ignore"):
+            pde.solve()
+        out = pde.get_output()
+        meta = dict(ctor={k: v for k, v in spec["ctor"].items()}, init=spec["init"], nsteps=int(pde.nsteps), numpy=np.__version__)
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), meta=np.array(json.dumps(meta)), **init,
+                            rho_p=out["rho_p"], rho_m=out["rho_m"], m_series=out["m_series"], var_series=out["var_series"],
+                            snapshots=out["snapshots"], m_snapshots=out["m_snapshots"], times=out["times"],
+                            v_eff_series=out["v_eff_series"], D_eff_series=out["D_eff_series"],
+                            fft_amp_head=out["fft_amp"][:: max(1, pde.nsteps // 10), :16].copy())
+        print(f"{name}: nsteps={pde.nsteps} mass={float((out['rho_p'] + out['rho_m']).sum()):.12f} m_end={out['m_series'][-1]:.6f}")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     PS = import_reference()
@@ -464,6 +514,8 @@ def main():
         stat_fixture(PS)
     if not want or "pde" in want:
         pde_fixture()
+    if not want or "pde_step" in want:
+        pde_step_fixtures()
 
 
 if __name__ == "__main__":
