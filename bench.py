@@ -200,8 +200,8 @@ def main():
     # ---------------- device-resident arm (value) ----------------
     spec = la.build_beta_sweep_spec(betas, reps, PS_KWARGS, ik, run_kwargs, base_seed=1)
     lo, hi = la.shard_bounds(len(spec.betas), rank, world)
-    if world > 1:      # same strided assignment as launcher.run_ensemble: every rank gets 64 replicas of every beta
-        spec = la.permute_spec(spec, la.balanced_order(len(spec.betas), world))
+    # same schedule as launcher.run_ensemble: every rank gets 64 replicas of every beta, longest-running first
+    spec = la.permute_spec(spec, la.schedule_order(spec, world))
     ens = la.DeviceEnsemble(spec, lo, hi)
     for _ in range(max(3, args.warmup)):
         ens.step()

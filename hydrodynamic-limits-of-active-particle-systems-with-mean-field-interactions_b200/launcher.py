@@ -71,6 +71,48 @@ def balanced_order(n_items: int, world: int) -> np.ndarray:
     return np.concatenate([np.arange(r, n_items, world) for r in range(world)]) if world > 1 else np.arange(n_items)
 
 
+def replica_cost(spec: "EnsembleSpec") -> np.ndarray:
+    """Relative cost estimate of every replica: its total event rate in the initial state,
+    n (2D + lambda f_plus) + n_plus exp(-beta m0) + n_minus exp(+beta m0) with m0 the initial magnetisation (the rates
+    of CLASS.py:276-319,59-60 without the exclusion factors).  Only the ORDER matters: it drives longest-first scheduling."""
+    ps = spec.ps_kwargs
+    L, K = int(ps["L"]), int(ps.get("site_capacity", 1))
+    D, lam = float(ps["rate_diffusion"]), float(ps["rate_active"])
+    if ps.get("scale_rates", True):
+        dx = float(ps.get("xlim", 1.0)) / L
+        D, lam = D / dx ** 2, lam / dx
+    R = len(spec.betas)
+    if ps.get("init", "fixed") == "poisson" and spec.profiles_plus is not None:
+        rp, rm = np.asarray(spec.profiles_plus, float), np.asarray(spec.profiles_minus, float)
+        tot = rp + rm
+        occ = np.minimum(float(K), tot) if K > 1 else 1.0 - np.exp(-tot)            # expected particles per site (K = 1 exact)
+        frac = np.divide(rp, tot, out=np.full_like(tot, 0.5), where=tot > 0)
+        n_plus_p, n_minus_p = (occ * frac).sum(axis=1), (occ * (1.0 - frac)).sum(axis=1)
+        which = np.asarray(spec.profile_of, int) if spec.profile_of is not None else np.zeros(R, int)
+        n_plus, n_minus = n_plus_p[which], n_minus_p[which]
+    else:
+        n = np.asarray(spec.N_of, float) if spec.N_of is not None else np.full(R, float(ps.get("N", 1000)))
+        n_plus = n_minus = 0.5 * n
+    n = n_plus + n_minus
+    m0 = np.divide(n_plus - n_minus, n, out=np.zeros(R), where=n > 0)
+    b = np.asarray(spec.betas, float)
+    return n * 2.0 * D + lam * n_plus + n_plus * np.exp(-b * m0) + n_minus * np.exp(b * m0)
+
+
+def schedule_order(spec: "EnsembleSpec", world: int) -> np.ndarray:
+    """Replica order for a launch over `world` ranks: strided rank assignment (balanced_order), then longest-first inside
+    every rank's block — the replicas of a block fill the GPU in about two waves of CTAs, and starting the expensive
+    ones first shortens the tail of the last wave."""
+    n_items = len(spec.betas)
+    order = balanced_order(n_items, world)
+    cost = replica_cost(spec)
+    for r in range(world):
+        lo, hi = shard_bounds(n_items, r, world)
+        blk = order[lo:hi]
+        order[lo:hi] = blk[np.argsort(-cost[blk], kind="stable")]
+    return order
+
+
 def permute_spec(spec: "EnsembleSpec", order: np.ndarray) -> "EnsembleSpec":
     """The same ensemble with its per-replica arrays reordered (seeds travel with their replica, so results do not change)."""
     from dataclasses import replace
@@ -225,8 +267,8 @@ def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_c
     rank, world = dist_info()
     Rtot = len(spec.betas)
     lo, hi = shard_bounds(Rtot, rank, world)
-    order = balanced_order(Rtot, world)            # rank r runs replicas r, r+world, ... (equal mix of sweep points)
-    ens = (ensemble_cls or DeviceEnsemble)(permute_spec(spec, order) if world > 1 else spec, lo, hi, device=device)
+    order = schedule_order(spec, world)            # rank r runs replicas r, r+world, ... (equal mix of sweep points), longest first
+    ens = (ensemble_cls or DeviceEnsemble)(permute_spec(spec, order), lo, hi, device=device)
     ens.step(want_profiles=want_profiles)
     scal = ens.pack_scalars()
     prof = ens.prof
@@ -242,10 +284,10 @@ def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_c
             a, b = shard_bounds(Rtot, r, world)
             parts.append(gathered[r][: b - a])
         scal = torch.cat(parts, dim=0)
-        scal = torch.empty_like(scal).index_copy_(0, torch.as_tensor(order, device=scal.device), scal)   # original replica order
         if prof is not None:
             torch.distributed.all_reduce(prof, op=torch.distributed.ReduceOp.SUM)
-    scal_h = scal.cpu().numpy()
+    scal_h = np.empty(tuple(scal.shape), dtype=np.float64)
+    scal_h[order] = scal.cpu().numpy()             # back to the caller's replica order
     prof_h = prof.cpu().numpy() if prof is not None else None
     reps = np.bincount(np.asarray(spec.point_of, dtype=np.int64)) if len(spec.point_of) else None
     info = dict(rank=rank, world=world, shard=(lo, hi), n_max=ens.n_max, h2d_bytes=ens.h2d_bytes,

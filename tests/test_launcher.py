@@ -267,3 +267,24 @@ def test_sweep_over_sigmas_and_raw_structure_series(tmp_path):
     from aps_b200 import structure as st
     lk = st.lowk_variance_time(torch.from_numpy(raw[0]["out"]["fft_amp_list"])[None], k_cut=10)
     assert lk.shape == (1, 16) and float(lk[0, 8:].mean()) > 0
+
+
+def test_schedule_order_is_longest_first_inside_balanced_blocks():
+    """schedule_order = strided rank assignment, then descending replica_cost inside every rank's block; results are
+    returned in the caller's order (covered by test_world2_gloo_equals_single_process)."""
+    ik = init_kwargs()
+    spec = la.build_beta_sweep_spec(np.linspace(0, 3, 7), 6, PS, ik, RUN)
+    cost = la.replica_cost(spec)
+    assert cost.shape == (42,) and (cost > 0).all()
+    by_beta = cost.reshape(7, 6)[:, 0]
+    assert by_beta[-1] > by_beta[0] and by_beta.argmin() not in (0, 6)      # frac_plus = 0.75: minimum at exp(beta) = 3
+    for world in (1, 3):
+        order = la.schedule_order(spec, world)
+        assert sorted(order.tolist()) == list(range(42))
+        for r in range(world):
+            lo, hi = la.shard_bounds(42, r, world)
+            assert sorted(order[lo:hi].tolist()) == list(range(r, 42, world))
+            assert (np.diff(cost[order[lo:hi]]) <= 1e-12).all()
+    fixed = la.build_beta_sweep_spec([0.0, 2.0], 3, dict(PS, init="fixed", N=20), {}, RUN)
+    assert np.allclose(la.replica_cost(fixed), la.replica_cost(fixed)[0])     # m0 = 0: no beta dependence, order untouched
+    assert np.array_equal(la.schedule_order(fixed, 1), np.arange(6))
