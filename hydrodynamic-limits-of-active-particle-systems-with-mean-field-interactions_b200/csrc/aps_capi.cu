@@ -323,7 +323,7 @@ int aps_reduce_runs_device(const aps_reduce_args* a, void* stream) {
         return fail(APS_ERR_INVALID, "aps_reduce_runs: missing argument");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
     if (a->n_replicas == 0) return APS_OK;
-    size_t smem = ((size_t)3 * a->M + 32) * 8;
+    size_t smem = ((size_t)3 * a->M + 32 + 64) * 8;     // row scalars, reduction scratch, density table
     if (smem > 200 * 1024) return fail(APS_ERR_CAPACITY, "too many observation rows for the reducer");
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     aps::reduce_kernel<<<a->n_replicas, 128, smem, (cudaStream_t)stream>>>(*a);

@@ -106,20 +106,39 @@ __global__ void reduce_kernel(aps_reduce_args a) {
     const double dxg = L > 1 ? APS_SUB(xgrid(1, L, step), xgrid(0, L, step)) : 0.0;
     const double denom = APS_MUL((double)(n > 1 ? n : 1), a.dx);
 
+    // density of a site holding c particles of one species: c / (max(1,n)*dx) (CLASS.py:208-213), tabulated once
+    double* dtab = scr + 32;        // [64]
+    for (int c = tid; c < 64; c += NT) dtab[c] = APS_DIV((double)c, denom);
+    __syncthreads();
+    auto dens = [&](int c) { return (unsigned)c < 64u ? dtab[c] : APS_DIV((double)c, denom); };
+    const bool vec = (L % 4) == 0;  // rows start 4-byte aligned: four sites per load
     // ---- per-row sums over the lattice (rows never reached are all-zero in the reference) ----
     for (int m = wid; m < M; m += NW) {
         double sx = 0.0, st = 0.0, sb = 0.0;
         if (m < nobs) {
             const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
             const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
-            for (int l = lane; l < L; l += 32) {
-                const int p = cp[l], q = cm[l];
-                if (p | q) {
-                    double d = APS_ADD(APS_DIV((double)p, denom), APS_DIV((double)q, denom));
-                    double x = xgrid(l, L, step);
-                    st += d; sx += d * x;
-                    if (x >= a.boundary_xmin) sb += d;
+            auto site = [&](int l, int p, int q) {
+                double d = APS_ADD(dens(p), dens(q));
+                double x = xgrid(l, L, step);
+                st += d; sx += d * x;
+                if (x >= a.boundary_xmin) sb += d;
+            };
+            if (vec) {
+                const uint32_t* cp4 = reinterpret_cast<const uint32_t*>(cp);
+                const uint32_t* cm4 = reinterpret_cast<const uint32_t*>(cm);
+                for (int w = lane; w < L / 4; w += 32) {
+                    const uint32_t pw = cp4[w], qw = cm4[w];
+                    if (pw | qw) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int pj = (pw >> (8 * j)) & 0xff, qj = (qw >> (8 * j)) & 0xff;
+                            if (pj | qj) site(4 * w + j, pj, qj);
+                        }
+                    }
                 }
+            } else {
+                for (int l = lane; l < L; l += 32) { const int pj = cp[l], qj = cm[l]; if (pj | qj) site(l, pj, qj); }
             }
         }
         st = warp_sum(st); sx = warp_sum(sx); sb = warp_sum(sb);
@@ -176,24 +195,47 @@ __global__ void reduce_kernel(aps_reduce_args a) {
         const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
         int jmax = -1;
         double att = 0.0, blk = 0.0;
-        for (int l = lane; l < L; l += 32) {
-            const int p = cp[l], q = cm[l];
-            if ((p + q) > 0 && l > jmax) jmax = l;
-            if (p > 0 && l + 1 < L) {
-                double rp = APS_DIV((double)p, denom);
+        auto site2 = [&](int l, int pj, int qj, int pn, int qn) {      // pn, qn: counts of the right neighbour
+            if ((pj + qj) > 0 && l > jmax) jmax = l;
+            if (pj > 0 && l + 1 < L) {
+                double rp = dens(pj);
                 att += rp;
-                double tn = APS_ADD(APS_DIV((double)cp[l + 1], denom), APS_DIV((double)cm[l + 1], denom));
-                if (tn >= 1.0) blk += rp;
+                if (APS_ADD(dens(pn), dens(qn)) >= 1.0) blk += rp;
+            }
+        };
+        if (vec) {
+            const uint32_t* cp4 = reinterpret_cast<const uint32_t*>(cp);
+            const uint32_t* cm4 = reinterpret_cast<const uint32_t*>(cm);
+            for (int w = lane; w < L / 4; w += 32) {
+                const uint32_t pw = cp4[w], qw = cm4[w];
+                if (pw | qw) {
+                    const int l0 = 4 * w;
+                    const int pnext = l0 + 4 < L ? cp[l0 + 4] : 0, qnext = l0 + 4 < L ? cm[l0 + 4] : 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int pj = (pw >> (8 * j)) & 0xff, qj = (qw >> (8 * j)) & 0xff;
+                        const int pn = j < 3 ? (int)((pw >> (8 * j + 8)) & 0xff) : pnext, qn = j < 3 ? (int)((qw >> (8 * j + 8)) & 0xff) : qnext;
+                        if (pj | qj) site2(l0 + j, pj, qj, pn, qn);
+                    }
+                }
+            }
+        } else {
+            for (int l = lane; l < L; l += 32) {
+                const int pj = cp[l], qj = cm[l];
+                if (pj | qj) site2(l, pj, qj, l + 1 < L ? cp[l + 1] : 0, l + 1 < L ? cm[l + 1] : 0);
             }
         }
         for (int o = 16; o > 0; o >>= 1) { int v = __shfl_xor_sync(0xffffffffu, jmax, o); jmax = v > jmax ? v : jmax; }
         attempts += warp_sum(att); blocked += warp_sum(blk);
         if (jmax >= 0) {
             const double xmax = xgrid(jmax, L, step), lo = xmax - a.window_fraction;
+            // only the sites of the front window can pass the test below: start two grid points left of lo
+            int lfirst = step > 0.0 ? (int)(lo / step) - 2 : 0;
+            if (lfirst < 0) lfirst = 0;
             double s2 = 0.0;
-            for (int l = lane; l <= jmax; l += 32) {
+            for (int l = lfirst + lane; l <= jmax; l += 32) {
                 double x = xgrid(l, L, step);
-                if (x >= lo && x <= xmax) s2 += APS_ADD(APS_DIV((double)cp[l], denom), APS_DIV((double)cm[l], denom));
+                if (x >= lo && x <= xmax) s2 += APS_ADD(dens(cp[l]), dens(cm[l]));
             }
             s2 = warp_sum(s2);
             rsum += s2 * dxg / a.window_fraction; rcnt += 1.0;
