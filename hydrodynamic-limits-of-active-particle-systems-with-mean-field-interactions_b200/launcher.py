@@ -47,6 +47,8 @@ def make_exp_gradient(L, N, frac_plus, decay_length, anchor_positions=(0.25, 0.6
     def rho0_minus(x):
         return float(rho_minus[int(np.clip(np.round(x * L), 0, L - 1))])
 
+    # the tabulated profile travels with the callable, so a sweep does not have to call it L times from Python
+    rho0_plus.grid, rho0_minus.grid = (L, rho_plus), (L, rho_minus)
     return [rho0_plus, rho0_minus, rho_plus, rho_minus]
 
 
@@ -303,9 +305,13 @@ def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_c
 # ---- reference-shaped entry points -------------------------------------------------------------
 def _profiles_from_init_kwargs(ps_kwargs, init_kwargs):
     L = int(ps_kwargs["L"])
-    rp = np.array([init_kwargs["rho0_plus"](i / L) for i in range(L)], dtype=float)     # CLASS.py:71-72
-    rm = np.array([init_kwargs["rho0_minus"](i / L) for i in range(L)], dtype=float)
-    return rp, rm
+    def tabulate(fn):                                                                    # CLASS.py:71-72: fn(i / L), i = 0..L-1
+        grid = getattr(fn, "grid", None)
+        if grid is not None and grid[0] == L:      # a make_exp_gradient callable: same values, evaluated vectorised
+            idx = np.clip(np.round((np.arange(L) / L) * L), 0, L - 1).astype(int)
+            return np.asarray(grid[1], dtype=float)[idx]
+        return np.array([fn(i / L) for i in range(L)], dtype=float)
+    return tabulate(init_kwargs["rho0_plus"]), tabulate(init_kwargs["rho0_minus"])
 
 
 def _mean_std_se(x):
@@ -341,10 +347,10 @@ def sweep_over_betas(beta_values, n_runs_per_beta=10, ps_kwargs=None, init_kwarg
     # key names of the reference's pre_dict / save_dict (sweep_beta.py:952-970,1002-1026)
     for stem, col in [("", capi.APS_RED_V_EFF), ("D_", capi.APS_RED_D_EFF), ("m_", capi.APS_RED_M_MEAN),
                       ("rho_", capi.APS_RED_RHO_EFF), ("block_", capi.APS_RED_BLOCK)]:
-        stats = [_mean_std_se(red[b, :, col]) for b in range(nb)]
-        out[stem + "means"] = np.array([s[0] for s in stats])
-        out[stem + "stds"] = np.array([s[1] for s in stats])
-        out[stem + "ses"] = np.array([s[2] for s in stats])
+        x = red[:, :, col]                                   # [beta][run]; same statistics as _mean_std_se per row
+        out[stem + "means"] = x.mean(axis=1)
+        out[stem + "stds"] = x.std(axis=1, ddof=1) if n_runs_per_beta > 1 else np.zeros(nb)
+        out[stem + "ses"] = out[stem + "stds"] / np.sqrt(max(1, n_runs_per_beta))
     out["ps_kwargs"] = dict(ps_kwargs or {})
     out["outs"] = []          # per-run dicts stay on the device; the reducers above replace them
     out["n_events"] = res.n_events.reshape(nb, n_runs_per_beta)

@@ -22,3 +22,12 @@ for it in range(3):
     names=["spec","order","ensemble alloc+h2d","init","K1","reduce","profile_sums","index_add","d2h","free"]
     print(it, {n: round(1e3*(b-a),2) for n,a,b in zip(names,t[:-1],t[1:])})
 t0=time.perf_counter(); out=la.sweep_over_betas(betas, B.REPS_PER_BETA, B.PS_KWARGS, ik, run_kwargs, base_seed=7); sync(); print("sweep_over_betas total ms", 1e3*(time.perf_counter()-t0))
+import cProfile, pstats
+run_kwargs = dict(B.RUN_KWARGS, T=20.0)
+la.sweep_over_betas(betas, B.REPS_PER_BETA, B.PS_KWARGS, ik, run_kwargs, base_seed=8); sync()
+pr = cProfile.Profile(); pr.enable()
+t0 = time.perf_counter()
+for i in range(3):
+    la.sweep_over_betas(betas, B.REPS_PER_BETA, B.PS_KWARGS, ik, run_kwargs, base_seed=9 + i)
+sync(); print("T=20 sweep_over_betas ms per call", 1e3 * (time.perf_counter() - t0) / 3)
+pr.disable(); pstats.Stats(pr).sort_stats("tottime").print_stats(14)
