@@ -11,6 +11,9 @@ from aps_b200 import launcher as la
 from aps_b200.sublattice import SublatticeLattice, TILE
 
 rank, world = la.init_distributed_from_env()
+if world < 2:
+    print("multi_gpu_check: run under torchrun with at least 2 ranks (one per GPU); nothing to check with one rank")
+    sys.exit(0)
 PS = dict(L=200, xlim=1, rate_diffusion=0.1, rate_active=4, flip_rate_fn=None, init="poisson", N=110, scale_rates=False,
           local_kernel_sigma=0.02, periodic=False, anchor_positions=None, site_capacity=1, crowding_suppresses_rates=False)
 RUN = dict(T=4.0, obs_dt=0.1)
