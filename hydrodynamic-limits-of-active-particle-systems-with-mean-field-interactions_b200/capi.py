@@ -168,7 +168,7 @@ SYMBOLS = {
     "aps_reduce_runs_device": (C.c_int, [_P(ApsReduceArgs), C.c_void_p]),
     "aps_profile_sums_device": (C.c_int, [_P(ApsProfileArgs), C.c_void_p]),
     "aps_k2_rates_init": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double, _P(ApsK2Rates)]),
-    "aps_k2_flip_table": (C.c_int, [C.c_double, C.c_void_p]),
+    "aps_k2_flip_table": (C.c_int, [_P(ApsK2Rates), C.c_void_p]),
     "aps_k2_pass_device": (C.c_int, [_P(ApsK2Args), C.c_void_p]),
     "aps_k2_run_device": (C.c_int, [_P(ApsK2Args), C.c_int, C.c_void_p]),
     "aps_k2_init_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_void_p]),
@@ -206,7 +206,7 @@ def load(path: str | None = None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.aps_abi_version() != 2:
+    if lib.aps_abi_version() != 3:
         raise ApsError("libaps_b200.so ABI version mismatch")
     if path is None:
         _lib = lib

@@ -359,12 +359,12 @@ static size_t k2_smem(int radius, int cap) {
            (radius >= 0 ? aps::k2_scratch_bytes(radius, cap) + 16 : 0);
 }
 
-int aps_k2_flip_table(double beta, uint32_t* out) {
-    if (!out) return fail(APS_ERR_INVALID, "aps_k2_flip_table: null output");
-    const double cmax = aps_exp(beta < 0 ? -beta : beta), inv = 1.0 / cmax;
+int aps_k2_flip_table(const aps_k2_rates* r, uint32_t* out) {
+    if (!r || !out) return fail(APS_ERR_INVALID, "aps_k2_flip_table: null argument");
     for (int sgi = 0; sgi < 2; ++sgi)
         for (int i = 0; i <= 2 * APS_K2_MQ; ++i)
-            out[sgi * (2 * APS_K2_MQ + 1) + i] = aps_k2_flip_thr(beta, sgi == 0 ? 1 : -1, (double)(i - APS_K2_MQ) / (double)APS_K2_MQ, inv);
+            out[sgi * (2 * APS_K2_MQ + 1) + i] = aps_k2_flip_thr(r->beta, sgi == 0 ? 1 : -1, (double)(i - APS_K2_MQ) / (double)APS_K2_MQ,
+                                                                 r->inv_cmax, r->t_active);
     return APS_OK;
 }
 

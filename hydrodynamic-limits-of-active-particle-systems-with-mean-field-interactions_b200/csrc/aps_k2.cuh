@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (!LOCAL) {
             const double m = APS_DIV((double)(*a.msum_in), (double)a.n_particles);
-            thr_glob[0] = aps_k2_flip_thr(a.rates.beta, +1, m, a.rates.inv_cmax);
-            thr_glob[1] = aps_k2_flip_thr(a.rates.beta, -1, m, a.rates.inv_cmax);
+            thr_glob[0] = aps_k2_flip_thr(a.rates.beta, +1, m, a.rates.inv_cmax, a.rates.t_active);
+            thr_glob[1] = aps_k2_flip_thr(a.rates.beta, -1, m, a.rates.inv_cmax, a.rates.t_active);
         }
     }
     if (LOCAL && packed) {
@@ -239,15 +239,18 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         };
         auto category = [&](uint32_t slot) { return slot < t_left ? 0 : (slot < t_right ? 1 : (slot < t_active ? 2 : 3)); };
 
+        // trial word tr of this segment (one word per trial: call 0 holds the count and trials 0..2, later calls four each);
+        // `w4` is advanced when tr enters a new call, so trials must be visited in order
+        auto trial_word = [&](int tr) {
+            if (tr >= 3 && ((tr - 3) & 3) == 0) w4 = aps_philox4x32_10(c0, c1, aps_k2_trial_call(tr), chi, k0, k1);
+            const int wsel = aps_k2_trial_word(tr);
+            return wsel == 0 ? w4.v[0] : (wsel == 1 ? w4.v[1] : (wsel == 2 ? w4.v[2] : w4.v[3]));
+        };
         if (!LOCAL) {
             for (int tr = 0; tr < ntr; ++tr) {
-                uint32_t wa, wb;
-                if (tr == 0) { wa = w4.v[2]; wb = w4.v[3]; }
-                else {
-                    if (tr & 1) w4 = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
-                    wa = (tr & 1) ? w4.v[0] : w4.v[2]; wb = (tr & 1) ? w4.v[1] : w4.v[3];
-                }
-                hop_or_flip((int)(wa >> 27), category(wa << 5), [&](unsigned char v) { return wb < thr_glob[v == APS_K2_PLUS ? 0 : 1]; });
+                const uint32_t wa = trial_word(tr), slot = wa << 5;
+                hop_or_flip((int)(wa >> 27), category(slot),
+                            [&](unsigned char v) { return slot - t_active < thr_glob[v == APS_K2_PLUS ? 0 : 1]; });
             }
         } else {
             const int lane = tid & 31;
@@ -265,14 +268,8 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             int nl = 0;                                                    // warp-uniform length of the candidate list
             for (int tr = 0; tr < it_max; ++tr) {
                 const bool live = tr < tmax;
-                uint32_t wa = 0, wb = 0;
-                if (live) {
-                    if (tr == 0) { wa = w4.v[2]; wb = w4.v[3]; }
-                    else {
-                        if (tr & 1) w4 = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
-                        wa = (tr & 1) ? w4.v[0] : w4.v[2]; wb = (tr & 1) ? w4.v[1] : w4.v[3];
-                    }
-                }
+                const uint32_t wa = live ? trial_word(tr) : 0u;
+                const uint32_t wb = (wa << 5) - t_active;                  // position inside the flip slot (flip trials only)
                 const int x = (int)(wa >> 27), cat = category(wa << 5), slot = tr * 32 + lane;
                 const bool cand = live && cat == 3;
                 const unsigned mask = __ballot_sync(0xffffffffu, cand);
@@ -296,8 +293,10 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             // trials beyond the stash capacity (rare): acceptance bits into two register masks, still before the barrier
             unsigned long long ov_p = 0ULL, ov_m = 0ULL;
             for (int tr = cap; tr < ntr; ++tr) {
-                const aps_u32x4 wq = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
-                const uint32_t wa = (tr & 1) ? wq.v[0] : wq.v[2], wb = (tr & 1) ? wq.v[1] : wq.v[3];
+                const aps_u32x4 wq = aps_philox4x32_10(c0, c1, aps_k2_trial_call(tr), chi, k0, k1);
+                const int wsel = aps_k2_trial_word(tr);
+                const uint32_t wa = wsel == 0 ? wq.v[0] : (wsel == 1 ? wq.v[1] : (wsel == 2 ? wq.v[2] : wq.v[3]));
+                const uint32_t wb = (wa << 5) - t_active;
                 if (category(wa << 5) == 3) {
                     uint32_t thr_p, thr_m;
                     field_thresholds(cbase + (int)(wa >> 27), thr_p, thr_m);
@@ -313,8 +312,9 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
                     hop_or_flip((int)(code & 31u), (int)((code >> 5) & 3u),
                                 [&](unsigned char v) { return (code >> (v == APS_K2_PLUS ? 7 : 8)) & 1u; });
                 } else {
-                    const aps_u32x4 wq = aps_philox4x32_10(c0, c1, (uint32_t)((tr + 1) >> 1), chi, k0, k1);
-                    const uint32_t wa = (tr & 1) ? wq.v[0] : wq.v[2];
+                    const aps_u32x4 wq = aps_philox4x32_10(c0, c1, aps_k2_trial_call(tr), chi, k0, k1);
+                    const int wsel = aps_k2_trial_word(tr);
+                    const uint32_t wa = wsel == 0 ? wq.v[0] : (wsel == 1 ? wq.v[1] : (wsel == 2 ? wq.v[2] : wq.v[3]));
                     hop_or_flip((int)(wa >> 27), category(wa << 5),
                                 [&](unsigned char v) { return ((v == APS_K2_PLUS ? ov_p : ov_m) >> (tr - cap)) & 1ULL; });
                 }

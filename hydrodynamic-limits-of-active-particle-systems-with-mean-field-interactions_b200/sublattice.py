@@ -55,9 +55,9 @@ class CudaK2Backend:
         capi.check(self.lib.aps_k2_rates_init(D, lam, beta, dt, r), "aps_k2_rates_init")
         return r
 
-    def flip_table(self, beta):
+    def flip_table(self, rates):
         t = np.zeros(2 * 1025, np.uint32)
-        capi.check(self.lib.aps_k2_flip_table(beta, t.ctypes.data), "aps_k2_flip_table")
+        capi.check(self.lib.aps_k2_flip_table(rates, t.ctypes.data), "aps_k2_flip_table")
         return torch.from_numpy(t.view(np.int32).copy()).to(self.dev)
 
     def run(self, args, n_passes):
@@ -103,8 +103,8 @@ class SublatticeLattice:
         else:
             self.radius, w = fixed_point_taps(sigma_sites)
             self.w16 = self.be.from_numpy(w)
-        self.flip_tab = self.be.flip_table(float(beta)) if self.radius >= 0 else None
         self.rates = self.be.rates(float(D), float(lam), float(beta), float(dt))
+        self.flip_tab = self.be.flip_table(self.rates) if self.radius >= 0 else None
         self.buf = [self.be.zeros_u8(self.L), self.be.zeros_u8(self.L)]
         self.cur = 0
         self.msum = [self.be.zeros_i64(1), self.be.zeros_i64(1)]

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APS_ABI_VERSION 2
+#define APS_ABI_VERSION 3
 
 typedef enum aps_status {
     APS_OK = 0,
@@ -277,7 +277,7 @@ typedef struct aps_k2_args {
 /* thresholds / Poisson table for (D, lambda, beta, dt); returns non-zero if B*32*dt is out of (0, 24] */
 int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates* out);
 /* local-field acceptance thresholds: out[s][i] for sigma = +1 (s=0) / -1 (s=1) and m = (i-512)/512; host buffer of 2*1025 */
-int aps_k2_flip_table(double beta, uint32_t* out);
+int aps_k2_flip_table(const aps_k2_rates* rates, uint32_t* out);   /* needs the rate thresholds: acceptance is read off the flip slot */
 /* one pass (in -> out) */
 int aps_k2_pass_device(const aps_k2_args* a, void* stream);
 /* n_passes passes ping-ponging between a->in and a->out (a->pass, in/out and msum are advanced in the

@@ -19,10 +19,12 @@
  *   - every decision is an integer comparison of a 32-bit Philox word with a precomputed threshold;
  *   - two passes (q = 0, 1) advance every particle by dt.
  * Site encoding (one byte per site): 0 empty, 1 = '+', 2 = '-'.
- * Random numbers: Philox4x32-10, key = seed, counter = (segment, pass, call, APS_RNG_SUBLATTICE):
- * call 0 -> word 0: Poisson trial count, words 2,3: trial 0; call c >= 1 -> words (0,1): trial 2c-1,
- * words (2,3): trial 2c.  In a trial the first word gives site (top 5 bits) and rate slot, the second
- * the flip acceptance.
+ * Random numbers: Philox4x32-10, key = seed, counter = (segment, pass, call, APS_RNG_SUBLATTICE).  ONE 32-bit word per
+ * trial: call 0 -> word 0: Poisson trial count, words 1..3: trials 0..2; call c >= 1 -> words 0..3: trials 4c-1 .. 4c+2.
+ * In a trial word the top 5 bits give the site, the remaining 27 bits (shifted up) the rate slot; a flip trial is
+ * accepted iff its position inside the flip slot, slot - t_active in [0, 2^32 - t_active), is below
+ * exp(-beta*sigma*m)/exp(|beta|) * (2^32 - t_active)  — the same uniform variate decides slot and acceptance, which is
+ * exact (conditional on landing in the flip slot the position is uniform there) and halves the Philox work per trial.
  */
 #ifndef APS_K2_MODEL_H
 #define APS_K2_MODEL_H
@@ -48,12 +50,15 @@ typedef struct aps_k2_rates {
     uint32_t cdf32[APS_K2_MAX_TRIALS];  /* floor(2^32 * Poisson(mu) cdf): n = #{k : w >= cdf32[k]}   */
 } aps_k2_rates;
 
-/* 32-bit acceptance threshold of a flip with rate c = exp(-beta*sigma*m): accept iff word < thr */
-APS_HD uint32_t aps_k2_flip_thr(double beta, int sigma, double m, double inv_cmax) {
+/* acceptance threshold of a flip with rate c = exp(-beta*sigma*m): accept iff (slot - t_active) < thr */
+APS_HD uint32_t aps_k2_flip_thr(double beta, int sigma, double m, double inv_cmax, uint32_t t_active) {
     double c = aps_exp(APS_MUL(APS_MUL(-beta, (double)sigma), m));
-    double v = APS_MUL(APS_MUL(c, inv_cmax), 4294967296.0);
+    double v = APS_MUL(APS_MUL(c, inv_cmax), APS_SUB(4294967296.0, (double)t_active));
     return v >= 4294967295.0 ? 4294967295u : (uint32_t)v;
 }
+/* Philox call and word (0..3) that hold trial `tr` of a segment */
+APS_HD uint32_t aps_k2_trial_call(int tr) { return tr < 3 ? 0u : 1u + (uint32_t)((tr - 3) >> 2); }
+APS_HD int aps_k2_trial_word(int tr) { return tr < 3 ? tr + 1 : ((tr - 3) & 3); }
 /* quantised local field index in [0, 2*MQ]: round(MQ * sw / tw) + MQ (half away from zero), integer only */
 APS_HD int aps_k2_mq_index(int sw, int tw) {
     if (tw <= 0) return APS_K2_MQ;

@@ -470,8 +470,8 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
     uint32_t thr_glob[2] = {0, 0};
     if (r < 0) {
         const double m = (double)(*a->msum_in) / (double)a->n_particles;
-        thr_glob[0] = aps_k2_flip_thr(a->rates.beta, +1, m, a->rates.inv_cmax);
-        thr_glob[1] = aps_k2_flip_thr(a->rates.beta, -1, m, a->rates.inv_cmax);
+        thr_glob[0] = aps_k2_flip_thr(a->rates.beta, +1, m, a->rates.inv_cmax, a->rates.t_active);
+        thr_glob[1] = aps_k2_flip_thr(a->rates.beta, -1, m, a->rates.inv_cmax, a->rates.t_active);
     }
     for (long long seg = 0; seg * APS_K2_SEG < L; ++seg) {
         const long long abase = seg * APS_K2_SEG + q * APS_K2_HALF;
@@ -483,11 +483,11 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
         int ntr = 0;
         while (ntr < (int)a->rates.n_cdf && w4.v[0] >= a->rates.cdf32[ntr]) ++ntr;
         for (int t = 0; t < ntr; ++t) {
-            uint32_t wa, wb;
-            if (t == 0) { wa = w4.v[2]; wb = w4.v[3]; }
+            uint32_t wa;                                                  /* one word per trial (aps_k2_model.h) */
+            if (t < 3) wa = w4.v[t + 1];
             else {
-                aps_u32x4 c4 = aps_philox4x32_10(c0, c1, (uint32_t)((t + 1) >> 1), chi, k0, k1);
-                wa = (t & 1) ? c4.v[0] : c4.v[2]; wb = (t & 1) ? c4.v[1] : c4.v[3];
+                aps_u32x4 c4 = aps_philox4x32_10(c0, c1, aps_k2_trial_call(t), chi, k0, k1);
+                wa = c4.v[aps_k2_trial_word(t)];
             }
             const long long x = abase + (long long)(wa >> 27);
             const uint32_t slot = wa << 5;
@@ -510,7 +510,7 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
                     }
                     thr = a->flip_tab[(sg == 1 ? 0 : (2 * APS_K2_MQ + 1)) + aps_k2_mq_index(sw, tw)];
                 } else thr = thr_glob[sg == 1 ? 0 : 1];
-                if (wb < thr) { out[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
+                if (slot - a->rates.t_active < thr) { out[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
             }
         }
     }
@@ -533,11 +533,11 @@ int aps_oracle_k2_rates(double D, double lam, double beta, double dt, aps_k2_rat
     return aps_k2_make_rates(D, lam, beta, dt, out);
 }
 
-void aps_oracle_k2_flip_table(double beta, uint32_t* out) {
-    const double cmax = aps_exp(beta < 0 ? -beta : beta), inv = 1.0 / cmax;
+void aps_oracle_k2_flip_table(const aps_k2_rates* r, uint32_t* out) {
     for (int sgi = 0; sgi < 2; ++sgi)
         for (int i = 0; i <= 2 * APS_K2_MQ; ++i)
-            out[sgi * (2 * APS_K2_MQ + 1) + i] = aps_k2_flip_thr(beta, sgi == 0 ? 1 : -1, (double)(i - APS_K2_MQ) / (double)APS_K2_MQ, inv);
+            out[sgi * (2 * APS_K2_MQ + 1) + i] = aps_k2_flip_thr(r->beta, sgi == 0 ? 1 : -1, (double)(i - APS_K2_MQ) / (double)APS_K2_MQ,
+                                                                 r->inv_cmax, r->t_active);
 }
 
 void aps_oracle_k2_init(uint8_t* state, int64_t L, int64_t global_offset, uint64_t seed, double density, double frac_plus) {

@@ -52,7 +52,7 @@ def load():
         lib.aps_oracle_philox_log.restype = C.c_int64
         lib.aps_oracle_philox_log.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
         lib.aps_oracle_k2_flip_table.restype = None
-        lib.aps_oracle_k2_flip_table.argtypes = [C.c_double, C.c_void_p]
+        lib.aps_oracle_k2_flip_table.argtypes = [C.c_void_p, C.c_void_p]
         lib.aps_oracle_k2_init.restype = None
         lib.aps_oracle_k2_init.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double]
         _lib = lib

@@ -23,9 +23,10 @@ class OracleK2Backend:
         assert self.lib.aps_oracle_k2_rates(D, lam, beta, dt, r) == 0
         return r
 
-    def flip_table(self, beta):
+    def flip_table(self, rates):
+        import ctypes
         t = np.zeros(2 * 1025, np.uint32)
-        self.lib.aps_oracle_k2_flip_table(beta, t.ctypes.data)
+        self.lib.aps_oracle_k2_flip_table(ctypes.addressof(rates), t.ctypes.data)
         return torch.from_numpy(t.view(np.int32).copy())
 
     def run(self, args, n_passes):
