@@ -107,10 +107,10 @@ __global__ void reduce_kernel(aps_reduce_args a) {
     const double denom = APS_MUL((double)(n > 1 ? n : 1), a.dx);
 
     // density of a site holding c particles of one species: c / (max(1,n)*dx) (CLASS.py:208-213), tabulated once
-    double* dtab = scr + 32;        // [64]
-    for (int c = tid; c < 64; c += NT) dtab[c] = APS_DIV((double)c, denom);
+    double* dtab = scr + 32;        // [128]: the observation rows hold int8 counts, so the table covers every value
+    for (int c = tid; c < 128; c += NT) dtab[c] = APS_DIV((double)c, denom);
     __syncthreads();
-    auto dens = [&](int c) { return (unsigned)c < 64u ? dtab[c] : APS_DIV((double)c, denom); };
+    auto dens = [&](int c) { return dtab[c & 127]; };
     const bool vec = (L % 4) == 0;  // rows start 4-byte aligned: four sites per load
     // ---- per-row sums over the lattice (rows never reached are all-zero in the reference) ----
     for (int m = wid; m < M; m += NW) {
