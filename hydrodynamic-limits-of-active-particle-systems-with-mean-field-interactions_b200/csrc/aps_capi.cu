@@ -132,7 +132,7 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
         // single-warp CTAs (no block barriers) win for narrow update windows; wide windows (r > 30) use two warps
         const int fnt = g_k1_threads ? nt : (getenv("APS_K1_THREADS") ? nt : (p->radius <= 30 ? 32 : 64));
         CU(aps::launch_fast(a, philox, st, g_use_fast == 1, fnt, &launched));
-        if (launched) { g_launches.fetch_add(1); a.only_retry = 1; }   // 2nd launch: replicas violating K = 1 only
+        if (launched) { g_launches.fetch_add(launched); a.only_retry = 1; }   // last launch: replicas violating K = 1 only
     }
     switch (nt) {
         case 32: return launch_nt<32>(a, philox, smem, st);

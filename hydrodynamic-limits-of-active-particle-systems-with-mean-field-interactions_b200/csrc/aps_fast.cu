@@ -1,14 +1,16 @@
 // aps_fast.cu — instantiations and dispatch of the K = 1 specialised K1 kernel (aps_k1_fast.cuh).
 // Separate translation unit so that the two halves of the library compile in parallel.
+#include <cstdlib>
 #include <cuda_runtime.h>
 
-#include "aps_k1_fast.cuh"
+#include "aps_k1_lean.cuh"
 
 namespace aps {
 
 template <int NT, int RCAP, int NCAP, int LPCAP>
 static cudaError_t launch_nt(const K1Args& a, bool philox, cudaStream_t st) {
-    const size_t smem = k1_fast_smem_bytes(a.p.L, a.b.n_max, a.p.radius, RCAP, NCAP, LPCAP);
+    const char* extra = getenv("APS_K1_EXTRA_SMEM");   // occupancy experiments only
+    const size_t smem = k1_fast_smem_bytes(a.p.L, a.b.n_max, a.p.radius, RCAP, NCAP, LPCAP) + (extra ? (size_t)atoi(extra) : 0);
     if (philox) {
         auto k = k1_fast_kernel<NT, true, RCAP, NCAP, LPCAP>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -28,7 +30,24 @@ static cudaError_t launch_class(const K1Args& a, bool philox, cudaStream_t st) {
     return g_fast_nt == 32 ? launch_nt<32, RCAP, NCAP, LPCAP>(a, philox, st) : launch_nt<64, RCAP, NCAP, LPCAP>(a, philox, st);
 }
 
-// Returns cudaSuccess and *launched = 1 if a specialised kernel was enqueued; *launched = 0 if the
+template <int RCAP, int LPCAP>
+static cudaError_t launch_lean(const K1Args& a, bool philox, cudaStream_t st) {
+    const size_t smem = k1_lean_smem_bytes<RCAP, LPCAP>();
+    if (philox) {
+        auto k = k1_lean_kernel<true, RCAP, LPCAP>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<a.b.n_replicas, 32, smem, st>>>(a);
+    } else {
+        auto k = k1_lean_kernel<false, RCAP, LPCAP>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<a.b.n_replicas, 32, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+// Returns cudaSuccess and *launched = number of specialised kernels enqueued; *launched = 0 if the
 // configuration does not qualify (the caller then uses the generic kernel only).
 cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched) {
     *launched = 0;
@@ -37,7 +56,19 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
     if (k1_fast_smem_bytes(a.p.L, nm, a.p.radius, 0, 0, 0) > 227 * 1024) return cudaSuccess;
     *launched = 1;
     if (allow_static) {
-        if (r1 <= 21 && nm <= 512 && lp <= 1056) return launch_class<21, 512, 1056>(a, philox, st);
+        if (r1 <= 21 && nm <= 512 && lp <= 1056) {
+            if (nt == 32 && !getenv("APS_K1_NO_LEAN")) {
+                // half-size shared-memory image: all replicas of an SM resident at once; its rejects (unsorted initial
+                // positions) go through the full-size kernel in a second, otherwise empty launch
+                cudaError_t e = launch_lean<21, 1056>(a, philox, st);
+                if (e != cudaSuccess) return e;
+                *launched = 2;
+                K1Args b = a;
+                b.only_retry = 2;
+                return launch_class<21, 512, 1056>(b, philox, st);
+            }
+            return launch_class<21, 512, 1056>(a, philox, st);
+        }
         if (r1 <= 21 && nm <= 1024 && lp <= 1056) return launch_class<21, 1024, 1056>(a, philox, st);
         if (r1 <= 81 && nm <= 512 && lp <= 1184) return launch_class<81, 512, 1184>(a, philox, st);
         if (r1 <= 81 && nm <= 1024 && lp <= 1184) return launch_class<81, 1024, 1184>(a, philox, st);

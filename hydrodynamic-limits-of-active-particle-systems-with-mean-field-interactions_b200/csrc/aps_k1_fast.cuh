@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
     const int n = B.n[rep];
     const double beta = B.beta[rep], T = P.T, D = P.rate_diffusion, lam = P.rate_active;
 
+    if (A.only_retry == 2 && B.status[rep] != 101) return;   // second launch after aps_k1_lean.cuh: its rejects only
     FastFixed& F = *reinterpret_cast<FastFixed*>(smem_raw);
     unsigned char* dyn = smem_raw + ((sizeof(FastFixed) + 15) & ~(size_t)15);
     const size_t ncap = STATIC ? (size_t)NCAP : (size_t)n_max;

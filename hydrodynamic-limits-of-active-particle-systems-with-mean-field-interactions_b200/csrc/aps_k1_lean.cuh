@@ -1,0 +1,469 @@
+// aps_k1_lean.cuh — K1 for the sweep configurations with HALF the shared-memory image of aps_k1_fast.cuh.
+//
+// Why: measured on B200 (profiles/r1_k1_lean.md) one replica-warp takes ~17-19 ms for config 2 whether 3 or 14 of them
+// share an SM — the kernel is a latency chain with issue slots to spare — so throughput is (#replicas resident per SM)
+// and run time is (#waves of CTAs) x (replica latency).  The 15.5 KB image of the fast kernel gives 14 replicas per SM
+// = 2 waves for 4096 replicas; at <= 7.3 KB all 28 replicas of an SM are resident and the batch runs in ONE wave.
+// What was dropped to get there (same arithmetic, bit-identical outputs; checked against the oracle like the others):
+//   * the 3 KB product table: a tap pair is (multiplier[code_l + code_r]) * w_d with two 9-entry multiplier tables
+//     (the products equal the table entries bit for bit);
+//   * the site->particle map (2 KB): K = 1 hops cannot reorder particles, so when the initial positions are strictly
+//     increasing (device Poisson init, any sorted input) the particles inside an update window are a contiguous index
+//     range around the event particle, found with two ballots;  unsorted replicas are handed to aps_k1_fast.cuh
+//     (status APS_RUN_RETRY_FAST, second launch);
+//   * sigma / hop-flag / accumulator-slot arrays (1.5 KB): orientation is the lattice code at the particle's site,
+//     hop flags are two neighbour reads, the accumulator slot is recomputed from the index;
+//   * cached pairwise accumulators and chunk sums in shared memory: the 8 accumulators of a dirty leaf are re-summed
+//     by 8 lanes in lock-step anyway, the chunk sum of lane c lives in a register of lane c.
+// Limits: single-warp CTAs, n_max <= 512, r + 1 <= RCAP, L + 2r <= LPCAP.
+#pragma once
+#include "aps_k1_fast.cuh"
+
+namespace aps {
+
+constexpr int APS_RUN_RETRY_FAST = 101;
+constexpr int kLeanN = 512;
+constexpr int kLeanRing = 32;          // 8 events of variate look-ahead
+
+template <int RCAP>
+struct LeanFixed {
+    double ring[kLeanRing];
+    double hop_tab[8];
+    double ms[9], mt[9];               // multipliers (a_plus - a_minus), (a_plus + a_minus) of a pair code
+    double wtab[RCAP];
+    double leafsum[4];
+    double misc[4];
+    int32_t desc[16];
+    int8_t node_a[8], node_b[8], node_kind[8], node_level[8], node_leaf[8];
+    int16_t leaf_start[4], leaf_len[4];
+    uint8_t dirty_c[32];
+    uint8_t dirty_leaf[4];
+};
+
+template <int RCAP, int LPCAP>
+__host__ __device__ inline size_t k1_lean_smem_bytes() {
+    return ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15) + (size_t)kLeanN * 8 + (size_t)kLeanN * 2 + (size_t)LPCAP;
+}
+
+template <bool PHILOX, int RCAP, int LPCAP>
+__global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__ K1Args A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const aps_params& P = A.p;
+    const aps_batch& B = A.b;
+    const int rep = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int L = P.L, r = P.radius, pad = r, n_max = B.n_max, M = B.M;
+    const int n = B.n[rep];
+    const double beta = B.beta[rep], T = P.T, D = P.rate_diffusion, lam = P.rate_active;
+
+    LeanFixed<RCAP>& F = *reinterpret_cast<LeanFixed<RCAP>*>(smem_raw);
+    unsigned char* dyn = smem_raw + ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15);
+    double* const rates = reinterpret_cast<double*>(dyn); dyn += (size_t)kLeanN * 8;
+    uint16_t* const pos = reinterpret_cast<uint16_t*>(dyn); dyn += (size_t)kLeanN * 2;
+    uint8_t* const code = dyn;
+
+    // ---------------- prologue ----------------
+    for (int i = lane; i < L + 2 * pad; i += 32) code[i] = 0;
+    if (lane <= r) F.wtab[lane] = B.weights[lane];
+    if (lane < 9) { const int am = lane / 3, ap = lane - am * 3; F.ms[lane] = (double)(ap - am); F.mt[lane] = (double)(ap + am); }
+    if (lane < 16) F.desc[lane] = 0;
+    F.dirty_c[lane] = 1;
+    if (lane < 4) F.dirty_leaf[lane] = 1;
+    if (lane < 8) {
+        const double dz = APS_MUL(D, 0.0);
+        F.hop_tab[lane] = APS_ADD(APS_ADD((lane & 1) ? D : dz, (lane & 2) ? D : dz), (lane & 4) ? lam : 0.0);
+    }
+    __syncwarp();
+    int S = 0;
+    bool unsorted = false;
+    if (n > 0 && n <= kLeanN) {
+        const int32_t* gp = B.pos0 + (size_t)rep * n_max;
+        const int8_t* gs = B.sigma0 + (size_t)rep * n_max;
+        int part = 0, bad = 0;
+        for (int i = lane; i < n; i += 32) {
+            const int p = gp[i], sg = gs[i];
+            pos[i] = (uint16_t)p;
+            part += sg;
+            if (i + 1 < n && gp[i + 1] <= p) bad = 1;                 // needs strictly increasing positions (K = 1, sorted)
+            code[pad + p] = (uint8_t)(sg == 1 ? 1 : 3);               // distinct sites when sorted; garbage otherwise (we bail out)
+        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        S = part;
+        unsorted = __any_sync(0xffffffffu, bad);
+    }
+    if (unsorted || n > kLeanN || n == 0) {
+        if (lane == 0) {
+            if (n == 0) {
+                if (B.n_obs) B.n_obs[rep] = B.obs_start ? B.obs_start[rep] : 0;
+                if (B.n_events) B.n_events[rep] = B.ev_start ? B.ev_start[rep] : 0;
+                if (B.t_end) B.t_end[rep] = B.t_start ? B.t_start[rep] : 0.0;
+                if (B.n_guard) B.n_guard[rep] = 0;
+                if (B.draws_used) B.draws_used[rep] = 0;
+                if (B.n_end) B.n_end[rep] = 0;
+                if (B.n_exit && !B.ev_start) B.n_exit[rep] = 0;
+                B.status[rep] = APS_RUN_EMPTY;
+            } else B.status[rep] = APS_RUN_RETRY_FAST;
+        }
+        return;
+    }
+    __syncwarp();
+    // reflect images of the halo (sites within `pad` of a wall)
+    for (int i = lane; i < n; i += 32) {
+        const int p = pos[i];
+        const uint8_t c = code[pad + p];
+        if (p < pad) code[pad - 1 - p] = c;
+        if (p >= L - pad) code[pad + 2 * L - 1 - p] = c;
+    }
+    if (lane == 0) {
+        // numpy pairwise tree (<= 4 leaves for n <= 512), built in the still unused rates area
+        int32_t* na = reinterpret_cast<int32_t*>(rates); int32_t* nb = na + 16; int32_t* nk = nb + 16; int32_t* lv = nk + 16;
+        const int nn = build_sum_tree(n, na, nb, nk, 8);
+        int nl = 0;
+        for (int g = 0; g < nn; ++g) {
+            F.node_kind[g] = (int8_t)nk[g];
+            if (nk[g] == 0) { F.leaf_start[nl] = (int16_t)na[g]; F.leaf_len[nl] = (int16_t)nb[g]; F.node_leaf[g] = (int8_t)nl++; F.node_a[g] = 0; F.node_b[g] = 0; }
+            else { F.node_leaf[g] = -1; F.node_a[g] = (int8_t)na[g]; F.node_b[g] = (int8_t)nb[g]; }
+        }
+        lv[nn - 1] = 0;
+        int maxlev = 0;
+        for (int g = nn - 1; g >= 0; --g) if (nk[g] == 1) {
+            const int l2 = lv[g] + 1;
+            lv[na[g]] = l2; lv[nb[g]] = l2;
+            if (l2 > maxlev) maxlev = l2;
+        }
+        for (int g = 0; g < nn; ++g) F.node_level[g] = (int8_t)lv[g];
+        F.desc[D_NNODES] = nn; F.desc[12] = nl; F.desc[13] = maxlev;
+    }
+    __syncwarp();
+    const int nnodes = F.desc[D_NNODES], nleaf = F.desc[12], maxlev = F.desc[13];
+    // loop invariants of the clock in registers: node `lane` of the tree, the leaf of this lane's 8-lane group
+    const bool have_node = lane < nnodes;
+    const int nd_kind = have_node ? F.node_kind[lane] : 0, nd_lev = have_node ? F.node_level[lane] : -1;
+    const int nd_a = (have_node && nd_kind) ? F.node_a[lane] : 0, nd_b = (have_node && nd_kind) ? F.node_b[lane] : 0;
+    const int nd_leaf = (have_node && !nd_kind) ? F.node_leaf[lane] : 0;
+    const int my_g = lane >> 3;
+    const int g_start = my_g < nleaf ? F.leaf_start[my_g] : 0, g_len = my_g < nleaf ? F.leaf_len[my_g] : 0;
+    const int ls1 = nleaf > 1 ? F.leaf_start[1] : 0x7fff, ls2 = nleaf > 2 ? F.leaf_start[2] : 0x7fff, ls3 = nleaf > 3 ? F.leaf_start[3] : 0x7fff;
+    int cs_shift = 4;
+    while (((n + (1 << cs_shift) - 1) >> cs_shift) > 32) ++cs_shift;
+    const int CS = 1 << cs_shift;
+    const int nchunks = (n + CS - 1) >> cs_shift;
+    double my_cs = 0.0;                                           // cached sum of chunk `lane`
+
+    int64_t n_done = 0;
+    const int64_t ev_base = B.ev_start ? B.ev_start[rep] : 0;
+    int64_t cursor = 0, n_guard = 0, rbase = -(int64_t)kLeanRing - 8;
+    const int64_t draws_len = PHILOX ? 0 : (B.draw_off[rep + 1] - B.draw_off[rep]);
+    const double* gdraws = PHILOX ? nullptr : (B.draws + B.draw_off[rep]);
+    const uint32_t k0 = PHILOX ? (uint32_t)B.seeds[rep] : 0u, k1 = PHILOX ? (uint32_t)(B.seeds[rep] >> 32) : 0u;
+    double t = B.t_start ? B.t_start[rep] : 0.0;
+    int obs_idx = B.obs_start ? B.obs_start[rep] : 0;
+    int status = APS_RUN_DONE;
+    const int64_t max_events = B.max_events > 0 ? B.max_events : 0x7fffffffffffffffLL;
+
+    // local magnetisation at site p: scipy's symmetric tap order, products formed as multiplier * w (== the table entries)
+    auto local_m = [&](int p) {
+        const uint8_t* c = code + pad + p;
+        const double w0 = F.wtab[r];
+        double sc = APS_MUL(F.ms[c[0]], w0), tc = APS_MUL(F.mt[c[0]], w0);
+#pragma unroll 4
+        for (int jj = -r; jj < 0; ++jj) {
+            const int idx = (int)c[jj] + (int)c[-jj];
+            const double wj = F.wtab[r + jj];
+            sc = APS_ADD(sc, APS_MUL(F.ms[idx], wj));
+            tc = APS_ADD(tc, APS_MUL(F.mt[idx], wj));
+        }
+        double m = 0.0;
+        if (tc > 0.0) m = APS_DIV(sc, tc);
+        return m < -1.0 ? -1.0 : (m > 1.0 ? 1.0 : m);
+    };
+    auto write_rows = [&](int first, int count) {
+        for (int m = first; m < first + count; ++m) {
+            const size_t row = (size_t)rep * (size_t)M + (size_t)m;
+            if ((B.record & APS_REC_COUNTS) && B.obs_cp && B.obs_cm) {
+                int8_t* ocp = B.obs_cp + row * (size_t)L; int8_t* ocm = B.obs_cm + row * (size_t)L;
+                for (int l = lane; l < L; l += 32) { const uint8_t v = code[pad + l]; ocp[l] = (int8_t)(v == 1); ocm[l] = (int8_t)(v == 3); }
+            }
+            if ((B.record & APS_REC_POS) && B.obs_pos) {
+                int32_t* op = B.obs_pos + row * (size_t)n_max;
+                for (int i = lane; i < n; i += 32) op[i] = (int32_t)pos[i];
+            }
+            if (B.obs_sigma_sum && lane == 0) B.obs_sigma_sum[row] = S;
+            if (B.obs_n && lane == 0) B.obs_n[row] = n;
+            if (B.obs_bound) { int8_t* ob = B.obs_bound + row * (size_t)n_max; for (int i = lane; i < n; i += 32) ob[i] = 0; }
+        }
+    };
+    auto write_field = [&](int first, int count) {
+        if (!((B.record & APS_REC_MLOCAL) && B.obs_m_local)) return;
+        for (int l = lane; l < L; l += 32) {
+            const double m = local_m(l);
+            for (int mm = first; mm < first + count; ++mm)
+                B.obs_m_local[((size_t)rep * (size_t)M + (size_t)mm) * (size_t)L + l] = m;
+        }
+    };
+    auto hop_flags = [&](int p, int cd) {
+        const bool l_free = (p > 0) && code[pad + p - 1] == 0, r_free = (p < L - 1) && code[pad + p + 1] == 0;
+        return (l_free ? 1 : 0) | (r_free ? 2 : 0) | ((cd == 1 && r_free) ? 4 : 0);
+    };
+    // full rate of particle i (CLASS.py:351)
+    auto refresh = [&](int i) {
+        const int p = pos[i];
+        const int cd = code[pad + p];
+        const double sgd = cd == 1 ? 1.0 : -1.0;
+        const double h = F.hop_tab[hop_flags(p, cd)];
+        const double m = local_m(p);
+        rates[i] = APS_ADD(h, aps_exp(APS_MUL(APS_MUL(-beta, sgd), m)));
+        F.dirty_c[i >> cs_shift] = 1;
+        F.dirty_leaf[(i >= ls1) + (i >= ls2) + (i >= ls3)] = 1;
+    };
+    auto code_put = [&](int x, int delta) { code_add(code, L, pad, x, delta); };
+
+    for (int i = lane; i < n; i += 32) refresh(i);
+    if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
+    __syncwarp();
+    double next_obs = (obs_idx < M) ? B.times_obs[obs_idx] : 0.0;
+    const double guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
+
+    while (true) {
+        if (!(t < T)) { status = APS_RUN_DONE; break; }
+        if (n_done >= max_events) { status = APS_RUN_MAX_EVENTS; break; }
+        int avail; double e, uc, ue, ud;
+        if (PHILOX) {
+            const int slot = (int)(n_done & 7);
+            if (slot == 0) {
+                if (lane < 8) {
+                    const uint64_t ev = (uint64_t)(ev_base + n_done + lane);
+                    const aps_u32x4 a = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_A, 0u, k0, k1);
+                    const aps_u32x4 b = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_B, 0u, k0, k1);
+                    F.ring[4 * lane + 0] = -aps_log(APS_SUB(1.0, aps_u53(a.v[0], a.v[1])));
+                    F.ring[4 * lane + 1] = aps_u53(a.v[2], a.v[3]);
+                    F.ring[4 * lane + 2] = aps_u53(b.v[0], b.v[1]);
+                    F.ring[4 * lane + 3] = aps_u53(b.v[2], b.v[3]);
+                }
+                __syncwarp();
+            }
+            avail = 4;
+            e = F.ring[4 * slot]; uc = F.ring[4 * slot + 1]; ue = F.ring[4 * slot + 2]; ud = F.ring[4 * slot + 3];
+        } else {
+            if (cursor + 4 > rbase + kLeanRing) {
+                __syncwarp();
+                rbase = cursor;
+                F.ring[lane] = (rbase + lane < draws_len) ? __ldg(gdraws + rbase + lane) : 0.0;
+                __syncwarp();
+            }
+            const int64_t left = draws_len - cursor;
+            avail = left >= 4 ? 4 : (int)(left < 0 ? 0 : left);
+            if (B.spec_from >= 0 && cursor >= B.spec_from && avail > 3) avail = 3;
+            const int o = (int)(cursor - rbase);
+            e = F.ring[o]; uc = F.ring[o + 1]; ue = F.ring[o + 2]; ud = F.ring[o + 3];
+        }
+        if (avail < 3) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+        const int seq = (int)(n_done & 0x3fffffff) + 1;
+
+        auto decode_apply = [&](int sel) {
+            const int p = pos[sel];
+            const int cd = code[pad + p], sg = cd == 1 ? 1 : -1;
+            const int hf = hop_flags(p, cd);
+            const double dz = APS_MUL(D, 0.0);
+            const double rl = (hf & 1) ? D : dz, rr = (hf & 2) ? D : dz, ra = (hf & 4) ? lam : 0.0;
+            const double v = APS_MUL(ue, rates[sel]);
+            const double diff_thresh = APS_ADD(rl, rr), act_thresh = APS_ADD(diff_thresh, ra);
+            int kind, newp = p;
+            if (v < diff_thresh) {
+                if (avail < 4) { F.desc[D_STOP] = 1; F.desc[D_SEQ] = seq; return; }
+                if (ud < APS_DIV(rl, APS_ADD(rl, rr))) { kind = APS_EV_DIFF_LEFT; newp = clampi(p - 1, 0, L - 1); }
+                else { kind = APS_EV_DIFF_RIGHT; newp = clampi(p + 1, 0, L - 1); }
+            } else if (v < act_thresh) { kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, L - 1); }
+            else kind = APS_EV_FLIP;
+            if (kind == APS_EV_FLIP) code_put(p, sg == 1 ? 2 : -2);
+            else if (newp != p) { pos[sel] = (uint16_t)newp; code_put(p, -cd); code_put(newp, cd); }
+            F.desc[D_PART] = sel; F.desc[D_KIND] = kind; F.desc[D_OLD] = p; F.desc[D_NEW] = newp; F.desc[D_SG] = sg;
+            F.desc[D_STOP] = 0; F.desc[D_SEQ] = seq;
+        };
+
+        // ---- selection: chunk sums (dirty ones re-summed, cached in a register), warp scan, walk of the winning chunk ----
+        {
+            if (lane < nchunks && F.dirty_c[lane]) {
+                const int c0 = lane << cs_shift;
+                const int hi_i = (c0 + CS < n) ? c0 + CS : n;
+                double cs = 0.0;
+                for (int i = c0; i < hi_i; ++i) cs = APS_ADD(cs, rates[i]);
+                my_cs = cs; F.dirty_c[lane] = 0;
+            }
+            double incl = lane < nchunks ? my_cs : 0.0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const double up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl = APS_ADD(incl, up);
+            }
+            double prev = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) prev = 0.0;
+            const double atot = __shfl_sync(0xffffffffu, incl, 31);
+            const double target = APS_MUL(uc, atot);
+            const unsigned wmask = __ballot_sync(0xffffffffu, lane < nchunks && prev <= target && target < incl);
+            bool exact = (__popc(wmask) != 1);
+            if (!exact) {
+                const int wl = __ffs(wmask) - 1;
+                const double prev_w = __shfl_sync(0xffffffffu, prev, wl), inc_w = __shfl_sync(0xffffffffu, incl, wl);
+                const int i = (wl << cs_shift) + lane;
+                const bool mine = lane < CS && i < n;
+                double run = mine ? rates[i] : 0.0;
+                for (int o = 1; o < CS; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, run, o);
+                    if (lane >= o) run = APS_ADD(run, up);
+                }
+                const bool last = mine && (lane == CS - 1 || i == n - 1);
+                const double hi = last ? inc_w : APS_ADD(prev_w, run);
+                double lo = __shfl_up_sync(0xffffffffu, hi, 1);
+                if (lane == 0) lo = prev_w;
+                const unsigned smask = __ballot_sync(0xffffffffu, mine && lo <= target && target < hi);
+                if (__popc(smask) != 1) exact = true;
+                else if (lane == __ffs(smask) - 1) {
+                    const double band = APS_MUL(guard, atot);
+                    if ((target - lo) < band || (hi - target) < band) F.desc[D_EXACT] = 1;
+                    else decode_apply(i);
+                }
+            }
+            if (exact && lane == 0) F.desc[D_EXACT] = 1;
+        }
+        // ---- clock: numpy's pairwise sum exactly (8 lanes per leaf, <= 4 leaves), R, tau, observation crossings ----
+        {
+            if (my_g < nleaf && F.dirty_leaf[my_g]) {                 // uniform within the 8-lane group
+                const unsigned gmask = 0xffu << (lane & 24);
+                const int k = lane & 7;
+                double res;
+                if (g_len < 8) {
+                    res = 0.0;
+                    for (int i = 0; i < g_len; ++i) res = APS_ADD(res, rates[g_start + i]);
+                } else {
+                    const int body = g_len - (g_len & 7);
+                    double acc = rates[g_start + k];
+                    for (int i = 8; i < body; i += 8) acc = APS_ADD(acc, rates[g_start + i + k]);
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 1));
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 2));
+                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 4));
+                    res = acc;
+                    for (int i = body; i < g_len; ++i) res = APS_ADD(res, rates[g_start + i]);
+                }
+                __syncwarp(gmask);
+                if (k == 0) { F.leafsum[my_g] = res; F.dirty_leaf[my_g] = 0; }
+            }
+            __syncwarp();
+            double val = (have_node && !nd_kind) ? F.leafsum[nd_leaf] : 0.0;
+            for (int lev = maxlev - 1; lev >= 0; --lev) {
+                const double va = __shfl_sync(0xffffffffu, val, nd_a), vb = __shfl_sync(0xffffffffu, val, nd_b);
+                if (nd_kind && nd_lev == lev) val = APS_ADD(va, vb);
+            }
+            if (lane == nnodes - 1) {
+                const double R = val;
+                const double tau = APS_MUL(APS_DIV(1.0, R), e);
+                const double tn = APS_ADD(t, tau);
+                F.misc[X_R] = R; F.misc[X_TNEW] = tn;
+                F.desc[D_BADR] = !(R > 0.0);
+                F.desc[D_END] = tn > T;
+                int nc = 0;
+                if (!(tn > T) && obs_idx < M && next_obs <= tn) {
+                    nc = 1;
+                    while (obs_idx + nc < M && B.times_obs[obs_idx + nc] <= tn) ++nc;
+                }
+                F.desc[D_NCROSS] = nc;
+            }
+        }
+        __syncwarp();
+
+        if (F.desc[D_BADR]) { status = APS_RUN_EMPTY; break; }
+        if (F.desc[D_EXACT] || F.desc[D_SEQ] != seq) {
+            __syncwarp();
+            if (lane == 0) {
+                const double R = F.misc[X_R];
+                double acc = 0.0;
+                for (int i = 0; i < n; ++i) acc = APS_ADD(acc, APS_DIV(rates[i], R));
+                const double last = acc;
+                int sel = n - 1; acc = 0.0;
+                for (int i = 0; i < n; ++i) { acc = APS_ADD(acc, APS_DIV(rates[i], R)); if (APS_DIV(acc, last) > uc) { sel = i; break; } }
+                decode_apply(sel);
+                F.desc[D_EXACT] = 0;
+            }
+            ++n_guard;
+            __syncwarp();
+        }
+        if (F.desc[D_STOP]) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+        const int kind = F.desc[D_KIND], part = F.desc[D_PART], oldp = F.desc[D_OLD], newp = F.desc[D_NEW];
+        const int ncross = F.desc[D_NCROSS], endflag = F.desc[D_END];
+        const int sg_now = F.desc[D_SG];                             // orientation of the particle BEFORE the event
+        const double tnew = F.misc[X_TNEW];
+        if (B.trace && lane == 0 && n_done < B.trace_cap) {
+            int32_t* tr = B.trace + ((size_t)rep * (size_t)B.trace_cap + (size_t)n_done) * 3;
+            tr[0] = part; tr[1] = kind; tr[2] = (kind == APS_EV_FLIP) ? -1 : newp;
+        }
+        ++n_done;
+        cursor += 3 + (kind < 2 ? 1 : 0);
+        if (kind == APS_EV_FLIP) S -= 2 * sg_now;
+        t = tnew;
+        if (endflag) { status = APS_RUN_DONE; break; }
+        if (ncross > 0) {
+            if ((B.record & APS_REC_MLOCAL) && B.obs_m_local) {
+                const int cd = sg_now == 1 ? 1 : 3;
+                __syncwarp();
+                if (lane == 0) {   // undo on the code array only: the recorded field is the pre-event one
+                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? -2 : 2);
+                    else if (newp != oldp) { code_put(newp, -cd); code_put(oldp, cd); }
+                }
+                __syncwarp();
+                write_field(obs_idx, ncross);
+                __syncwarp();
+                if (lane == 0) {   // redo
+                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? 2 : -2);
+                    else if (newp != oldp) { code_put(newp, cd); code_put(oldp, -cd); }
+                }
+                __syncwarp();
+            }
+            write_rows(obs_idx, ncross);
+            obs_idx += ncross;
+            if (obs_idx < M) next_obs = B.times_obs[obs_idx];
+        }
+        if (obs_idx >= M) { status = APS_RUN_DONE; break; }
+
+        // ---- refresh the rates inside the window: the particles there are a contiguous index range around `part` ----
+        {
+            const int reach = r > 1 ? r : 1;
+            const int mn = oldp < newp ? oldp : newp, mx = oldp < newp ? newp : oldp;
+            const int wlo = mn - reach, whi = mx + reach;
+            const int ia = part - 31 + lane;                           // candidates part-31 .. part
+            const bool in_a = ia >= 0 && (int)pos[ia >= 0 ? ia : 0] >= wlo;
+            const unsigned ma = __ballot_sync(0xffffffffu, in_a);
+            // in_a is monotone in the lane (sorted positions): the first set lane is the lowest index in the window
+            int ilo = ma ? part - 31 + (__ffs(ma) - 1) : part;
+            if (ma == 0xffffffffu && part - 31 > 0) {
+                // more than 32 particles to the left inside the window: extend the search one more block
+                const int ib = part - 63 + lane;
+                const bool in_b = ib >= 0 && (int)pos[ib >= 0 ? ib : 0] >= wlo;
+                const unsigned mb = __ballot_sync(0xffffffffu, in_b);
+                if (mb) ilo = part - 63 + (__ffs(mb) - 1);
+            }
+            for (int i0 = ilo; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const bool in = i < n && (int)pos[i < n ? i : n - 1] <= whi;
+                if (in) refresh(i);
+                if (!__all_sync(0xffffffffu, in)) break;
+            }
+        }
+        __syncwarp();
+    }
+
+    if (lane == 0) {
+        if (B.n_obs) B.n_obs[rep] = obs_idx;
+        if (B.n_events) B.n_events[rep] = ev_base + n_done;
+        if (B.t_end) B.t_end[rep] = t;
+        B.status[rep] = status;
+        if (B.n_guard) B.n_guard[rep] = n_guard;
+        if (B.draws_used) B.draws_used[rep] = PHILOX ? 0 : cursor;
+        if (B.n_end) B.n_end[rep] = n;
+        if (B.n_exit && !B.ev_start) B.n_exit[rep] = 0;
+    }
+    __syncwarp();
+    if (B.bound_end) for (int i = lane; i < n; i += 32) B.bound_end[(size_t)rep * n_max + i] = 0;
+    if (B.pos_end) for (int i = lane; i < n; i += 32) B.pos_end[(size_t)rep * n_max + i] = (int32_t)pos[i];
+    if (B.sigma_end) for (int i = lane; i < n; i += 32) B.sigma_end[(size_t)rep * n_max + i] = (int8_t)(code[pad + pos[i]] == 1 ? 1 : -1);
+}
+
+}  // namespace aps
