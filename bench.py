@@ -278,7 +278,7 @@ def main():
         ncu_file = os.path.join(ROOT, "profiles", "k1_ncu_summary.json")
         ncu_k1 = json.load(open(ncu_file)) if os.path.exists(ncu_file) else {}
         smem_traffic = ncu_k1.get("smem_bytes_per_event_at_128B_per_wavefront")
-        roofline = dict(bound="smem", kernel="aps::k1_fast_kernel<32,true,21,512,1056>", achieved=achieved, peak=peak, unit="GB/s",
+        roofline = dict(bound="smem", kernel="aps::k1_lean_kernel<true,21,1056>", achieved=achieved, peak=peak, unit="GB/s",
                         frac=achieved / peak,
                         traffic=(smem_traffic * events_per_launch if smem_traffic else None),
                         traffic_note="shared-memory wavefronts x 128 B per launch from the ncu capture (DRAM traffic of K1 is ~0.1 GB per launch)",
