@@ -13,14 +13,18 @@ from common import HostRun, assert_same_outputs, run_oracle
 pytestmark = pytest.mark.gpu
 
 
-def random_case(seed):
+def random_case(seed, sorted_init=False, lean=False):
+    """sorted_init: initial positions in increasing order (what the device Poisson init produces);
+    lean: restrict to what the half-image kernel aps_k1_lean.cuh accepts (K = 1, local field with r <= 20, plain model)."""
     g = np.random.default_rng(seed)
-    L = int(g.integers(8, 300))
-    K = int(g.choice([1, 1, 2, 3, 5]))
-    kind = g.choice(["global", "local", "wide", "periodic", "periodic_global"])
+    L = int(g.integers(8, 300)) if not lean else int(g.integers(8, 1000))
+    K = int(g.choice([1, 1, 2, 3, 5])) if not lean else 1
+    kind = g.choice(["global", "local", "wide", "periodic", "periodic_global"]) if not lean else "local"
     flags = 0
     if kind in ("global", "periodic_global"):
         radius, weights = -1, np.zeros(1)
+    elif kind == "local" and lean:
+        radius, weights = gaussian_weights(float(g.uniform(0.2, min(5.1, max(0.3, (L - 1) / 4.2)))))   # r <= 20 and r < L
     elif kind == "local":
         radius, weights = gaussian_weights(float(g.uniform(0.2, max(0.3, L / 12))))
     elif kind == "wide":
@@ -29,9 +33,9 @@ def random_case(seed):
         radius, weights = periodic_weights(L, 1.0 / L, float(g.uniform(0.3, max(0.4, L / 40))) / L)
     if kind.startswith("periodic"):
         flags |= capi.APS_FLAG_PERIODIC
-    if g.random() < 0.3:
+    if g.random() < 0.3 and not lean:
         flags |= capi.APS_FLAG_CROWDING
-    anchors = g.random() < 0.35
+    anchors = g.random() < 0.35 and not lean
     k_on = k_off = k_exit = 0.0
     mask = None
     if anchors:
@@ -49,6 +53,8 @@ def random_case(seed):
     for r, n in enumerate(ns):
         slots = np.repeat(np.arange(L), K)                      # respects the capacity
         pos0[r, :n] = g.permutation(slots)[:n]
+        if sorted_init:
+            pos0[r, :n] = np.sort(pos0[r, :n])
         sigma0[r, :n] = g.choice([1, -1], n)
     betas = g.uniform(0.0, 3.0, R)
     M = int(g.integers(3, 12))
@@ -90,3 +96,27 @@ def test_replay_mode_random_parameters(seed):
     ora = run_oracle(c["params"], build(c, draws=draws, draw_off=off), mode=0, threads=2)
     assert_same_outputs(gpu, ora)
     assert set(gpu.status.tolist()) <= {capi.APS_RUN_DONE, capi.APS_RUN_DRAWS_EXHAUSTED, capi.APS_RUN_EMPTY}
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_half_image_kernel_random_parameters(seed):
+    """Sorted initial positions, K = 1, local field with r <= 20: the configurations aps_k1_lean.cuh takes (28 replicas per SM),
+    native and replay mode alternating; ragged replica sizes, lattices from 8 to 1000 sites."""
+    lib = capi.load()
+    c = random_case(9000 + seed, sorted_init=True, lean=True)
+    assert c["params"].radius <= 20 and c["params"].radius < c["L"] and c["K"] == 1
+    if seed % 2 == 0:
+        seeds = np.array([seed, 2 ** 33 + seed, 7 * seed + 1, 2 ** 63 + seed], np.uint64)
+        gpu = build(c, seeds=seeds)
+        capi.check(lib.aps_run_philox_host(c["params"], gpu.batch), "aps_run_philox_host")
+        ora = run_oracle(c["params"], build(c, seeds=seeds), mode=1, threads=2)
+    else:
+        g = np.random.default_rng(seed)
+        lens = g.integers(200, 3000, len(c["ns"]))
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        draws = g.random(int(off[-1]))
+        gpu = build(c, draws=draws, draw_off=off)
+        capi.check(lib.aps_run_replay_host(c["params"], gpu.batch), "aps_run_replay_host")
+        ora = run_oracle(c["params"], build(c, draws=draws, draw_off=off), mode=0, threads=2)
+    assert_same_outputs(gpu, ora)
+    assert (gpu.n_events > 0).any()
