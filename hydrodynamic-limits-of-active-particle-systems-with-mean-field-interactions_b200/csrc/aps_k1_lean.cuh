@@ -15,14 +15,16 @@
 //     hop flags are two neighbour reads, the accumulator slot is recomputed from the index;
 //   * cached pairwise accumulators and chunk sums in shared memory: the 8 accumulators of a dirty leaf are re-summed
 //     by 8 lanes in lock-step anyway, the chunk sum of lane c lives in a register of lane c.
-// Limits: single-warp CTAs, n_max <= 512, r + 1 <= RCAP, L + 2r <= LPCAP.
+// Limits: single-warp CTAs, n_max <= 512 and n <= 488 per replica (<= 4 leaves in numpy's pairwise tree; larger replicas go to
+// the fast kernel like the unsorted ones), r + 1 <= RCAP, L + 2r <= LPCAP.
 #pragma once
 #include "aps_k1_fast.cuh"
 
 namespace aps {
 
 constexpr int APS_RUN_RETRY_FAST = 101;
-constexpr int kLeanN = 512;
+constexpr int kLeanN = 512;            // capacity of the per-particle arrays
+constexpr int kLeanNMax = 488;         // largest n whose numpy pairwise-sum tree has <= 4 leaves (489 has 5)
 constexpr int kLeanRing = 32;          // 8 events of variate look-ahead
 
 template <int RCAP>
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
     __syncwarp();
     int S = 0;
     bool unsorted = false;
-    if (n > 0 && n <= kLeanN) {
+    if (n > 0 && n <= kLeanNMax) {
         const int32_t* gp = B.pos0 + (size_t)rep * n_max;
         const int8_t* gs = B.sigma0 + (size_t)rep * n_max;
         int part = 0, bad = 0;
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
         S = part;
         unsorted = __any_sync(0xffffffffu, bad);
     }
-    if (unsorted || n > kLeanN || n == 0) {
+    if (unsorted || n > kLeanNMax || n == 0) {
         if (lane == 0) {
             if (n == 0) {
                 if (B.n_obs) B.n_obs[rep] = B.obs_start ? B.obs_start[rep] : 0;

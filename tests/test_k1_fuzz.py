@@ -120,3 +120,29 @@ def test_half_image_kernel_random_parameters(seed):
         ora = run_oracle(c["params"], build(c, draws=draws, draw_off=off), mode=0, threads=2)
     assert_same_outputs(gpu, ora)
     assert (gpu.n_events > 0).any()
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 128, 129, 257, 488, 489, 495, 505, 512])
+def test_half_image_kernel_particle_count_edges(n):
+    """Sorted K = 1 inputs around the sizes where numpy's pairwise-sum tree changes shape (129: two leaves, 257: three,
+    489: five leaves -> the half-image kernel hands the replica to the full-size kernel): all must equal the oracle."""
+    lib = capi.load()
+    g = np.random.default_rng(n)
+    L = 700
+    radius, weights = gaussian_weights(3.0)
+    R = 3
+    ns = [n, max(1, n - 3), n]
+    pos0 = np.zeros((R, n), np.int32); sigma0 = np.ones((R, n), np.int8)
+    for r, k in enumerate(ns):
+        pos0[r, :k] = np.sort(g.choice(L, k, replace=False)); sigma0[r, :k] = g.choice([1, -1], k)
+    M = 4
+    T = 300.0 / (n * 4.0)
+    params = make_params(L, 1, radius, 0.3, 2.0, T, 0)
+    c = dict(L=L, n_max=n, M=M, ns=ns, pos0=pos0, sigma0=sigma0, betas=np.array([0.5, 1.5, 2.5]), times=np.arange(M) * (T / M),
+             weights=weights, params=params, mask=None)
+    seeds = np.array([n, n + 1, n + 2], np.uint64)
+    gpu = build(c, seeds=seeds)
+    capi.check(lib.aps_run_philox_host(params, gpu.batch), "aps_run_philox_host")
+    ora = run_oracle(params, build(c, seeds=seeds), mode=1, threads=2)
+    assert_same_outputs(gpu, ora)
+    assert (gpu.n_events > 20).all()
