@@ -18,10 +18,10 @@
 
 namespace aps {
 
-constexpr int kFastLeafCap = 8;       // n <= 1024
+constexpr int kFastLeafCap = 8;       // n <= 968 (kFastMaxN); larger replicas are re-run by the generic kernel
 constexpr int kFastNodeCap = 16;
 constexpr int kFastRing = 64;         // doubles of variate look-ahead (16 events in native mode)
-constexpr int kFastMaxN = 1024;
+constexpr int kFastMaxN = 968;        // largest n whose numpy pairwise-sum tree has <= 8 leaves / 15 nodes (969 has 9 leaves)
 constexpr int APS_RUN_RETRY_GENERIC = 100;
 
 struct FastFixed {                    // compile-time-offset part of the shared-memory image

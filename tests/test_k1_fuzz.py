@@ -122,13 +122,14 @@ def test_half_image_kernel_random_parameters(seed):
     assert (gpu.n_events > 0).any()
 
 
-@pytest.mark.parametrize("n", [1, 7, 8, 9, 128, 129, 257, 488, 489, 495, 505, 512])
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 128, 129, 257, 488, 489, 495, 505, 512, 600, 968, 969, 1000, 1024])
 def test_half_image_kernel_particle_count_edges(n):
     """Sorted K = 1 inputs around the sizes where numpy's pairwise-sum tree changes shape (129: two leaves, 257: three,
-    489: five leaves -> the half-image kernel hands the replica to the full-size kernel): all must equal the oracle."""
+    489: five leaves -> the half-image kernel hands the replica to the full-size kernel; 969: nine leaves -> the full-size
+    kernel hands it to the generic one): all must equal the oracle."""
     lib = capi.load()
     g = np.random.default_rng(n)
-    L = 700
+    L = 700 if n <= 512 else 1030
     radius, weights = gaussian_weights(3.0)
     R = 3
     ns = [n, max(1, n - 3), n]
