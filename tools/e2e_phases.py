@@ -5,7 +5,7 @@ import bench as B
 from aps_b200 import launcher as la
 ik = B.init_kwargs()
 betas = np.linspace(0, 3, B.N_BETA)
-run_kwargs = dict(B.RUN_KWARGS, T=5.0)
+run_kwargs = dict(B.RUN_KWARGS, T=20.0)
 def sync(): torch.cuda.synchronize()
 for it in range(3):
     t=[time.perf_counter()]
