@@ -134,7 +134,7 @@ class ApsK2Args(C.Structure):
     _fields_ = [("L", C.c_int64), ("L_global", C.c_int64), ("global_offset", C.c_int64), ("n_particles", C.c_int64),
                 ("seed", C.c_uint64), ("pass_", C.c_uint64), ("radius", C.c_int32), ("reserved", C.c_int32),
                 ("rates", ApsK2Rates), ("w16", C.c_void_p), ("flip_tab", C.c_void_p), ("in_", C.c_void_p), ("out", C.c_void_p),
-                ("msum_in", C.c_void_p), ("msum_out", C.c_void_p)]
+                ("msum_in", C.c_void_p), ("msum_out", C.c_void_p), ("count_lo", C.c_int64), ("count_hi", C.c_int64)]
 
 
 class ApsPdeArgs(C.Structure):          # include/aps_pde.h
@@ -207,7 +207,7 @@ def load(path: str | None = None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.aps_abi_version() != 3:
+    if lib.aps_abi_version() != 4:
         raise ApsError("libaps_b200.so ABI version mismatch")
     if path is None:
         _lib = lib

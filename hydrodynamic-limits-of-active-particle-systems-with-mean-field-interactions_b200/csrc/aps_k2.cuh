@@ -219,6 +219,8 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         const uint32_t chi = (uint32_t)(seg_global >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
         const long long abase = t0 + (long long)tid * APS_K2_SEG + qpar * APS_K2_HALF;     // first active site (slab index)
         const bool seg_ok = abase + APS_K2_HALF <= L;
+        // slab decomposition: flips of ghost segments are recomputed by the neighbour rank and must not be counted twice
+        const int dsig_on = (a.count_hi <= a.count_lo) || (abase >= a.count_lo && abase < a.count_hi);
         aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
         int ntr = 0;
         if (seg_ok) while (ntr < (int)a.rates.n_cdf && w4.v[0] >= a.rates.cdf32[ntr]) ++ntr;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             } else if (cat == 1 || (cat == 2 && v == APS_K2_PLUS)) {
                 if (lx < L - 1 && act[x + 1] == APS_K2_EMPTY) { act[x + 1] = v; act[x] = APS_K2_EMPTY; }
             } else if (cat == 3) {
-                if (accept(v)) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= (v == APS_K2_PLUS) ? 2 : -2; }
+                if (accept(v)) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= dsig_on * ((v == APS_K2_PLUS) ? 2 : -2); }
             }
         };
         auto category = [&](uint32_t slot) { return slot < t_left ? 0 : (slot < t_right ? 1 : (slot < t_active ? 2 : 3)); };

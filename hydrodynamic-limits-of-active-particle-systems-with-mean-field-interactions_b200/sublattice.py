@@ -97,9 +97,7 @@ class SublatticeLattice:
         self.hi = min(L, self.own_hi + self.ghost)
         self.L = self.hi - self.lo
         if sigma_sites is None or sigma_sites <= 0:
-            self.radius, self.w16 = -1, None
-            if self.world > 1:
-                raise NotImplementedError("the global-magnetisation mode needs a per-pass allreduce; use a local kernel")
+            self.radius, self.w16 = -1, None           # global magnetisation: one 8-byte all-reduce per pass when sliced
         else:
             self.radius, w = fixed_point_taps(sigma_sites)
             self.w16 = self.be.from_numpy(w)
@@ -153,17 +151,26 @@ class SublatticeLattice:
         a.flip_tab = self.be.ptr(self.flip_tab) if self.flip_tab is not None else None
         a.in_, a.out = self.be.ptr(self.buf[self.cur]), self.be.ptr(self.buf[1 - self.cur])
         a.msum_in, a.msum_out = self.be.ptr(self.msum[0]), self.be.ptr(self.msum[1])
+        if self.world > 1 and self.radius < 0:          # ghost segments are recomputed by the neighbours: count own flips only
+            a.count_lo, a.count_hi = self.own_lo - self.lo, self.own_hi - self.lo
         return a
 
     def run_passes(self, n_passes):
         done = 0
+        sliced_global = self.world > 1 and self.radius < 0
         while done < n_passes:
             k = min(n_passes - done, self.refresh_every - self.since_refresh)
+            if sliced_global:
+                k = 1                                  # every pass needs the lattice-wide sum(sigma) of the previous one
             a = self._args()
             self.be.run(a, k)
             if k % 2:
                 self.cur = 1 - self.cur
                 self.msum.reverse()
+            if sliced_global:                          # msum[0] = old + own flips, msum[1] = old: all-reduce the increments
+                delta = self.msum[0] - self.msum[1]
+                torch.distributed.all_reduce(delta)
+                self.msum[0].copy_(self.msum[1] + delta)
             self.passes_done += k
             self.since_refresh += k
             done += k

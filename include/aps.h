@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APS_ABI_VERSION 3
+#define APS_ABI_VERSION 4
 
 typedef enum aps_status {
     APS_OK = 0,
@@ -273,6 +273,8 @@ typedef struct aps_k2_args {
     uint8_t* out;               /* [L] ping-pong target                                              */
     const int64_t* msum_in;     /* global-field mode: sum(sigma) at pass start (device)             */
     int64_t* msum_out;          /* must hold *msum_in on entry; receives the flips' increments      */
+    int64_t count_lo, count_hi; /* slab decomposition: only flips at buffer sites [count_lo, count_hi) are added to   */
+                                /* msum_out (the caller all-reduces the increments of the ranks); 0, 0 = whole buffer */
 } aps_k2_args;
 /* thresholds / Poisson table for (D, lambda, beta, dt); returns non-zero if B*32*dt is out of (0, 24] */
 int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates* out);

@@ -476,6 +476,7 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
     for (long long seg = 0; seg * APS_K2_SEG < L; ++seg) {
         const long long abase = seg * APS_K2_SEG + q * APS_K2_HALF;
         if (abase + APS_K2_HALF > L) continue;
+        const int dsig_on = (a->count_hi <= a->count_lo) || (abase >= a->count_lo && abase < a->count_hi);
         const uint64_t sg64 = (uint64_t)(a->global_offset / APS_K2_SEG) + (uint64_t)seg;
         const uint32_t c0 = (uint32_t)sg64, c1 = (uint32_t)a->pass;
         const uint32_t chi = (uint32_t)(sg64 >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
@@ -510,7 +511,7 @@ int aps_oracle_k2_pass(const aps_k2_args* a) {
                     }
                     thr = a->flip_tab[(sg == 1 ? 0 : (2 * APS_K2_MQ + 1)) + aps_k2_mq_index(sw, tw)];
                 } else thr = thr_glob[sg == 1 ? 0 : 1];
-                if (slot - a->rates.t_active < thr) { out[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= 2 * sg; }
+                if (slot - a->rates.t_active < thr) { out[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= dsig_on * 2 * sg; }
             }
         }
     }

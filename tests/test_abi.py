@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, n), f"{n} declared in include/aps.h but not exported"
         assert n in capi.SYMBOLS, f"{n} has no ctypes prototype in capi.py"
     assert sorted(capi.SYMBOLS) == names
-    assert lib.aps_abi_version() == 3
+    assert lib.aps_abi_version() == 4
 
 
 def test_struct_layout_matches_header(lib):

@@ -59,30 +59,35 @@ def _slab_worker(rank, world, port, q, sigma, passes):
     lat.run_passes(passes)
     full = lat.gather_state()
     rp, rm = lat.profile(24)
-    q.put((rank, full, rp, rm, lat.n_particles))
+    q.put((rank, full, rp, rm, lat.n_particles, int(lat.msum[0][0])))
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
 
+@pytest.mark.parametrize("sigma", [3.0, None])
 @pytest.mark.parametrize("world", [2, 3])
-def test_slab_decomposition_is_bit_identical_to_single_slab(world):
-    sigma, passes = 3.0, 70
+def test_slab_decomposition_is_bit_identical_to_single_slab(world, sigma):
+    """sigma = None: global magnetisation — every rank counts the flips of its own segments only and the increments are
+    all-reduced after every pass, so all ranks use the same m as the single-slab run."""
+    passes = 70
     single = oracle_lattice(6 * TILE, sigma_sites=sigma, seed=11, **PARAMS)
     single.init_random(0.5, 0.6)
     single.run_passes(passes)
     want = single.state.numpy()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + 7 * world
+    port = 29500 + (os.getpid() % 2000) + 7 * world + (100 if sigma is None else 0)
     procs = [ctx.Process(target=_slab_worker, args=(r, world, port, q, sigma, passes)) for r in range(world)]
     [p.start() for p in procs]
     got = [q.get(timeout=600) for _ in range(world)]
     [p.join(60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
     rp1, rm1 = single.profile(24)
-    for rank, full, rp, rm, n in got:
+    for rank, full, rp, rm, n, msum in got:
         assert np.array_equal(full, want), f"rank {rank}: slab run differs from the single-slab run"
         assert np.array_equal(rp, rp1) and np.array_equal(rm, rm1) and n == single.n_particles
+        if sigma is None:
+            assert msum == int(single.msum[0][0]) == int((want == 1).sum()) - int((want == 2).sum())
 
 
 def test_small_dt_limit_matches_exact_gillespie():

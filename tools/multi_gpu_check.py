@@ -41,6 +41,19 @@ one.init_random(0.5, 0.6)
 one.run_passes(90)
 assert np.array_equal(full, one.state.cpu().numpy()), "slab run differs from single-GPU run"
 rp, rm = lat.profile(32)
+# global-magnetisation mode across ranks: own flips only + one 8-byte all-reduce per pass
+kwg = dict(D=0.3, lam=3.0, beta=1.2, dt=0.01, sigma_sites=None, seed=13)
+latg = SublatticeLattice(8 * TILE, **kwg)
+latg.init_random(0.5, 0.6)
+latg.refresh_every = 24
+latg.run_passes(60)
+fullg = latg.gather_state()
+oneg = SublatticeLattice(8 * TILE, single_rank=True, **kwg)
+oneg.init_random(0.5, 0.6)
+oneg.run_passes(60)
+assert np.array_equal(fullg, oneg.state.cpu().numpy()), "global-field slab run differs from single-GPU run"
+assert int(latg.msum[0][0]) == int(oneg.msum[0][0])
+print(f"rank {rank}/{world}: K2 global-field slabs bit-identical to single GPU, sum(sigma)={int(latg.msum[0][0])}", flush=True)
 rp1, rm1 = one.profile(32)
 assert np.array_equal(rp, rp1) and np.array_equal(rm, rm1)
 print(f"rank {rank}/{world}: K2 slab decomposition bit-identical to single GPU (own sites {lat.own_lo}..{lat.own_hi})", flush=True)
