@@ -30,16 +30,16 @@ static cudaError_t launch_class(const K1Args& a, bool philox, cudaStream_t st) {
     return g_fast_nt == 32 ? launch_nt<32, RCAP, NCAP, LPCAP>(a, philox, st) : launch_nt<64, RCAP, NCAP, LPCAP>(a, philox, st);
 }
 
-template <int RCAP, int LPCAP>
+template <int RCAP, int LPCAP, int NCAP, bool WHO>
 static cudaError_t launch_lean(const K1Args& a, bool philox, cudaStream_t st) {
-    const size_t smem = k1_lean_smem_bytes<RCAP, LPCAP>();
+    const size_t smem = k1_lean_smem_bytes<RCAP, LPCAP, NCAP, WHO>();
     if (philox) {
-        auto k = k1_lean_kernel<true, RCAP, LPCAP>;
+        auto k = k1_lean_kernel<true, RCAP, LPCAP, NCAP, WHO>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k<<<a.b.n_replicas, 32, smem, st>>>(a);
     } else {
-        auto k = k1_lean_kernel<false, RCAP, LPCAP>;
+        auto k = k1_lean_kernel<false, RCAP, LPCAP, NCAP, WHO>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k<<<a.b.n_replicas, 32, smem, st>>>(a);
@@ -60,7 +60,7 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
             if (nt == 32 && !getenv("APS_K1_NO_LEAN")) {
                 // half-size shared-memory image: all replicas of an SM resident at once; its rejects (unsorted initial
                 // positions) go through the full-size kernel in a second, otherwise empty launch
-                cudaError_t e = launch_lean<21, 1056>(a, philox, st);
+                cudaError_t e = launch_lean<21, 1056, 512, false>(a, philox, st);
                 if (e != cudaSuccess) return e;
                 *launched = 2;
                 K1Args b = a;
@@ -69,7 +69,19 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
             }
             return launch_class<21, 512, 1056>(a, philox, st);
         }
-        if (r1 <= 21 && nm <= 1024 && lp <= 1056) return launch_class<21, 1024, 1056>(a, philox, st);
+        if (r1 <= 21 && nm <= 1024 && lp <= 1056) {
+            if (nt == 32 && !getenv("APS_K1_NO_LEAN")) {
+                // mid-size replicas (config 3: N = 900): trimmed image WITH the site map (any particle order), 15 instead of
+                // 10 replicas per SM; its rejects (n > 968, K = 1 violated) fall through to the full-size and generic kernels
+                cudaError_t e = launch_lean<21, 1056, 1024, true>(a, philox, st);
+                if (e != cudaSuccess) return e;
+                *launched = 2;
+                K1Args b = a;
+                b.only_retry = 2;
+                return launch_class<21, 1024, 1056>(b, philox, st);
+            }
+            return launch_class<21, 1024, 1056>(a, philox, st);
+        }
         if (r1 <= 81 && nm <= 512 && lp <= 1184) return launch_class<81, 512, 1184>(a, philox, st);
         if (r1 <= 81 && nm <= 1024 && lp <= 1184) return launch_class<81, 1024, 1184>(a, philox, st);
     }

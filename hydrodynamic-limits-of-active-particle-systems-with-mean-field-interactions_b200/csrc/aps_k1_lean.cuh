@@ -15,6 +15,8 @@
 //     hop flags are two neighbour reads, the accumulator slot is recomputed from the index;
 //   * cached pairwise accumulators and chunk sums in shared memory: the 8 accumulators of a dirty leaf are re-summed
 //     by 8 lanes in lock-step anyway, the chunk sum of lane c lives in a register of lane c.
+// Two instantiations: <NCAP = 512, WHO = false> as described (sorted inputs, 28 replicas per SM) and <NCAP = 1024, WHO = true>,
+// which keeps the site map and therefore takes any particle order (n <= 968, 15 replicas per SM instead of the fast kernel's 10).
 // Limits: single-warp CTAs, n_max <= 512 and n <= 488 per replica (<= 4 leaves in numpy's pairwise tree; larger replicas go to
 // the fast kernel like the unsorted ones), r + 1 <= RCAP, L + 2r <= LPCAP.
 #pragma once
@@ -33,22 +35,26 @@ struct LeanFixed {
     double hop_tab[8];
     double ms[9], mt[9];               // multipliers (a_plus - a_minus), (a_plus + a_minus) of a pair code
     double wtab[RCAP];
-    double leafsum[4];
+    double leafsum[8];
     double misc[4];
     int32_t desc[16];
-    int8_t node_a[8], node_b[8], node_kind[8], node_level[8], node_leaf[8];
-    int16_t leaf_start[4], leaf_len[4];
+    int8_t node_a[16], node_b[16], node_kind[16], node_level[16], node_leaf[16];
+    int16_t leaf_start[8], leaf_len[8];
+    uint16_t list[64];                 // compacted particle list of an update window (site-map variant only)
     uint8_t dirty_c[32];
-    uint8_t dirty_leaf[4];
+    uint8_t dirty_leaf[8];
 };
 
-template <int RCAP, int LPCAP>
+// NCAP = 512: particles must come sorted (no site map), n <= 488, 28 replicas per SM.
+// NCAP = 1024 (WHO = true): site->particle map kept (any particle order), n <= 968 (<= 8 leaves), 15 replicas per SM.
+template <int RCAP, int LPCAP, int NCAP, bool WHO>
 __host__ __device__ inline size_t k1_lean_smem_bytes() {
-    return ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15) + (size_t)kLeanN * 8 + (size_t)kLeanN * 2 + (size_t)LPCAP;
+    return ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15) + (size_t)NCAP * 8 + (size_t)NCAP * 2 + (size_t)LPCAP + (WHO ? (size_t)LPCAP * 2 : 0);
 }
 
-template <bool PHILOX, int RCAP, int LPCAP>
-__global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__ K1Args A) {
+template <bool PHILOX, int RCAP, int LPCAP, int NCAP, bool WHO>
+__global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(const __grid_constant__ K1Args A) {
+    constexpr int kNMax = NCAP <= 512 ? kLeanNMax : 968;          // largest n with <= 4 (8) leaves in numpy's pairwise tree
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const aps_params& P = A.p;
     const aps_batch& B = A.b;
@@ -60,17 +66,19 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
 
     LeanFixed<RCAP>& F = *reinterpret_cast<LeanFixed<RCAP>*>(smem_raw);
     unsigned char* dyn = smem_raw + ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15);
-    double* const rates = reinterpret_cast<double*>(dyn); dyn += (size_t)kLeanN * 8;
-    uint16_t* const pos = reinterpret_cast<uint16_t*>(dyn); dyn += (size_t)kLeanN * 2;
+    double* const rates = reinterpret_cast<double*>(dyn); dyn += (size_t)NCAP * 8;
+    uint16_t* const pos = reinterpret_cast<uint16_t*>(dyn); dyn += (size_t)NCAP * 2;
+    uint16_t* const who = reinterpret_cast<uint16_t*>(dyn); dyn += WHO ? (size_t)LPCAP * 2 : 0;
     uint8_t* const code = dyn;
 
     // ---------------- prologue ----------------
     for (int i = lane; i < L + 2 * pad; i += 32) code[i] = 0;
+    if (WHO) for (int i = lane; i < L; i += 32) who[i] = 0xFFFFu;
     if (lane <= r) F.wtab[lane] = B.weights[lane];
     if (lane < 9) { const int am = lane / 3, ap = lane - am * 3; F.ms[lane] = (double)(ap - am); F.mt[lane] = (double)(ap + am); }
     if (lane < 16) F.desc[lane] = 0;
     F.dirty_c[lane] = 1;
-    if (lane < 4) F.dirty_leaf[lane] = 1;
+    if (lane < 8) F.dirty_leaf[lane] = 1;
     if (lane < 8) {
         const double dz = APS_MUL(D, 0.0);
         F.hop_tab[lane] = APS_ADD(APS_ADD((lane & 1) ? D : dz, (lane & 2) ? D : dz), (lane & 4) ? lam : 0.0);
@@ -78,7 +86,7 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
     __syncwarp();
     int S = 0;
     bool unsorted = false;
-    if (n > 0 && n <= kLeanNMax) {
+    if (n > 0 && n <= kNMax) {
         const int32_t* gp = B.pos0 + (size_t)rep * n_max;
         const int8_t* gs = B.sigma0 + (size_t)rep * n_max;
         int part = 0, bad = 0;
@@ -86,14 +94,19 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
             const int p = gp[i], sg = gs[i];
             pos[i] = (uint16_t)p;
             part += sg;
-            if (i + 1 < n && gp[i + 1] <= p) bad = 1;                 // needs strictly increasing positions (K = 1, sorted)
-            code[pad + p] = (uint8_t)(sg == 1 ? 1 : 3);               // distinct sites when sorted; garbage otherwise (we bail out)
+            if (!WHO && i + 1 < n && gp[i + 1] <= p) bad = 1;         // needs strictly increasing positions (K = 1, sorted)
+            code[pad + p] = (uint8_t)(sg == 1 ? 1 : 3);               // distinct sites when valid; garbage otherwise (we bail out)
+            if (WHO) who[p] = (uint16_t)i;
+        }
+        if (WHO) {                                                    // two particles on one site: only the last writer is in who[]
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) bad |= (who[pos[i]] != (uint16_t)i);
         }
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         S = part;
         unsorted = __any_sync(0xffffffffu, bad);
     }
-    if (unsorted || n > kLeanNMax || n == 0) {
+    if (unsorted || n > kNMax || n == 0) {
         if (lane == 0) {
             if (n == 0) {
                 if (B.n_obs) B.n_obs[rep] = B.obs_start ? B.obs_start[rep] : 0;
@@ -119,7 +132,7 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
     if (lane == 0) {
         // numpy pairwise tree (<= 4 leaves for n <= 512), built in the still unused rates area
         int32_t* na = reinterpret_cast<int32_t*>(rates); int32_t* nb = na + 16; int32_t* nk = nb + 16; int32_t* lv = nk + 16;
-        const int nn = build_sum_tree(n, na, nb, nk, 8);
+        const int nn = build_sum_tree(n, na, nb, nk, 16);
         int nl = 0;
         for (int g = 0; g < nn; ++g) {
             F.node_kind[g] = (int8_t)nk[g];
@@ -145,7 +158,10 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
     const int nd_leaf = (have_node && !nd_kind) ? F.node_leaf[lane] : 0;
     const int my_g = lane >> 3;
     const int g_start = my_g < nleaf ? F.leaf_start[my_g] : 0, g_len = my_g < nleaf ? F.leaf_len[my_g] : 0;
+    const int g2_start = my_g + 4 < nleaf ? F.leaf_start[my_g + 4] : 0, g2_len = my_g + 4 < nleaf ? F.leaf_len[my_g + 4] : 0;   // NCAP = 1024 only
     const int ls1 = nleaf > 1 ? F.leaf_start[1] : 0x7fff, ls2 = nleaf > 2 ? F.leaf_start[2] : 0x7fff, ls3 = nleaf > 3 ? F.leaf_start[3] : 0x7fff;
+    const int ls4 = nleaf > 4 ? F.leaf_start[4] : 0x7fff, ls5 = nleaf > 5 ? F.leaf_start[5] : 0x7fff;
+    const int ls6 = nleaf > 6 ? F.leaf_start[6] : 0x7fff, ls7 = nleaf > 7 ? F.leaf_start[7] : 0x7fff;
     int cs_shift = 4;
     while (((n + (1 << cs_shift) - 1) >> cs_shift) > 32) ++cs_shift;
     const int CS = 1 << cs_shift;
@@ -216,7 +232,9 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
         const double m = local_m(p);
         rates[i] = APS_ADD(h, aps_exp(APS_MUL(APS_MUL(-beta, sgd), m)));
         F.dirty_c[i >> cs_shift] = 1;
-        F.dirty_leaf[(i >= ls1) + (i >= ls2) + (i >= ls3)] = 1;
+        int lf = (i >= ls1) + (i >= ls2) + (i >= ls3);
+        if (NCAP > 512) lf += (i >= ls4) + (i >= ls5) + (i >= ls6) + (i >= ls7);
+        F.dirty_leaf[lf] = 1;
     };
     auto code_put = [&](int x, int delta) { code_add(code, L, pad, x, delta); };
 
@@ -278,7 +296,10 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
             } else if (v < act_thresh) { kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, L - 1); }
             else kind = APS_EV_FLIP;
             if (kind == APS_EV_FLIP) code_put(p, sg == 1 ? 2 : -2);
-            else if (newp != p) { pos[sel] = (uint16_t)newp; code_put(p, -cd); code_put(newp, cd); }
+            else if (newp != p) {
+                pos[sel] = (uint16_t)newp; code_put(p, -cd); code_put(newp, cd);
+                if (WHO) { who[p] = 0xFFFFu; who[newp] = (uint16_t)sel; }
+            }
             F.desc[D_PART] = sel; F.desc[D_KIND] = kind; F.desc[D_OLD] = p; F.desc[D_NEW] = newp; F.desc[D_SG] = sg;
             F.desc[D_STOP] = 0; F.desc[D_SEQ] = seq;
         };
@@ -329,25 +350,30 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
         }
         // ---- clock: numpy's pairwise sum exactly (8 lanes per leaf, <= 4 leaves), R, tau, observation crossings ----
         {
-            if (my_g < nleaf && F.dirty_leaf[my_g]) {                 // uniform within the 8-lane group
-                const unsigned gmask = 0xffu << (lane & 24);
-                const int k = lane & 7;
-                double res;
-                if (g_len < 8) {
-                    res = 0.0;
-                    for (int i = 0; i < g_len; ++i) res = APS_ADD(res, rates[g_start + i]);
-                } else {
-                    const int body = g_len - (g_len & 7);
-                    double acc = rates[g_start + k];
-                    for (int i = 8; i < body; i += 8) acc = APS_ADD(acc, rates[g_start + i + k]);
-                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 1));
-                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 2));
-                    acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 4));
-                    res = acc;
-                    for (int i = body; i < g_len; ++i) res = APS_ADD(res, rates[g_start + i]);
+#pragma unroll
+            for (int half = 0; half < (NCAP > 512 ? 2 : 1); ++half) {
+                const int gg = my_g + 4 * half;
+                const int gs = half ? g2_start : g_start, gl = half ? g2_len : g_len;
+                if (gg < nleaf && F.dirty_leaf[gg]) {                 // uniform within the 8-lane group
+                    const unsigned gmask = 0xffu << (lane & 24);
+                    const int k = lane & 7;
+                    double res;
+                    if (gl < 8) {
+                        res = 0.0;
+                        for (int i = 0; i < gl; ++i) res = APS_ADD(res, rates[gs + i]);
+                    } else {
+                        const int body = gl - (gl & 7);
+                        double acc = rates[gs + k];
+                        for (int i = 8; i < body; i += 8) acc = APS_ADD(acc, rates[gs + i + k]);
+                        acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 1));
+                        acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 2));
+                        acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 4));
+                        res = acc;
+                        for (int i = body; i < gl; ++i) res = APS_ADD(res, rates[gs + i]);
+                    }
+                    __syncwarp(gmask);
+                    if (k == 0) { F.leafsum[gg] = res; F.dirty_leaf[gg] = 0; }
                 }
-                __syncwarp(gmask);
-                if (k == 0) { F.leafsum[my_g] = res; F.dirty_leaf[my_g] = 0; }
             }
             __syncwarp();
             double val = (have_node && !nd_kind) ? F.leafsum[nd_leaf] : 0.0;
@@ -425,8 +451,28 @@ __global__ void __launch_bounds__(32, 28) k1_lean_kernel(const __grid_constant__
         }
         if (obs_idx >= M) { status = APS_RUN_DONE; break; }
 
-        // ---- refresh the rates inside the window: the particles there are a contiguous index range around `part` ----
-        {
+        // ---- refresh the rates inside the window ----
+        if (WHO) {                                                     // any particle order: site->particle map + ballot compaction
+            const int reach = r > 1 ? r : 1;
+            const int mn = oldp < newp ? oldp : newp, mx = oldp < newp ? newp : oldp;
+            int wlo = mn - reach, whi = mx + reach;
+            if (wlo < 0) wlo = 0;
+            if (whi > L - 1) whi = L - 1;
+            int count = 0;
+            for (int s0 = wlo; s0 <= whi; s0 += 32) {
+                const int site = s0 + lane;
+                const unsigned v = (site <= whi) ? who[site] : 0xFFFFu;
+                const unsigned mask = __ballot_sync(0xffffffffu, v != 0xFFFFu);
+                if (v != 0xFFFFu) F.list[count + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)v;
+                count += __popc(mask);
+                if (count >= 32 || s0 + 32 > whi) {                    // the list holds at most 64 entries
+                    __syncwarp();
+                    for (int j0 = 0; j0 < count; j0 += 32) { const int j = j0 + lane; if (j < count) refresh(F.list[j]); }
+                    __syncwarp();
+                    count = 0;
+                }
+            }
+        } else {   // sorted particles: the window is a contiguous index range around `part`
             const int reach = r > 1 ? r : 1;
             const int mn = oldp < newp ? oldp : newp, mx = oldp < newp ? newp : oldp;
             const int wlo = mn - reach, whi = mx + reach;
