@@ -136,6 +136,8 @@ def test_half_image_kernel_particle_count_edges(n):
     pos0 = np.zeros((R, n), np.int32); sigma0 = np.ones((R, n), np.int8)
     for r, k in enumerate(ns):
         pos0[r, :k] = np.sort(g.choice(L, k, replace=False)); sigma0[r, :k] = g.choice([1, -1], k)
+        if r == 1:                       # one replica in random particle order: site-map kernels (lean n > 512, fast otherwise)
+            pos0[r, :k] = g.permutation(pos0[r, :k])
     M = 4
     T = 300.0 / (n * 4.0)
     params = make_params(L, 1, radius, 0.3, 2.0, T, 0)
