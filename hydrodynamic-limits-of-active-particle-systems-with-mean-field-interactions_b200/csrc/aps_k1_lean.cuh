@@ -33,7 +33,7 @@ template <int RCAP>
 struct LeanFixed {
     double ring[kLeanRing];
     double hop_tab[8];
-    double ms[9], mt[9];               // multipliers (a_plus - a_minus), (a_plus + a_minus) of a pair code
+    double2 mst[9];                    // multipliers (a_plus - a_minus, a_plus + a_minus) of a pair code: one 16-byte load
     double wtab[RCAP];
     double leafsum[8];
     double misc[4];
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     for (int i = lane; i < L + 2 * pad; i += 32) code[i] = 0;
     if (WHO) for (int i = lane; i < L; i += 32) who[i] = 0xFFFFu;
     if (lane <= r) F.wtab[lane] = B.weights[lane];
-    if (lane < 9) { const int am = lane / 3, ap = lane - am * 3; F.ms[lane] = (double)(ap - am); F.mt[lane] = (double)(ap + am); }
+    if (lane < 9) { const int am = lane / 3, ap = lane - am * 3; F.mst[lane] = make_double2((double)(ap - am), (double)(ap + am)); }
     if (lane < 16) F.desc[lane] = 0;
     F.dirty_c[lane] = 1;
     if (lane < 8) F.dirty_leaf[lane] = 1;
@@ -183,13 +183,15 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     auto local_m = [&](int p) {
         const uint8_t* c = code + pad + p;
         const double w0 = F.wtab[r];
-        double sc = APS_MUL(F.ms[c[0]], w0), tc = APS_MUL(F.mt[c[0]], w0);
+        const double2 m0 = F.mst[c[0]];
+        double sc = APS_MUL(m0.x, w0), tc = APS_MUL(m0.y, w0);
 #pragma unroll 4
         for (int jj = -r; jj < 0; ++jj) {
             const int idx = (int)c[jj] + (int)c[-jj];
             const double wj = F.wtab[r + jj];
-            sc = APS_ADD(sc, APS_MUL(F.ms[idx], wj));
-            tc = APS_ADD(tc, APS_MUL(F.mt[idx], wj));
+            const double2 mm = F.mst[idx];
+            sc = APS_ADD(sc, APS_MUL(mm.x, wj));
+            tc = APS_ADD(tc, APS_MUL(mm.y, wj));
         }
         double m = 0.0;
         if (tc > 0.0) m = APS_DIV(sc, tc);
