@@ -71,3 +71,21 @@ def test_oracle_native_mode_matches_reference_statistics(bi, beta):
 @pytest.mark.parametrize("bi,beta", [(0, 0.5), (1, 2.0)])
 def test_gpu_native_mode_matches_reference_statistics(bi, beta):
     _check(bi, beta, None)
+
+
+@pytest.mark.gpu
+def test_mean_field_fixed_point_with_global_magnetisation():
+    """Known-answer check the drivers themselves plot (sweep_beta.py:232-254): with the GLOBAL magnetisation
+    (local_kernel_sigma = 0) and flip rate exp(-beta*sigma*m) the stationary magnetisation solves m = tanh(beta*m).
+    256 replicas of n = 400 particles, beta = 1.5 (m* = 0.8586), no hops: |<m>| over the second half of the run within
+    0.03 of m* (finite-size fluctuations ~ 1/sqrt(n) average out over replicas and time); beta = 0.5: |m| ~ 0."""
+    from scipy.optimize import brentq
+    ps = dict(L=1000, xlim=1, rate_diffusion=0.0, rate_active=0.0, flip_rate_fn=None, init="fixed", N=400, scale_rates=False,
+              local_kernel_sigma=0.0, periodic=False, anchor_positions=None, site_capacity=1, crowding_suppresses_rates=False)
+    run = dict(T=30.0, obs_dt=0.5)
+    spec = la.build_beta_sweep_spec([0.5, 1.5], 256, ps, {}, run, base_seed=77)
+    res = la.run_ensemble(spec, want_profiles=False)
+    m = res.reducers[:, capi.APS_RED_M_MEAN].reshape(2, 256)
+    m_star = brentq(lambda x: x - np.tanh(1.5 * x), 0.1, 1.0)
+    assert abs(np.abs(m[1]).mean() - m_star) < 0.03, (np.abs(m[1]).mean(), m_star)
+    assert np.abs(m[0]).mean() < 0.08                   # paramagnetic side: fluctuations only
