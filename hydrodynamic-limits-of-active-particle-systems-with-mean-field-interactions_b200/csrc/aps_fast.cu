@@ -62,10 +62,12 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
                 // positions) go through the full-size kernel in a second, otherwise empty launch
                 cudaError_t e = launch_lean<21, 1056, 512, false>(a, philox, st);
                 if (e != cudaSuccess) return e;
-                *launched = 2;
                 K1Args b = a;
                 b.only_retry = 2;
-                return launch_class<21, 512, 1056>(b, philox, st);
+                e = launch_lean<21, 1056, 512, true>(b, philox, st);      // unsorted rejects: same image + site map, 22 per SM
+                if (e != cudaSuccess) return e;
+                *launched = 3;
+                return launch_class<21, 512, 1056>(b, philox, st);        // what is left (n > 488)
             }
             return launch_class<21, 512, 1056>(a, philox, st);
         }

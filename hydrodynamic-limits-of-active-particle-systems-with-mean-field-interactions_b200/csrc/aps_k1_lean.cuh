@@ -45,7 +45,8 @@ struct LeanFixed {
     uint8_t dirty_leaf[8];
 };
 
-// NCAP = 512: particles must come sorted (no site map), n <= 488, 28 replicas per SM.
+// NCAP = 512, WHO = false: particles must come sorted (no site map), n <= 488, 28 replicas per SM.
+// NCAP = 512, WHO = true: any particle order, n <= 488, 22 replicas per SM (second link of the chain for small replicas).
 // NCAP = 1024 (WHO = true): site->particle map kept (any particle order), n <= 968 (<= 8 leaves), 15 replicas per SM.
 template <int RCAP, int LPCAP, int NCAP, bool WHO>
 __host__ __device__ inline size_t k1_lean_smem_bytes() {
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     const int n = B.n[rep];
     const double beta = B.beta[rep], T = P.T, D = P.rate_diffusion, lam = P.rate_active;
 
+    if (A.only_retry == 2 && B.status[rep] != APS_RUN_RETRY_FAST) return;   // later launch of the chain: earlier rejects only
     LeanFixed<RCAP>& F = *reinterpret_cast<LeanFixed<RCAP>*>(smem_raw);
     unsigned char* dyn = smem_raw + ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15);
     double* const rates = reinterpret_cast<double*>(dyn); dyn += (size_t)NCAP * 8;
