@@ -55,7 +55,8 @@ CONFIG = dict(workload="BASELINE config 2: sweep_beta ensemble, 64 beta x 64 rep
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (every 250 ms: polling perturbs the running
+    kernels measurably — 100 ms polling cost 1.6 % of the step on a B200)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -66,7 +67,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "250"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 if self._stop_ev.is_set():
                     break
@@ -207,7 +208,8 @@ def main():
         ens.step()
     barrier()
     sampler = ClockSampler(dev.index or 0)
-    sampler.start()
+    if not os.environ.get("APS_BENCH_NO_SAMPLER"):
+        sampler.start()
     time.sleep(0.3)
     n0 = lib.aps_launch_count()
     ev_total = torch.zeros((), dtype=torch.int64, device=dev)
@@ -229,6 +231,8 @@ def main():
     k1_ms = sum(a.elapsed_time(b) for a, b in k_ev)      # K1 launches of the timed steps (events read after the final sync)
     launches = lib.aps_launch_count() - n0
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if os.environ.get("APS_BENCH_DEBUG"):
+        print(f"[rank {rank}] device-arm ms/step {float(ms) / args.steps:.2f}  K1 {sum(a.elapsed_time(b) for a, b in k_ev) / args.steps:.2f}", file=sys.stderr, flush=True)
     evs = ev_total.double().reshape(1)
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
