@@ -170,3 +170,27 @@ def assert_matches_reference(c, hr: HostRun, rep=0):
     assert np.array_equal(got, want), f"m_local differs: max abs {np.abs(got - want).max()}"
     # rows never reached stay zero in the reference (CLASS.py:466-472)
     assert not c["rho_p_list"][n_obs:].any()
+
+
+def _sha(a):
+    import hashlib
+
+    a = np.ascontiguousarray(a)
+    if a.dtype.kind == "f":
+        a = a + 0.0                      # -0.0 and +0.0 compare equal in the reference's own tests of equality
+    return hashlib.sha256(a.tobytes()).hexdigest()[:32]
+
+
+def digest_out(out):
+    """Digests of a `ParticleSystem.run()` dict (reference or drop-in): the full-length pins of
+    tests/golden/full_length.json (tools/gen_golden_full.py).  FFT arrays are post-processing of total_list by a
+    different FFT library on the device and are compared by value elsewhere, not digested."""
+    n_obs = sum(p is not None for p in out["pos_list"])
+    d = dict(n_obs=int(n_obs),
+             pos=_sha(np.stack([np.asarray(p, dtype=np.int64) for p in out["pos_list"][:n_obs]])),
+             counts=[int(x) for x in out["particle_count_list"][:n_obs]][:4])
+    for k in ["rho_p_list", "rho_m_list", "total_list", "m_local_list", "m_global"]:
+        d[k] = _sha(out[k])
+    if out.get("var_list") is not None:
+        d["var_list"] = _sha(out["var_list"])
+    return d
