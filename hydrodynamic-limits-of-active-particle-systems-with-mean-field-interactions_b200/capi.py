@@ -14,6 +14,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
 LIB_PATH = os.path.join(PKG_DIR, "csrc", "libaps_b200.so")
 
+ABI_VERSION = 5          # APS_ABI_VERSION of include/aps.h
 APS_OK = 0
 APS_ERR_INVALID, APS_ERR_NO_DEVICE, APS_ERR_CUDA, APS_ERR_CAPACITY = 1, 2, 3, 4
 APS_RUN_DONE, APS_RUN_EMPTY, APS_RUN_DRAWS_EXHAUSTED, APS_RUN_MAX_EVENTS = 0, 1, 2, 3
@@ -118,7 +119,15 @@ class ApsReduceArgs(C.Structure):
 class ApsProfileArgs(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("reps_per_point", C.c_int32), ("M", C.c_int32), ("L", C.c_int32),
                 ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("dx", C.c_double), ("n", C.c_void_p),
-                ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p), ("obs_cm", C.c_void_p), ("prof", C.c_void_p)]
+                ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p), ("obs_cm", C.c_void_p), ("prof", C.c_void_p),
+                ("point_start", C.c_void_p), ("point_reps", C.c_void_p)]
+
+
+class ApsHistArgs(C.Structure):
+    _fields_ = [("n_replicas", C.c_int32), ("M", C.c_int32), ("n_points", C.c_int32), ("n_bins", C.c_int32),
+                ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("lo", C.c_double), ("hi", C.c_double),
+                ("n", C.c_void_p), ("n_obs", C.c_void_p), ("obs_sigma_sum", C.c_void_p), ("obs_n", C.c_void_p),
+                ("point_of", C.c_void_p), ("mbar", C.c_void_p), ("hist", C.c_void_p)]
 
 
 APS_K2_MAX_TRIALS = 64
@@ -143,7 +152,7 @@ class ApsPdeArgs(C.Structure):          # include/aps_pde.h
                 ("dt", C.c_double), ("dx", C.c_double), ("xlim", C.c_double)] + \
                [(k, C.c_void_p) for k in ["beta", "lam", "gamma", "kernel", "radius", "seeds", "rho_p", "rho_m", "m_series",
                                           "var_series", "snapshots", "m_snapshots", "tracer_pos", "tracer_state",
-                                          "tracer_hist", "v_eff_series", "D_eff_series"]]
+                                          "tracer_hist", "v_eff_series", "D_eff_series", "tot_series"]]
 
 
 APS_PDE_BC = {"periodic": 0, "neumann": 1}
@@ -167,6 +176,7 @@ SYMBOLS = {
     "aps_expand_obs_device": (C.c_int, [_P(ApsExpandArgs), C.c_void_p]),
     "aps_reduce_runs_device": (C.c_int, [_P(ApsReduceArgs), C.c_void_p]),
     "aps_profile_sums_device": (C.c_int, [_P(ApsProfileArgs), C.c_void_p]),
+    "aps_m_histogram_device": (C.c_int, [_P(ApsHistArgs), C.c_void_p]),
     "aps_k2_rates_init": (C.c_int, [C.c_double, C.c_double, C.c_double, C.c_double, _P(ApsK2Rates)]),
     "aps_k2_flip_table": (C.c_int, [_P(ApsK2Rates), C.c_void_p]),
     "aps_k2_pass_device": (C.c_int, [_P(ApsK2Args), C.c_void_p]),
@@ -207,7 +217,7 @@ def load(path: str | None = None):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.aps_abi_version() != 4:
+    if lib.aps_abi_version() != ABI_VERSION:
         raise ApsError("libaps_b200.so ABI version mismatch")
     if path is None:
         _lib = lib

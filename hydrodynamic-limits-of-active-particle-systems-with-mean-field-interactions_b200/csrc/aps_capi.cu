@@ -100,10 +100,16 @@ int launch_nt(const aps::K1Args& a, bool philox, size_t smem, cudaStream_t st) {
     return APS_OK;
 }
 
+// APS_K1_THREADS (A/B knob of include/aps.h): read once at load time, never on the launch path
+const int g_env_k1_threads = [] {
+    const char* e = getenv("APS_K1_THREADS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 32 || v == 64 || v == 128 || v == 256) ? v : 0;
+}();
+
 int pick_threads(int n_max) {
     if (g_k1_threads) return g_k1_threads;
-    const char* e = getenv("APS_K1_THREADS");
-    if (e) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) return v; }
+    if (g_env_k1_threads) return g_env_k1_threads;
     return n_max > 2048 ? 128 : 64;
 }
 
@@ -130,7 +136,7 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     if (fast_ok) {
         int launched = 0;
         // single-warp CTAs (no block barriers) win for narrow update windows; wide windows (r > 30) use two warps
-        const int fnt = g_k1_threads ? nt : (getenv("APS_K1_THREADS") ? nt : (p->radius <= 30 ? 32 : 64));
+        const int fnt = (g_k1_threads || g_env_k1_threads) ? nt : (p->radius <= 30 ? 32 : 64);
         CU(aps::launch_fast(a, philox, st, g_use_fast == 1, fnt, &launched));
         if (launched) { g_launches.fetch_add(launched); a.only_retry = 1; }   // last launch: replicas violating K = 1 only
     }
@@ -335,12 +341,24 @@ int aps_reduce_runs_device(const aps_reduce_args* a, void* stream) {
 
 int aps_profile_sums_device(const aps_profile_args* a, void* stream) {
     if (!a || a->L < 1 || a->M < 1 || !a->n || !a->n_obs || !a->obs_cp || !a->obs_cm || !a->prof || a->row_hi <= a->row_lo ||
-        a->row_lo < 0 || a->row_hi > a->M || a->reps_per_point < 1)
+        a->row_lo < 0 || a->row_hi > a->M || (a->reps_per_point < 1 && !a->point_start) || (a->point_start && !a->point_reps))
         return fail(APS_ERR_INVALID, "aps_profile_sums: bad argument");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
     if (a->n_points == 0) return APS_OK;
     dim3 grid((a->L + 127) / 128, a->n_points);
     aps::profile_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
+    CU(cudaGetLastError());
+    g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+int aps_m_histogram_device(const aps_hist_args* a, void* stream) {
+    if (!a || a->M < 1 || a->n_bins < 1 || a->n_points < 1 || !a->n || !a->n_obs || !a->obs_sigma_sum || !a->hist ||
+        a->row_lo < 0 || a->row_hi > a->M || a->row_hi <= a->row_lo || !(a->hi > a->lo))
+        return fail(APS_ERR_INVALID, "aps_m_histogram: bad argument");
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (a->n_replicas == 0) return APS_OK;
+    aps::hist_kernel<<<(a->n_replicas + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*a);
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return APS_OK;

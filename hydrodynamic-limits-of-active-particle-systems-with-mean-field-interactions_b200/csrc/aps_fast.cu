@@ -7,10 +7,13 @@
 
 namespace aps {
 
+// A/B knobs of include/aps.h, read ONCE when the library is loaded (never on the launch path)
+static const int g_env_extra_smem = [] { const char* e = getenv("APS_K1_EXTRA_SMEM"); return e ? atoi(e) : 0; }();   // occupancy experiments only
+static const bool g_env_no_lean = getenv("APS_K1_NO_LEAN") != nullptr;
+
 template <int NT, int RCAP, int NCAP, int LPCAP>
 static cudaError_t launch_nt(const K1Args& a, bool philox, cudaStream_t st) {
-    const char* extra = getenv("APS_K1_EXTRA_SMEM");   // occupancy experiments only
-    const size_t smem = k1_fast_smem_bytes(a.p.L, a.b.n_max, a.p.radius, RCAP, NCAP, LPCAP) + (extra ? (size_t)atoi(extra) : 0);
+    const size_t smem = k1_fast_smem_bytes(a.p.L, a.b.n_max, a.p.radius, RCAP, NCAP, LPCAP) + (size_t)g_env_extra_smem;
     if (philox) {
         auto k = k1_fast_kernel<NT, true, RCAP, NCAP, LPCAP>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -24,10 +27,9 @@ static cudaError_t launch_nt(const K1Args& a, bool philox, cudaStream_t st) {
     }
     return cudaGetLastError();
 }
-static int g_fast_nt = 64;
 template <int RCAP, int NCAP, int LPCAP>
-static cudaError_t launch_class(const K1Args& a, bool philox, cudaStream_t st) {
-    return g_fast_nt == 32 ? launch_nt<32, RCAP, NCAP, LPCAP>(a, philox, st) : launch_nt<64, RCAP, NCAP, LPCAP>(a, philox, st);
+static cudaError_t launch_class(const K1Args& a, bool philox, cudaStream_t st, int nt) {
+    return nt == 32 ? launch_nt<32, RCAP, NCAP, LPCAP>(a, philox, st) : launch_nt<64, RCAP, NCAP, LPCAP>(a, philox, st);
 }
 
 template <int RCAP, int LPCAP, int NCAP, bool WHO>
@@ -51,13 +53,13 @@ static cudaError_t launch_lean(const K1Args& a, bool philox, cudaStream_t st) {
 // configuration does not qualify (the caller then uses the generic kernel only).
 cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched) {
     *launched = 0;
-    g_fast_nt = nt == 32 ? 32 : 64;
+    nt = nt == 32 ? 32 : 64;
     const int r1 = a.p.radius + 1, nm = a.b.n_max, lp = a.p.L + 2 * a.p.radius;
     if (k1_fast_smem_bytes(a.p.L, nm, a.p.radius, 0, 0, 0) > 227 * 1024) return cudaSuccess;
     *launched = 1;
     if (allow_static) {
         if (r1 <= 21 && nm <= 512 && lp <= 1056) {
-            if (nt == 32 && !getenv("APS_K1_NO_LEAN")) {
+            if (nt == 32 && !g_env_no_lean) {
                 // half-size shared-memory image: all replicas of an SM resident at once; its rejects (unsorted initial
                 // positions) go through the full-size kernel in a second, otherwise empty launch
                 cudaError_t e = launch_lean<21, 1056, 512, false>(a, philox, st);
@@ -67,12 +69,12 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
                 e = launch_lean<21, 1056, 512, true>(b, philox, st);      // unsorted rejects: same image + site map, 22 per SM
                 if (e != cudaSuccess) return e;
                 *launched = 3;
-                return launch_class<21, 512, 1056>(b, philox, st);        // what is left (n > 488)
+                return launch_class<21, 512, 1056>(b, philox, st, nt);        // what is left (n > 488)
             }
-            return launch_class<21, 512, 1056>(a, philox, st);
+            return launch_class<21, 512, 1056>(a, philox, st, nt);
         }
         if (r1 <= 21 && nm <= 1024 && lp <= 1056) {
-            if (nt == 32 && !getenv("APS_K1_NO_LEAN")) {
+            if (nt == 32 && !g_env_no_lean) {
                 // mid-size replicas (config 3: N = 900): trimmed image WITH the site map (any particle order), 15 instead of
                 // 10 replicas per SM; its rejects (n > 968, K = 1 violated) fall through to the full-size and generic kernels
                 cudaError_t e = launch_lean<21, 1056, 1024, true>(a, philox, st);
@@ -80,14 +82,14 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
                 *launched = 2;
                 K1Args b = a;
                 b.only_retry = 2;
-                return launch_class<21, 1024, 1056>(b, philox, st);
+                return launch_class<21, 1024, 1056>(b, philox, st, nt);
             }
-            return launch_class<21, 1024, 1056>(a, philox, st);
+            return launch_class<21, 1024, 1056>(a, philox, st, nt);
         }
-        if (r1 <= 81 && nm <= 512 && lp <= 1184) return launch_class<81, 512, 1184>(a, philox, st);
-        if (r1 <= 81 && nm <= 1024 && lp <= 1184) return launch_class<81, 1024, 1184>(a, philox, st);
+        if (r1 <= 81 && nm <= 512 && lp <= 1184) return launch_class<81, 512, 1184>(a, philox, st, nt);
+        if (r1 <= 81 && nm <= 1024 && lp <= 1184) return launch_class<81, 1024, 1184>(a, philox, st, nt);
     }
-    return launch_class<0, 0, 0>(a, philox, st);
+    return launch_class<0, 0, 0>(a, philox, st, nt);
 }
 
 }  // namespace aps

@@ -293,8 +293,9 @@ __global__ void profile_kernel(aps_profile_args a) {
     const int L = a.L, M = a.M;
     double sp = 0.0, sm = 0.0, sp2 = 0.0, sm2 = 0.0;
     const int rows = a.row_hi - a.row_lo;
-    for (int j = 0; j < a.reps_per_point; ++j) {
-        const int rep = g * a.reps_per_point + j;
+    const int j_lo = a.point_start ? a.point_start[g] : 0, j_hi = a.point_start ? a.point_start[g + 1] : a.reps_per_point;
+    for (int j = j_lo; j < j_hi; ++j) {
+        const int rep = a.point_start ? a.point_reps[j] : g * a.reps_per_point + j;
         const int n = a.n[rep];
         const double denom = (double)(n > 1 ? n : 1) * a.dx;
         int cp = 0, cm = 0;
@@ -308,6 +309,26 @@ __global__ void profile_kernel(aps_profile_args a) {
     }
     double* o = a.prof + ((size_t)g * 4) * L;
     o[l] = sp; o[L + l] = sm; o[2 * L + l] = sp2; o[3 * L + l] = sm2;
+}
+
+// One thread per replica: time-averaged m_global over a row window -> per-grid-point histogram (integer atomics).
+__global__ void hist_kernel(aps_hist_args a) {
+    const int rep = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rep >= a.n_replicas) return;
+    const int hi_row = a.row_hi < a.n_obs[rep] ? a.row_hi : a.n_obs[rep];
+    double acc = 0.0;
+    int rows = 0;
+    for (int m = a.row_lo; m < hi_row; ++m, ++rows) {
+        const int n = a.obs_n ? a.obs_n[(size_t)rep * a.M + m] : a.n[rep];
+        acc += (double)a.obs_sigma_sum[(size_t)rep * a.M + m] / (double)(n > 1 ? n : 1);
+    }
+    if (rows == 0) { if (a.mbar) a.mbar[rep] = nan(""); return; }
+    const double mb = acc / (double)rows;
+    if (a.mbar) a.mbar[rep] = mb;
+    int bin = (int)floor((mb - a.lo) / (a.hi - a.lo) * (double)a.n_bins);
+    bin = bin < 0 ? 0 : (bin >= a.n_bins ? a.n_bins - 1 : bin);
+    const int g = a.point_of ? a.point_of[rep] : 0;
+    atomicAdd(a.hist + (size_t)g * a.n_bins + bin, 1ull);
 }
 
 }  // namespace aps

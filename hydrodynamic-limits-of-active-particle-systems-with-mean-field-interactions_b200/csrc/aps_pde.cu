@@ -201,6 +201,10 @@ __global__ void __launch_bounds__(kPdeThreads, 1) pde_kernel(const __grid_consta
                 a.var_series[(size_t)run * (nsteps + 1) + n] = var;
             }
         }
+        if (a.tot_series) {                                       // rows of the per-step spectra (:247-249)
+            double* row = a.tot_series + ((size_t)run * (size_t)(nsteps + 1) + (size_t)n) * L;
+            for (int i = tid; i < L; i += kPdeThreads) row[i] = S.p[i] + S.m[i];
+        }
         if (n % a.snapshot_interval == 0) {                       // :251-254
             const size_t row = ((size_t)run * n_snap_rows + (size_t)(n / a.snapshot_interval)) * L;
             for (int i = tid; i < L; i += kPdeThreads) {

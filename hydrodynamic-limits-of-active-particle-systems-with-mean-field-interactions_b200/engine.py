@@ -15,7 +15,7 @@ import torch
 
 from . import capi
 from .batch import make_batch, make_params
-from .capi import (APS_REC_COUNTS, APS_REC_MLOCAL, APS_REC_POS, APS_RED_N, ApsExpandArgs, ApsProfileArgs,
+from .capi import (APS_REC_COUNTS, APS_REC_MLOCAL, APS_REC_POS, APS_RED_N, ApsExpandArgs, ApsHistArgs, ApsProfileArgs,
                    ApsReduceArgs)
 
 
@@ -187,3 +187,29 @@ class ReplicaBatch:
                            self.n_obs.data_ptr(), self.obs_cp.data_ptr(), self.obs_cm.data_ptr(), prof.data_ptr())
         capi.check(self.lib.aps_profile_sums_device(a, _stream()), "aps_profile_sums_device")
         return prof
+
+    def profile_sums_by_point(self, n_points, point_start, point_reps, row_lo=None, row_hi=None):
+        """Same sums with an explicit replica list per grid point (int32 device tensors, CSR layout): the replicas of a
+        rank's shard come in schedule order, not grid-point-major."""
+        row_lo = self.M // 2 if row_lo is None else row_lo
+        row_hi = self.M if row_hi is None else row_hi
+        prof = torch.empty((n_points, 4, self.L), dtype=torch.float64, device=self.dev)
+        a = ApsProfileArgs(n_points, 0, self.M, self.L, row_lo, row_hi, self.dx, self.n.data_ptr(), self.n_obs.data_ptr(),
+                           self.obs_cp.data_ptr(), self.obs_cm.data_ptr(), prof.data_ptr(), point_start.data_ptr(),
+                           point_reps.data_ptr())
+        capi.check(self.lib.aps_profile_sums_device(a, _stream()), "aps_profile_sums_device")
+        return prof
+
+    def m_histogram(self, n_points=1, point_of=None, n_bins=256, lo=-1.0, hi=1.0, row_lo=None, row_hi=None):
+        """Per-grid-point histogram (int64 [n_points][n_bins]) of the time-averaged magnetisation of every replica and
+        the per-replica values (f64 [R]); device-side accumulation (`aps_m_histogram_device`)."""
+        row_lo = self.M // 2 if row_lo is None else row_lo
+        row_hi = self.M if row_hi is None else row_hi
+        hist = torch.zeros((n_points, n_bins), dtype=torch.int64, device=self.dev)
+        mbar = torch.empty((self.R,), dtype=torch.float64, device=self.dev)
+        obs_n = getattr(self, "obs_n", None)
+        a = ApsHistArgs(self.R, self.M, n_points, n_bins, row_lo, row_hi, lo, hi, self.n.data_ptr(), self.n_obs.data_ptr(),
+                        self.obs_sigma_sum.data_ptr(), obs_n.data_ptr() if obs_n is not None else None,
+                        point_of.data_ptr() if point_of is not None else None, mbar.data_ptr(), hist.data_ptr())
+        capi.check(self.lib.aps_m_histogram_device(a, _stream()), "aps_m_histogram_device")
+        return hist, mbar

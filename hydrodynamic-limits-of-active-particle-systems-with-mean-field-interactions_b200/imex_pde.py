@@ -7,8 +7,11 @@ What is identical to the reference for a given `seed`: the initial fields and tr
 and — to rounding, see tests — every deterministic output of `solve()`: final `rho_p`/`rho_m`, `m_series`,
 `var_series`, `snapshots`, `m_snapshots`, `times`.  What is equal in distribution only: `v_eff_series` / `D_eff_series`
 (the reference draws the tracer noise from numpy's global stream inside the time loop; the kernel uses Philox).
-`fft_amp` / `fft_phase` are returned for the snapshot rows (`fft_times`), not for every step: the reference's
-(nsteps+1, L/2+1) arrays are 320 MB per run at its default sizes and only feed plots.
+`fft_amp` / `fft_phase`: `solve()` returns them for EVERY step, shape (nsteps+1, L/2+1) like the reference (:246-249;
+the kernel streams `rho_p + rho_m` of every step to HBM and one batched cuFFT transforms the rows — 320 MB per run at
+the reference's default sizes, as in the reference).  `solve_many(..., spectra="snapshots")`, the default for batches,
+returns them for the snapshot rows only (`fft_times`): a sweep of 33 runs x 80 000 steps would need 42 GB otherwise.
+`plot_all()` / `plot_individual()` are the reference's own plotting code, borrowed from its file (see `reference_class`).
 
 `solve_many(solvers)` runs any number of compatible instances (same L, dt, T, bc, model, kernel mode, tracer count)
 in ONE launch, one CTA per instance — this is how the sweep scripts' `for beta: for run:` loops map onto the GPU.
@@ -51,6 +54,7 @@ class IMEXPDE:
         self.snapshot_interval = snapshot_interval
         self.seed = seed
         self.outdir = Path(outdir)
+        self.outdir.mkdir(exist_ok=True)                        # :53
         self._rs = np.random.RandomState(seed) if seed is not None else np.random.RandomState()
         self.rho_mean = 1.0 / self.xlim
         self.kernel = None
@@ -88,12 +92,43 @@ class IMEXPDE:
         self._out = None
 
     def solve(self):
-        solve_many([self])
+        solve_many([self], spectra="all")
+
+    # ---- plotting: the reference's own code (IMEX_PDE_solver_class.py:309-461), applied to this instance ----
+    def plot_all(self, *a, **k):
+        return reference_class().plot_all(self, *a, **k)
+
+    def plot_individual(self, *a, **k):
+        return reference_class().plot_individual(self, *a, **k)
 
     def get_output(self):
         if self._out is None:
             raise RuntimeError("call solve() first")
         return dict(self._out)
+
+
+_REF_CLASS = None
+
+
+def reference_class():
+    """The reference's `IMEXPDE` loaded under a private module name from $APS_REFERENCE_PATH, <repo>/baseline/_ref or
+    /root/reference; only its plot methods are used (they read the attributes solve() fills in)."""
+    global _REF_CLASS
+    if _REF_CLASS is None:
+        import importlib.util
+        import os
+        for d in (os.environ.get("APS_REFERENCE_PATH"), os.path.join(capi.REPO_ROOT, "baseline", "_ref"), "/root/reference"):
+            f = os.path.join(d, "IMEX_PDE_solver_class.py") if d else None
+            if f and os.path.exists(f):
+                spec = importlib.util.spec_from_file_location("_aps_reference_IMEX_PDE_solver_class", f)
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)                    # needs matplotlib, like the reference
+                _REF_CLASS = mod.IMEXPDE
+                break
+        else:
+            raise RuntimeError("plot_all / plot_individual are delegated to the reference's code: set APS_REFERENCE_PATH "
+                               "to a directory holding IMEX_PDE_solver_class.py (or run tools/install_reference.py)")
+    return _REF_CLASS
 
 
 def _same(solvers, attr):
@@ -103,9 +138,10 @@ def _same(solvers, attr):
     return vals.pop()
 
 
-def solve_many(solvers, device=None):
+def solve_many(solvers, device=None, spectra="snapshots"):
     """Run every instance of `solvers` through its nsteps steps in one kernel launch (one CTA per instance) and
-    attach the reference's output dict to each (`get_output()`)."""
+    attach the reference's output dict to each (`get_output()`).  spectra="all": fft_amp / fft_phase for every step
+    (the reference's shapes); "snapshots": for the snapshot rows only."""
     import torch
 
     if not torch.cuda.is_available():
@@ -141,8 +177,14 @@ def solve_many(solvers, device=None):
                            tracer_pos=ptr(tpos) if ntr else None, tracer_state=ptr(tstate) if ntr else None,
                            tracer_hist=ptr(hist) if ntr else None, v_eff_series=ptr(v_eff) if ntr else None,
                            D_eff_series=ptr(d_eff) if ntr else None)
+    tot_series = z(R, nsteps + 1, L) if spectra == "all" else None
+    args.tot_series = ptr(tot_series)
     capi.check(lib.aps_pde_solve_device(args, torch.cuda.current_stream().cuda_stream), "aps_pde_solve_device")
-    fft = torch.fft.rfft(snaps, dim=-1) / L                    # spectra of the snapshot rows (:247-249 per step there)
+    if spectra == "all":                                       # :247-249, every step
+        fft = torch.cat([torch.fft.rfft(tot_series[:, i:i + 8192], dim=-1) / L for i in range(0, nsteps + 1, 8192)], dim=1)
+        del tot_series
+    else:
+        fft = torch.fft.rfft(snaps, dim=-1) / L                # spectra of the snapshot rows only
     h = lambda t: t.cpu().numpy()
     rho_p_h, rho_m_h, m_h, var_h, snaps_h, msnaps_h, fft_h = map(h, (rho_p, rho_m, m_series, var_series, snaps, msnaps, fft))
     times = np.arange(n_snap) * interval * dt
@@ -154,9 +196,11 @@ def solve_many(solvers, device=None):
             s.tracers_unwrapped = tpos[r].cpu().numpy()
             s.tracers = s.tracers_unwrapped % s.xlim
             s.tracer_state = tstate[r].cpu().numpy().astype(int)
+        s.fft_amp, s.fft_phase = np.abs(fft_h[r]), fft_h[r]    # attributes the reference's plot methods read
+        s.snapshots, s.m_snapshots, s.times = list(snaps_h[r]), list(msnaps_h[r]), list(times)
         s.v_eff_series = v_eff[r].cpu().numpy() if ntr > 0 else nan_series.copy()
         s.D_eff_series = d_eff[r].cpu().numpy() if ntr > 0 else nan_series.copy()
         s._out = dict(rho_p=s.rho_p, rho_m=s.rho_m, m_series=s.m_series, var_series=s.var_series,
-                      fft_amp=np.abs(fft_h[r]), fft_phase=fft_h[r], fft_times=times, snapshots=snaps_h[r],
+                      fft_amp=np.abs(fft_h[r]), fft_phase=fft_h[r], fft_times=times if spectra != "all" else np.arange(nsteps + 1) * dt, snapshots=snaps_h[r],
                       m_snapshots=msnaps_h[r], times=times, v_eff_series=s.v_eff_series, D_eff_series=s.D_eff_series)
     return solvers

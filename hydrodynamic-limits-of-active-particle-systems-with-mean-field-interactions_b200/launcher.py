@@ -160,6 +160,8 @@ class EnsembleResult:
     n_particles: np.ndarray           # [R]
     profiles: np.ndarray | None       # [points][4][L] sums over the point's replicas (all ranks)
     reps_per_point: np.ndarray | None
+    m_hist: np.ndarray | None = None  # [points][256] histogram of the per-replica time-averaged magnetisation on [-1, 1] (all ranks)
+    mbar: np.ndarray | None = None    # [R] the per-replica values themselves
     info: dict = field(default_factory=dict)
 
 
@@ -229,8 +231,13 @@ class DeviceEnsemble:
                                sigma0=self.sigma0, seeds=self.seeds, record=spec.record, crowding=mp["crowding"],
                                device=self.dev.index, dx=mp["dx"], periodic=mp["periodic"])
         self.h2d_bytes += (self.rb.times_obs.numel() + self.rb.beta.numel() + (self.rb.weights.numel() if self.rb.weights is not None else 0)) * 8
-        self.point_local = torch.as_tensor(np.asarray(spec.point_of[sl], dtype=np.int64)).to(self.dev)
         self.n_points = int(spec.point_of.max()) + 1 if len(spec.point_of) else 0
+        # replica lists per grid point (CSR) for the device-side per-point sums: the shard is in schedule order
+        pl = np.asarray(spec.point_of[sl], dtype=np.int64)
+        by_point = np.argsort(pl, kind="stable")
+        self.point_of = upc(pl, np.int32)
+        self.point_reps = upc(by_point, np.int32)
+        self.point_start = upc(np.searchsorted(pl[by_point], np.arange(self.n_points + 1)), np.int32)
 
     def init_particles(self):
         mp = self.mp
@@ -244,22 +251,22 @@ class DeviceEnsemble:
         capi.check(self.lib.aps_init_particles_device(a, _stream()), "aps_init_particles_device")
 
     def step(self, want_profiles=True):
-        """init -> K1 -> per-run reducers (-> per-point profile sums).  All on the device, no sync."""
+        """init -> K1 -> per-run reducers, magnetisation histogram (-> per-point profile sums).  Hand-written kernels
+        only, all on the device, no sync."""
         self.init_particles()
         self.rb.run_philox()
         self.red = self.rb.reduce()
+        self.hist, self.mbar = self.rb.m_histogram(max(1, self.n_points), self.point_of)     # [points][256] int64, [R]
         self.prof = None
         if want_profiles and self.n_points:
-            per_rep = self.rb.profile_sums(1)                       # [R][4][L]
-            self.prof = torch.zeros((self.n_points, 4, self.mp["L"]), dtype=torch.float64, device=self.dev)
-            self.prof.index_add_(0, self.point_local, per_rep)
+            self.prof = self.rb.profile_sums_by_point(self.n_points, self.point_start, self.point_reps)   # [points][4][L]
         return self
 
     def pack_scalars(self):
-        """[R][APS_RED_N + 3] f64: reducers, n_events, status, n — the only per-replica D2H payload."""
+        """[R][APS_RED_N + 4] f64: reducers, n_events, status, n, time-averaged m — the only per-replica D2H payload."""
         rb = self.rb
         return torch.cat([self.red, rb.n_events.double()[:, None], rb.status.double()[:, None],
-                          self.n.double()[:, None]], dim=1)
+                          self.n.double()[:, None], self.mbar[:, None]], dim=1)
 
 
 def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_cls=None) -> EnsembleResult:
@@ -274,6 +281,7 @@ def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_c
     ens.step(want_profiles=want_profiles)
     scal = ens.pack_scalars()
     prof = ens.prof
+    hist = getattr(ens, "hist", None)
     if world > 1:
         width = scal.shape[1]
         most = shard_bounds(Rtot, 0, world)[1]
@@ -288,18 +296,22 @@ def run_ensemble(spec: EnsembleSpec, want_profiles=True, device=None, ensemble_c
         scal = torch.cat(parts, dim=0)
         if prof is not None:
             torch.distributed.all_reduce(prof, op=torch.distributed.ReduceOp.SUM)
+        if hist is not None:
+            torch.distributed.all_reduce(hist, op=torch.distributed.ReduceOp.SUM)
     scal_h = np.empty(tuple(scal.shape), dtype=np.float64)
     scal_h[order] = scal.cpu().numpy()             # back to the caller's replica order
     prof_h = prof.cpu().numpy() if prof is not None else None
     reps = np.bincount(np.asarray(spec.point_of, dtype=np.int64)) if len(spec.point_of) else None
     info = dict(rank=rank, world=world, shard=(lo, hi), n_max=ens.n_max, h2d_bytes=ens.h2d_bytes,
-                d2h_bytes=int(scal.numel() * 8 + (prof.numel() * 8 if prof is not None else 0)), M=ens.rb.M)
+                d2h_bytes=int(scal.numel() * 8 + (prof.numel() * 8 if prof is not None else 0) +
+                              (hist.numel() * 8 if hist is not None else 0)), M=ens.rb.M)
     n_part = scal_h[:, APS_RED_N + 2].astype(np.int64)
     if (n_part < 0).any():
         raise capi.ApsError("initial sample exceeded n_max; raise the particle bound")
     return EnsembleResult(reducers=scal_h[:, :APS_RED_N], n_events=scal_h[:, APS_RED_N].astype(np.int64),
                           status=scal_h[:, APS_RED_N + 1].astype(np.int32), n_particles=n_part, profiles=prof_h,
-                          reps_per_point=reps, info=info)
+                          reps_per_point=reps, info=info, m_hist=hist.cpu().numpy() if hist is not None else None,
+                          mbar=scal_h[:, APS_RED_N + 3] if scal_h.shape[1] > APS_RED_N + 3 else None)
 
 
 # ---- reference-shaped entry points -------------------------------------------------------------
@@ -321,11 +333,24 @@ def _mean_std_se(x):
     return mean, std, std / np.sqrt(max(1, x.size))
 
 
-def build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, base_seed=0):
+def replica_seeds(point_of, run_idx, base_seed=None):
+    """Philox keys of the replicas (they also key the device-side initial conditions).
+    base_seed=None (the default of every sweep entry point): fresh OS entropy, independent streams for every replica
+    and every call — what the reference does with `rng=None` (sweep_beta.py:77-83 -> default_rng(), CLASS.py:75-76).
+    base_seed=int: reproducible, seed = base + stride * point + run with stride = max(10 000, runs per point), so
+    that keys cannot collide inside a sweep (seed = 10 000 * beta_idx + replica_idx for config 2)."""
+    point_of, run_idx = np.asarray(point_of, dtype=np.uint64), np.asarray(run_idx, dtype=np.uint64)
+    if base_seed is None:
+        return np.random.SeedSequence().generate_state(len(point_of), np.uint64)
+    stride = np.uint64(max(10_000, int(run_idx.max()) + 1 if len(run_idx) else 1))
+    return np.uint64(base_seed) + stride * point_of + run_idx
+
+
+def build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, base_seed=None):
     betas = np.repeat(np.asarray(beta_values, dtype=float), n_runs_per_beta)
     point_of = np.repeat(np.arange(len(beta_values)), n_runs_per_beta)
     run_idx = np.tile(np.arange(n_runs_per_beta), len(beta_values))
-    seeds = (np.uint64(base_seed) + np.uint64(10_000) * point_of.astype(np.uint64) + run_idx.astype(np.uint64))
+    seeds = replica_seeds(point_of, run_idx, base_seed)
     ps = dict(ps_kwargs)
     kw = {}
     if ps.get("init", "fixed") == "poisson":
@@ -335,7 +360,7 @@ def build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, 
 
 
 def sweep_over_betas(beta_values, n_runs_per_beta=10, ps_kwargs=None, init_kwargs=None, run_kwargs=None,
-                     base_seed=0, want_profiles=True, ensemble_cls=None):
+                     base_seed=None, want_profiles=True, ensemble_cls=None):
     """All (beta, run) replicas in one sharded launch; returns the arrays the reference's
     sweep_over_betas collects (sweep_beta.py:880-931), keyed like its save_dict."""
     spec = build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs or {}, init_kwargs or {}, run_kwargs or {},
@@ -355,6 +380,10 @@ def sweep_over_betas(beta_values, n_runs_per_beta=10, ps_kwargs=None, init_kwarg
     out["outs"] = []          # per-run dicts stay on the device; the reducers above replace them
     out["n_events"] = res.n_events.reshape(nb, n_runs_per_beta)
     out["status"] = res.status.reshape(nb, n_runs_per_beta)
+    if res.m_hist is not None:      # device-side histogram of the per-run time-averaged magnetisation, 256 bins on [-1, 1]
+        out["m_hist"], out["m_hist_edges"] = res.m_hist, np.linspace(-1.0, 1.0, res.m_hist.shape[1] + 1)
+    if res.mbar is not None:
+        out["m_bar"] = res.mbar.reshape(nb, n_runs_per_beta)
     if res.profiles is not None:
         reps = float(n_runs_per_beta)
         out["rho_plus_profile_mean"] = res.profiles[:, 0] / reps
@@ -394,7 +423,7 @@ def init_distributed_from_env():
 
 # ---- (N_part, beta) double sweep: ..._double_sweep.py:851-873 -------------------------------------
 def build_double_sweep_spec(n_part_values, beta_values, n_runs, ps_kwargs, run_kwargs, frac_plus=0.75, decay_plus=0.2,
-                            decay_minus=0.2, base_seed=0):
+                            decay_minus=0.2, base_seed=None):
     """Grid points ordered N_part-major, beta-minor (the order of the reference's nested loops); every
     density gets its own Poisson intensity profile (make_exp_gradient with N = N_part)."""
     n_part_values = [int(v) for v in n_part_values]
@@ -409,7 +438,7 @@ def build_double_sweep_spec(n_part_values, beta_values, n_runs, ps_kwargs, run_k
     point_of = np.repeat(point, n_runs)
     profile_of = np.repeat(np.repeat(np.arange(len(n_part_values)), nb), n_runs).astype(np.int32)
     run_idx = np.tile(np.arange(n_runs), len(point))
-    seeds = np.uint64(base_seed) + np.uint64(10_000) * point_of.astype(np.uint64) + run_idx.astype(np.uint64)
+    seeds = replica_seeds(point_of, run_idx, base_seed)
     ps = dict(ps_kwargs, init="poisson")
     return EnsembleSpec(ps_kwargs=ps, run_kwargs=dict(run_kwargs), betas=betas, point_of=point_of, seeds=seeds,
                         profiles_plus=prof_p, profiles_minus=prof_m, profile_of=profile_of)
@@ -440,7 +469,7 @@ from .structure import structure_observables, fft_amplitudes      # noqa: E402  
 
 
 def sweep_betas_for_structures(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, start_fraction=0.5,
-                               k_max=None, base_seed=0, keep_raw=True, k_keep=64):
+                               k_max=None, base_seed=None, keep_raw=True, k_keep=64):
     """Drop-in for local_structure.py:167-193: dict keyed by beta with the ensemble keys of
     sweep_beta_structure_ensemble (:105-165).  `raw` holds one entry per run with the per-run observables and a light
     `out` dict (`times_obs`, `fft_amp_list` restricted to the first `k_keep` modes, `var_list`, `m_global`) — enough
@@ -483,15 +512,17 @@ def sweep_betas_for_structures(beta_values, n_runs_per_beta, ps_kwargs, init_kwa
 
 
 def sweep_over_sigmas(sigma_values, beta_values, n_runs_per_beta=5, ps_kwargs=None, init_kwargs=None, run_kwargs=None,
-                      base_seed=0, save_dir=None):
+                      base_seed=None, save_dir=None):
     """Drop-in for sweep_beta_2.py:1030-1075: one beta sweep per interaction width sigma (each sigma is its own launch
     group: the filter radius differs), results keyed by sigma with the reference's keys; with `save_dir` every sigma
     is also written to `v_eff_vs_beta_sigma_<sigma>.npz` under the reference's key names (:1059-1067)."""
     import os
     results = {}
-    for sigma in sigma_values:
+    for si, sigma in enumerate(sigma_values):
         ps = dict(ps_kwargs or {}, local_kernel_sigma=float(sigma))
-        sd = sweep_over_betas(beta_values, n_runs_per_beta, ps, init_kwargs, run_kwargs, base_seed=base_seed,
+        # every sigma gets its own streams (a reproducible base_seed is offset per sigma; None = fresh entropy per sweep)
+        seed_s = None if base_seed is None else int(base_seed) + si * 1_000_003 * max(10_000, n_runs_per_beta)
+        sd = sweep_over_betas(beta_values, n_runs_per_beta, ps, init_kwargs, run_kwargs, base_seed=seed_s,
                               want_profiles=False)
         results[sigma] = {"beta": np.asarray(beta_values, dtype=float), "v_mean": sd["means"], "v_se": sd["ses"],
                           "D_mean": sd["D_means"], "D_se": sd["D_ses"], "ps_kwargs": sd["ps_kwargs"]}

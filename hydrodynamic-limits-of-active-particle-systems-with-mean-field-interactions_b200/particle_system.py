@@ -44,6 +44,43 @@ class PhiloxRNG:
     def poisson(self, *a, **k):
         return self._gen.poisson(*a, **k)
 
+    # single-step entry (`step_gillespie`) draws its variates on the host like the reference does (CLASS.py:358-362,378)
+    def exponential(self, *a, **k):
+        return self._gen.exponential(*a, **k)
+
+    def random(self, *a, **k):
+        return self._gen.random(*a, **k)
+
+
+_REF_CLASS = None
+
+
+def reference_class():
+    """The reference's own `ParticleSystem` (PARTICLE_solver_CLASS.py), loaded under a private module name from
+    $APS_REFERENCE_PATH, <repo>/baseline/_ref (tools/install_reference.py) or /root/reference.  Only the plotting /
+    animation methods (CLASS.py:561-1093, out of scope for the CUDA path: they post-process the `out` dict) are
+    borrowed from it; it needs matplotlib and vispy like the reference itself."""
+    global _REF_CLASS
+    if _REF_CLASS is not None:
+        return _REF_CLASS
+    import importlib.util
+    cands = [os.environ.get("APS_REFERENCE_PATH"), os.path.join(capi.REPO_ROOT, "baseline", "_ref"), "/root/reference"]
+    for d in cands:
+        f = os.path.join(d, "PARTICLE_solver_CLASS.py") if d else None
+        if f and os.path.exists(f):
+            spec = importlib.util.spec_from_file_location("_aps_reference_PARTICLE_solver_CLASS", f)
+            mod = importlib.util.module_from_spec(spec)
+            try:
+                spec.loader.exec_module(mod)
+            except ImportError as e:
+                raise ImportError(f"the reference's plotting code at {f} could not be imported ({e}); it needs "
+                                  "matplotlib and vispy exactly like the reference does") from e
+            _REF_CLASS = mod.ParticleSystem
+            return _REF_CLASS
+    raise RuntimeError("visualize_all / plot_individuals / animate_profiles are the reference's own post-processing of "
+                       "the `out` dict and are delegated to its code: set APS_REFERENCE_PATH to a directory holding the "
+                       "reference's PARTICLE_solver_CLASS.py (or run tools/install_reference.py)")
+
 
 class ParticleSystem:
     def __init__(self, L, xlim, rate_diffusion, rate_active, beta, flip_rate_fn=None, init="fixed", N=1000,
@@ -85,10 +122,12 @@ class ParticleSystem:
         self.anchor_radius = anchor_radius
         # anchor sites: positions -> lattice indices within anchor_radius (CLASS.py:88-104)
         self.is_anchor_site = np.zeros(self.L, dtype=bool)
+        self.anchor_idx_array = np.array([], dtype=int)
         if anchor_positions is None:
             self.anchor_positions = None
             self.anchor_idxs = np.array([], dtype=int)
         else:
+            self.anchor_positions = anchor_positions
             ap = np.asarray(anchor_positions, dtype=float)
             self.anchor_idxs = np.unique(np.round((ap / self.xlim) * (self.L - 1)).astype(int))
             r_idx = int(np.ceil(anchor_radius / self.dx))
@@ -296,13 +335,30 @@ class ParticleSystem:
                 head = draws[used:used + 3]
             prefix = np.concatenate([head, [rng.random()]])
 
+    # ---- plotting / animation: the reference's own post-processing of `out`, borrowed from its code ----
+    def visualize_all(self, out, *args, **kwargs):
+        """CLASS.py:561-661 (delegated to the reference's implementation, see reference_class())."""
+        return reference_class().visualize_all(self, out, *args, **kwargs)
+
+    def plot_individuals(self, out, *args, **kwargs):
+        """CLASS.py:663-978 (delegated; returns the reference's `mean_v_eff`)."""
+        return reference_class().plot_individuals(self, out, *args, **kwargs)
+
+    def animate_profiles(self, out, *args, **kwargs):
+        """CLASS.py:980-1093 (delegated)."""
+        return reference_class().animate_profiles(self, out, *args, **kwargs)
+
     def step_gillespie(self, pos, sigma, bound, m_field, counts_p, counts_m, init_bin, exit_times,
                        exit_positions, exit_init_bin, t):
         """One event (CLASS.py:254-448) on the device.  Arrays are updated in place and returned like the
-        reference does; `m_field` is honoured as given (it is an input of the reference's step)."""
+        reference does; `m_field` is honoured as given (it is an input of the reference's step).
+        Systems with anchors (bind / unbind / exit events, `bound` flags) are supported by `run()` only."""
         n = sigma.size
         if n == 0:
             return pos, sigma, bound, np.inf, counts_p, counts_m
+        if self._has_anchors:
+            raise NotImplementedError("step_gillespie: the single-step entry does not carry anchor binding state; "
+                                      "use run() for systems with anchor_positions (CLASS.py:307-348,418-436)")
         from .engine import ReplicaBatch
         import torch
 

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define APS_ABI_VERSION 4
+#define APS_ABI_VERSION 5
 
 typedef enum aps_status {
     APS_OK = 0,
@@ -241,8 +241,10 @@ typedef struct aps_reduce_args {
 } aps_reduce_args;
 int aps_reduce_runs_device(const aps_reduce_args* a, void* stream);
 
-/* ensemble profile sums per grid point (replicas grid-point-major); prof is [n_points][4][L]:
- * sum of time-averaged rho_plus, rho_minus over the point's replicas, and the sums of their squares */
+/* ensemble profile sums per grid point; prof is [n_points][4][L]: sum of time-averaged rho_plus, rho_minus
+ * over the point's replicas, and the sums of their squares.  Replica membership: either grid-point-major
+ * (replica = g*reps_per_point + j; point_start == NULL) or an explicit list per point (any replica order,
+ * e.g. a rank's strided shard of a sweep): replicas point_reps[point_start[g] .. point_start[g+1]). */
 typedef struct aps_profile_args {
     int32_t n_points, reps_per_point, M, L;
     int32_t row_lo, row_hi;
@@ -252,8 +254,29 @@ typedef struct aps_profile_args {
     const int8_t* obs_cp;
     const int8_t* obs_cm;
     double* prof;
+    const int32_t* point_start; /* [n_points+1] optional                                          */
+    const int32_t* point_reps;  /* [point_start[n_points]] replica indices, ascending per point   */
 } aps_profile_args;
 int aps_profile_sums_device(const aps_profile_args* a, void* stream);
+
+/* Histogram of the per-replica time-averaged magnetisation (BASELINE north_star: "density and magnetisation
+ * profile and histogram accumulation stays on device"; the sample of the KS test of the native-mode parity check).
+ * mbar[r] = mean over rows [row_lo, min(row_hi, n_obs[r])) of m_global = sum(sigma)/n (CLASS.py:526, the quantity
+ * compute_mean_magnetizatoin averages, sweep_beta.py:316-319); bin = floor((mbar - lo) / (hi - lo) * n_bins)
+ * clamped to [0, n_bins-1]; hist[point_of[r]][bin] += 1 (integer atomics: order-independent, all-reducible). */
+typedef struct aps_hist_args {
+    int32_t n_replicas, M, n_points, n_bins;
+    int32_t row_lo, row_hi;
+    double lo, hi;                  /* histogram range, normally [-1, 1]                           */
+    const int32_t* n;               /* [n_replicas]                                               */
+    const int32_t* n_obs;           /* [n_replicas]                                               */
+    const int32_t* obs_sigma_sum;   /* [n_replicas][M]                                            */
+    const int32_t* obs_n;           /* [n_replicas][M] optional per-row particle count (exits)    */
+    const int32_t* point_of;        /* [n_replicas] optional grid point of every replica (else 0) */
+    double* mbar;                   /* [n_replicas] optional                                      */
+    unsigned long long* hist;       /* [n_points][n_bins], accumulated into (caller zeroes)       */
+} aps_hist_args;
+int aps_m_histogram_device(const aps_hist_args* a, void* stream);
 
 /* ---- K2: sublattice-parallel kernel for one lattice too large for shared memory -------------- */
 #include "aps_k2_model.h"

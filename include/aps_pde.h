@@ -59,6 +59,8 @@ typedef struct aps_pde_args {
     double* tracer_hist;        /* [n_runs][window][n_tracers] scratch ring of unwrapped positions          */
     double* v_eff_series;       /* [n_runs][nsteps+1], NaN where undefined (:274-282)                       */
     double* D_eff_series;       /* [n_runs][nsteps+1]                                                       */
+    double* tot_series;         /* [n_runs][nsteps+1][L] rho_p + rho_m of EVERY step, or NULL: input of the per-step
+                                   spectra fft_amp / fft_phase of solve() (:247-249), transformed by the caller    */
 } aps_pde_args;
 
 /* Runs every instance from its initial state through nsteps steps (device pointers, enqueued on `stream`). */

@@ -15,7 +15,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def case_names():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
-    return [n for n in names if not n.startswith(("stat_", "pde_"))]
+    return [n for n in names if not n.startswith(("stat_", "pde_", "full_"))]
 
 
 def load_case(name):
@@ -41,7 +41,7 @@ class HostRun:
 
     def __init__(self, L, n_max, M, n, pos0, sigma0, beta, times_obs, weights, draws=None, draw_off=None,
                  seeds=None, record=7, trace_cap=0, max_events=0, t_start=None, obs_start=None, ev_start=None,
-                 anchor_mask=None, bound0=None, exit_cap=0):
+                 anchor_mask=None, bound0=None, exit_cap=0, alloc_m_local=True):
         R = len(n)
         self.R, self.L, self.n_max, self.M = R, L, n_max, M
         self.n = np.ascontiguousarray(n, dtype=np.int32)
@@ -61,7 +61,7 @@ class HostRun:
         self.obs_cm = np.full((R, Mr, L), -7, np.int8)
         self.obs_pos = np.full((R, Mr, n_max), -1, np.int32)
         self.obs_sigma_sum = np.full((R, Mr), -99999, np.int32)
-        self.obs_m_local = np.full((R, Mr, L), np.nan, np.float64)
+        self.obs_m_local = np.full((R, Mr, L), np.nan, np.float64) if alloc_m_local else None   # 8 B/site/row: skip for big batches
         self.n_obs = np.zeros(R, np.int32)
         self.n_events = np.zeros(R, np.int64)
         self.t_end = np.zeros(R, np.float64)

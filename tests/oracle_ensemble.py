@@ -64,6 +64,7 @@ class OracleEnsemble:
         red = np.zeros((self.R, capi.APS_RED_N))
         L, dx, M = mp["L"], mp["dx"], len(self.times_obs)
         prof = np.zeros((self.n_points, 4, L))
+        mbar = np.zeros(self.R); hist = np.zeros((max(1, self.n_points), 256), np.int64)
         for r in range(self.R):
             nobs, nn = int(hr.n_obs[r]), int(n[r])
             denom = float(max(1, nn)) * dx
@@ -77,12 +78,16 @@ class OracleEnsemble:
             d_eff = rn.d_eff_active(self.times_obs, pos_list, dx, si, ei) if nobs >= ei else np.nan
             red[r] = [mean_v, d_eff, rn.mean_magnetisation(mg, si, ei), rn.rho_eff(total, si, ei),
                       rn.blocking_probability(total, rho_p, si, ei), si, ei, nobs]
+            mbar[r] = mg[M // 2:nobs].sum() / max(1, nobs - M // 2)        # aps_m_histogram_device: rows [M/2, n_obs)
+            b = int(np.floor((mbar[r] + 1.0) / 2.0 * 256))
+            hist[int(spec.point_of[self.lo + r]), min(255, max(0, b))] += 1
             if want_profiles:
                 lo_r, hi_r = M // 2, M
                 g = int(spec.point_of[self.lo + r])
                 mp_, mm_ = rho_p[lo_r:hi_r].mean(0), rho_m[lo_r:hi_r].mean(0)
                 prof[g, 0] += mp_; prof[g, 1] += mm_; prof[g, 2] += mp_ ** 2; prof[g, 3] += mm_ ** 2
         self.red = red
+        self.mbar, self.hist = mbar, torch.from_numpy(hist)
         self.n = n
         self.prof = torch.from_numpy(prof) if want_profiles else None
         return self
@@ -90,4 +95,5 @@ class OracleEnsemble:
     def pack_scalars(self):
         hr = self.hr
         return torch.from_numpy(np.concatenate([self.red, hr.n_events[:, None].astype(float),
-                                                hr.status[:, None].astype(float), self.n[:, None].astype(float)], axis=1))
+                                                hr.status[:, None].astype(float), self.n[:, None].astype(float),
+                                                self.mbar[:, None]], axis=1))

@@ -33,14 +33,15 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, n), f"{n} declared in include/aps.h but not exported"
         assert n in capi.SYMBOLS, f"{n} has no ctypes prototype in capi.py"
     assert sorted(capi.SYMBOLS) == names
-    assert lib.aps_abi_version() == 4
+    assert lib.aps_abi_version() == capi.ABI_VERSION == 5
 
 
 def test_struct_layout_matches_header(lib):
     # sizes the C compiler gives the two descriptors (x86-64 SysV): 4 int32 + 6 double; 4 int32 + 3 int64 + 36 pointers + exit_cap
     assert C.sizeof(capi.ApsParams) == 64
     assert C.sizeof(capi.ApsBatch) == 16 + 24 + 36 * 8 + 8
-    assert C.sizeof(capi.ApsPdeArgs) == 8 * 4 + 8 + 3 * 8 + 17 * 8      # include/aps_pde.h
+    assert C.sizeof(capi.ApsPdeArgs) == 8 * 4 + 8 + 3 * 8 + 18 * 8      # include/aps_pde.h
+    assert C.sizeof(capi.ApsProfileArgs) == 6 * 4 + 8 + 7 * 8 and C.sizeof(capi.ApsHistArgs) == 6 * 4 + 2 * 8 + 7 * 8
 
 
 def test_invalid_arguments_are_rejected(lib):
