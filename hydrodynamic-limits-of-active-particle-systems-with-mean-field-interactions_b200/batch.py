@@ -42,6 +42,7 @@ _FIELDS = {
     "exit_t": "float64",
     "exit_pos": "int32",
     "n_exit": "int32",
+    "flip_tab": "float64",
 }
 
 
@@ -66,7 +67,7 @@ def make_params(L, K, radius, D, lam, T, flags=0, k_on=0.0, k_off=0.0, k_exit=0.
                      float(k_exit))
 
 
-def make_batch(n_replicas, n_max, M, record=0, max_events=0, trace_cap=0, spec_from=-1, exit_cap=0, **arrays):
+def make_batch(n_replicas, n_max, M, record=0, max_events=0, trace_cap=0, spec_from=-1, exit_cap=0, flip_G=0, **arrays):
     """Returns (ApsBatch, keepalive list).  uint64 seeds may be passed as int64 torch tensors
     (torch has limited uint64 support); the bit pattern is what matters."""
     b = ApsBatch()
@@ -74,6 +75,7 @@ def make_batch(n_replicas, n_max, M, record=0, max_events=0, trace_cap=0, spec_f
     b.record, b.max_events, b.trace_cap = int(record), int(max_events), int(trace_cap)
     b.spec_from = int(spec_from)
     b.exit_cap = int(exit_cap)
+    b.flip_G = int(flip_G)
     keep = []
     for name, arr in arrays.items():
         if name not in _FIELDS:

@@ -85,6 +85,8 @@ class ApsBatch(C.Structure):
         ("exit_pos", C.c_void_p),
         ("n_exit", C.c_void_p),
         ("exit_cap", C.c_int64),
+        ("flip_tab", C.c_void_p),
+        ("flip_G", C.c_int64),
     ]
 
 

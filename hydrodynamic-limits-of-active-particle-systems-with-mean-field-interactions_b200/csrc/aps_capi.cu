@@ -81,6 +81,7 @@ int validate(const aps_params* p, const aps_batch* b, bool philox) {
         return fail(APS_ERR_INVALID, "periodic field needs 2*radius+1 <= L (truncate the ring kernel)");
     if (philox && !b->seeds) return fail(APS_ERR_INVALID, "seeds required in native (Philox) mode");
     if (!philox && (!b->draws || !b->draw_off)) return fail(APS_ERR_INVALID, "draws/draw_off required in replay mode");
+    if (b->flip_tab && b->flip_G < 1) return fail(APS_ERR_INVALID, "flip_tab needs flip_G >= 1 (grid m_k = -1 + 2k/flip_G)");
     return APS_OK;
 }
 
@@ -132,7 +133,7 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     a.only_retry = 0; a.reserved = 0;
     // specialised kernel for K = 1 with a local field (every shipped sweep configuration)
     const bool fast_ok = g_use_fast && p->K == 1 && p->radius >= 0 && p->radius < p->L && !(p->flags & (APS_FLAG_CROWDING | APS_FLAG_PERIODIC)) &&
-                         !b->m_field_in && !b->anchor_mask && b->n_max <= 1024 && b->status != nullptr;
+                         !b->m_field_in && !b->anchor_mask && !b->flip_tab && b->n_max <= 1024 && b->status != nullptr;
     if (fast_ok) {
         int launched = 0;
         // single-warp CTAs (no block barriers) win for narrow update windows; wide windows (r > 30) use two warps
@@ -232,6 +233,7 @@ int run_host(const aps_params* p, const aps_batch* hb, bool philox) {
     TRY(s.in(hb->m_field_in, R * L * 8, (const void**)&d.m_field_in));
     TRY(s.in(hb->anchor_mask, L, (const void**)&d.anchor_mask));
     TRY(s.in(hb->bound0, R * NM, (const void**)&d.bound0));
+    TRY(s.in(hb->flip_tab, hb->flip_tab ? 2 * (size_t)(hb->flip_G + 1) * 8 : 0, (const void**)&d.flip_tab));
     TRY(s.out(hb->n_end, R * 4, (void**)&d.n_end, false));
     TRY(s.out(hb->bound_end, R * NM, (void**)&d.bound_end));
     TRY(s.out(hb->obs_n, R * M * 4, (void**)&d.obs_n));

@@ -87,6 +87,8 @@ struct Smem {
     int8_t* bound;        // bound flags (anchors only; all zero otherwise)
     uint8_t* anchor;      // is_anchor_site, or nullptr when the batch has no anchors
     const double* m_in;   // optional injected field (global memory), see aps_batch.m_field_in
+    const double* flip_tab;   // optional tabulated flip_rate_fn (global memory, read through L1), see aps_batch.flip_tab
+    int64_t flip_G;
     int periodic;         // APS_FLAG_PERIODIC: the halo holds wrapped images and hops wrap
 };
 
@@ -256,7 +258,7 @@ __device__ __forceinline__ double particle_rate(const Smem& s, const aps_params&
     double cv = 0.0;
     if (!r.no_flip) {
         double m = s.m_in ? s.m_in[p] : ((P.radius < 0) ? m_global : site_m(s, P, pad, lut, b2, p));
-        cv = aps_exp(APS_MUL(APS_MUL(-beta, (double)sg), m));
+        cv = s.flip_tab ? aps_flip_interp(s.flip_tab, s.flip_G, sg, m) : aps_exp(APS_MUL(APS_MUL(-beta, (double)sg), m));
     }
     double rate = APS_ADD(APS_ADD(r.rdiff, r.ract), cv);
     if (s.anchor) rate = APS_ADD(APS_ADD(APS_ADD(rate, r.rbind), r.runbind), r.rexit);
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
     const bool periodic = (P.flags & APS_FLAG_PERIODIC) != 0;
     s.periodic = periodic ? 1 : 0;
     s.m_in = B.m_field_in ? B.m_field_in + (size_t)rep * (size_t)L : nullptr;
+    s.flip_tab = B.flip_tab; s.flip_G = B.flip_G;
     if (B.anchor_mask) { for (int l = tid; l < L; l += NT) s.anchor[l] = B.anchor_mask[l]; } else s.anchor = nullptr;
     for (int i = tid; i < n_max; i += NT) s.bound[i] = (B.bound0 && i < n) ? B.bound0[(size_t)rep * n_max + i] : 0;
 

@@ -31,6 +31,21 @@ def gaussian_weights(sigma_grid: float):
     return radius, phi[::-1].copy()
 
 
+FLIP_TABLE_G = 8192
+
+
+def tabulate_flip_rate(flip_rate_fn, G=FLIP_TABLE_G):
+    """A custom `flip_rate_fn(sigma, m)` (CLASS.py:59-62; called as fn(sigma[n] int8, m[n] float64) at :262) evaluated on
+    the host on the grid m_k = -1 + 2k/G for sigma = +1 and sigma = -1 -> float64 [2][G+1], the table the kernels
+    interpolate linearly (include/aps_math.h aps_flip_interp).  The callable never runs on the device."""
+    grid = -1.0 + 2.0 * np.arange(G + 1, dtype=np.float64) / G
+    rows = [np.asarray(flip_rate_fn(np.full(G + 1, sg, dtype=np.int8), grid), dtype=np.float64) for sg in (1, -1)]
+    tab = np.stack([np.broadcast_to(r, (G + 1,)) for r in rows]).copy()
+    if not np.isfinite(tab).all() or (tab < 0).any():
+        raise ValueError("flip_rate_fn must return finite, non-negative rates on m in [-1, 1]")
+    return tab
+
+
 def periodic_weights(L: int, dx: float, sigma: float, tail: float = 1e-22):
     """Taps of the reference's ring kernel (CLASS.py:111-121: exp(-0.5*(min(j, L-j)*dx/sigma)^2), normalised over the
     ring), truncated at the smallest radius whose discarded mass is below `tail`.  The reference applies the kernel
@@ -60,7 +75,7 @@ class ReplicaBatch:
     def __init__(self, *, L, K, radius, weights, D, lam, T, times_obs, betas, n, pos0, sigma0, seeds=None,
                  record=APS_REC_COUNTS | APS_REC_POS, crowding=False, device=None, dx=None, anchor_mask=None,
                  k_on=0.0, k_off=0.0, k_exit=0.0, suppress_flip_when_bound=True, immobilize_when_anchored=True,
-                 exit_cap=None, periodic=False):
+                 exit_cap=None, periodic=False, flip_tab=None):
         self.lib = capi.load()
         self.dev = _dev(device)
         self.L, self.K, self.radius = int(L), int(K), int(radius)
@@ -87,6 +102,9 @@ class ReplicaBatch:
         self.seeds = None if seeds is None else (seeds if isinstance(seeds, torch.Tensor) else
                                                  t(np.asarray(seeds, dtype=np.uint64).view(np.int64), np.int64))
         self.record = int(record)
+        # custom flip_rate_fn tabulated by the caller on m_k = -1 + 2k/G (see tabulate_flip_rate): [2][G+1]
+        self.flip_tab = None if flip_tab is None else t(np.asarray(flip_tab, dtype=np.float64).reshape(2, -1), np.float64)
+        self.flip_G = 0 if flip_tab is None else int(self.flip_tab.shape[1]) - 1
         R, M, Lq, nm, dv = self.R, self.M, self.L, self.n_max, self.dev
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dv)
         self.obs_cp = z((R, M, Lq), torch.int8) if record & APS_REC_COUNTS else None
@@ -123,7 +141,7 @@ class ReplicaBatch:
             self.R, self.n_max, self.M, record=self.record, max_events=extra.pop("max_events", 0),
             spec_from=extra.pop("spec_from", -1), exit_cap=self.exit_cap, n_end=self.n_end, obs_n=self.obs_n,
             anchor_mask=self.anchor_mask, bound0=self.bound0, bound_end=self.bound_end, obs_bound=self.obs_bound,
-            exit_t=self.exit_t, exit_pos=self.exit_pos, n_exit=self.n_exit,
+            exit_t=self.exit_t, exit_pos=self.exit_pos, n_exit=self.n_exit, flip_tab=self.flip_tab, flip_G=self.flip_G,
             times_obs=self.times_obs, weights=self.weights, beta=self.beta, n=self.n, pos0=self.pos0,
             sigma0=self.sigma0, obs_cp=self.obs_cp, obs_cm=self.obs_cm, obs_pos=self.obs_pos,
             obs_sigma_sum=self.obs_sigma_sum, obs_m_local=self.obs_m_local, n_obs=self.n_obs,

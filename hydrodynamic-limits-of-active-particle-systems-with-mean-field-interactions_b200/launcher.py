@@ -180,10 +180,12 @@ def _model_params(ps_kwargs):
         radius, weights = gaussian_weights(sigma / dx)
     else:
         radius, weights = -1, np.zeros(1)
-    for key, bad in [("flip_rate_fn", lambda v: v is not None), ("anchor_positions", lambda v: v is not None)]:
-        if bad(ps_kwargs.get(key)):
-            raise NotImplementedError(f"{key} is outside the accelerated path")
-    return dict(L=L, dx=dx, D=D, lam=lam, K=int(ps_kwargs.get("site_capacity", 1)), radius=radius, weights=weights,
+    if ps_kwargs.get("anchor_positions") is not None:
+        raise NotImplementedError("anchor_positions: use ParticleSystem.run() (variable particle count); the ensemble "
+                                  "launcher covers the anchor-free sweeps the drivers ship")
+    from .engine import tabulate_flip_rate
+    fn = ps_kwargs.get("flip_rate_fn")          # one callable for every replica of the sweep, as in the reference's loops
+    return dict(flip_tab=None if fn is None else tabulate_flip_rate(fn), L=L, dx=dx, D=D, lam=lam, K=int(ps_kwargs.get("site_capacity", 1)), radius=radius, weights=weights,
                 crowding=bool(ps_kwargs.get("crowding_suppresses_rates", False)), periodic=periodic, init=ps_kwargs.get("init", "fixed"),
                 N=int(ps_kwargs.get("N", 1000)))
 
@@ -229,7 +231,7 @@ class DeviceEnsemble:
         self.rb = ReplicaBatch(L=mp["L"], K=mp["K"], radius=mp["radius"], weights=mp["weights"], D=mp["D"], lam=mp["lam"],
                                T=T, times_obs=self.times_obs, betas=self.betas_h, n=self.n, pos0=self.pos0,
                                sigma0=self.sigma0, seeds=self.seeds, record=spec.record, crowding=mp["crowding"],
-                               device=self.dev.index, dx=mp["dx"], periodic=mp["periodic"])
+                               device=self.dev.index, dx=mp["dx"], periodic=mp["periodic"], flip_tab=mp["flip_tab"])
         self.h2d_bytes += (self.rb.times_obs.numel() + self.rb.beta.numel() + (self.rb.weights.numel() if self.rb.weights is not None else 0)) * 8
         self.n_points = int(spec.point_of.max()) + 1 if len(spec.point_of) else 0
         # replica lists per grid point (CSR) for the device-side per-point sums: the shard is in schedule order

@@ -16,7 +16,10 @@ Anchors / binding / unbinding / exit (`anchor_positions`, `k_on`, `k_off`, `k_ex
 (generic K1 kernel).  `periodic=True` (ring: hops wrap, :278-288) is supported too; its local field is the reference's ring
 kernel (:111-121) applied as a truncated direct sum instead of the FFT of :224-227, so trajectories match the reference for
 a given seed and `m_local_list` agrees to 1e-13 rather than bit for bit.
-Not supported (raises NotImplementedError; disabled in every shipped driver): a custom `flip_rate_fn`.
+A custom `flip_rate_fn(sigma, m)` (CLASS.py:59-62) is evaluated on the host on a grid of 8193 magnetisation values per
+orientation and interpolated linearly in the kernel (`engine.tabulate_flip_rate`, `aps_flip_interp`): rates agree with the
+callable to (2/8192)^2 max|f''|/8, so a trajectory equals the reference's for a given seed unless a uniform variate falls
+within that relative distance of a decision threshold (the fixture `custom_flip_*` matches event for event).
 """
 from __future__ import annotations
 
@@ -102,10 +105,13 @@ class ParticleSystem:
         self.k_on, self.k_off, self.k_exit = k_on, k_off, k_exit
         self.suppress_flip_when_bound = suppress_flip_when_bound
         self.crowding_suppresses_rates = crowding_suppresses_rates
-        if flip_rate_fn is not None:
-            raise NotImplementedError("custom flip_rate_fn is not supported by the CUDA stepper "
-                                      "(only the default exp(-beta*sigma*m), CLASS.py:59-60)")
-        self.flip_rate_fn = lambda sigma, m: np.exp(-self.beta * sigma * m)
+        if flip_rate_fn is None:                          # CLASS.py:59-62
+            self.flip_rate_fn = lambda sigma, m: np.exp(-self.beta * sigma * m)
+            self._flip_tab = None                         # evaluated in the kernel (exp with single-rounding operations)
+        else:
+            from .engine import tabulate_flip_rate
+            self.flip_rate_fn = flip_rate_fn
+            self._flip_tab = tabulate_flip_rate(flip_rate_fn)     # host-evaluated table, interpolated on the device
         assert init in ("fixed", "poisson")
         self.init_mode = init
         if self.init_mode == "fixed":
@@ -217,7 +223,8 @@ class ParticleSystem:
                             seeds=seeds, record=record, crowding=self.crowding_suppresses_rates, dx=self.dx,
                             anchor_mask=self.is_anchor_site if self._has_anchors else None, k_on=self.k_on, k_off=self.k_off,
                             k_exit=self.k_exit, suppress_flip_when_bound=self.suppress_flip_when_bound,
-                            immobilize_when_anchored=self.immobilize_when_anchored, periodic=self.periodic)
+                            immobilize_when_anchored=self.immobilize_when_anchored, periodic=self.periodic,
+                            flip_tab=self._flip_tab)
 
     def run(self, T=10.0, obs_dt=0.01, record_fft=False, record_var=False):
         import torch
@@ -365,7 +372,8 @@ class ParticleSystem:
         rb = ReplicaBatch(L=self.L, K=self.K, radius=self._radius, weights=self._weights, D=self.rate_diffusion,
                           lam=self.rate_active, T=np.inf, times_obs=[0.0], betas=[float(self.beta)], n=[n],
                           pos0=np.asarray(pos, np.int32).reshape(1, -1), sigma0=np.asarray(sigma, np.int8).reshape(1, -1),
-                          record=0, crowding=self.crowding_suppresses_rates, dx=self.dx, periodic=self.periodic)
+                          record=0, crowding=self.crowding_suppresses_rates, dx=self.dx, periodic=self.periodic,
+                          flip_tab=self._flip_tab)
         mf = torch.from_numpy(np.ascontiguousarray(m_field, dtype=np.float64)).to(rb.dev)
         one = torch.ones(1, dtype=torch.int32, device=rb.dev)
         draws = self._draw_triples(1)

@@ -150,6 +150,11 @@ typedef struct aps_batch {
     int32_t* exit_pos;          /* [n_replicas][exit_cap] site the particle left from             */
     int32_t* n_exit;            /* [n_replicas] exits recorded (in: previous count when resuming) */
     int64_t exit_cap;
+    /* custom flip_rate_fn (CLASS.py:59-62): NULL = the default exp(-beta*sigma*m).  Otherwise the callable tabulated
+     * by the caller on the grid m_k = -1 + 2k/flip_G, [2][flip_G+1] (sigma = +1 row first), shared by all replicas;
+     * the kernels interpolate linearly (aps_flip_interp, aps_math.h: tolerance stated there).                        */
+    const double* flip_tab;
+    int64_t flip_G;
 } aps_batch;
 
 int aps_abi_version(void);

@@ -157,4 +157,19 @@ APS_HD double aps_log(double x) {
     return APS_SUB(APS_MUL(dk, ln2_hi), APS_SUB(APS_SUB(APS_MUL(s, APS_SUB(f, R)), APS_MUL(dk, ln2_lo)), f));
 }
 
+/* Tabulated flip rate (custom `flip_rate_fn`, PARTICLE_solver_CLASS.py:59-62,262): tab[s*(G+1) + k] holds
+ * flip_rate_fn(sigma, m_k) evaluated ON THE HOST by the caller's Python callable at m_k = -1 + 2k/G, s = 0 for
+ * sigma = +1 and 1 for sigma = -1; between grid points the rate is interpolated linearly (single-rounding operations
+ * only, same code in the kernels and in the oracle).  Interpolation error <= (2/G)^2 * max|d2f/dm2| / 8
+ * (G = 8192: 7.5e-9 * max|f''|). */
+APS_HD double aps_flip_interp(const double* tab, int64_t G, int sg, double m) {
+    double x = APS_MUL(APS_ADD(m, 1.0), APS_MUL(0.5, (double)G));
+    int64_t k = (int64_t)x;
+    if (k < 0) k = 0;
+    if (k > G - 1) k = G - 1;
+    const double fr = APS_SUB(x, (double)k);
+    const double* t = tab + (sg == 1 ? 0 : (G + 1)) + k;
+    return APS_ADD(t[0], APS_MUL(fr, APS_SUB(t[1], t[0])));
+}
+
 #endif /* APS_MATH_H */

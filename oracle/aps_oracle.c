@@ -172,7 +172,8 @@ typedef struct draw_src {
 } draw_src;
 
 /* per-particle rates, CLASS.py:259-351 restricted to anchors=None (bind/unbind/exit rates are 0) */
-static double build_rates(work* w, const aps_params* P, int n, double beta, const uint8_t* anchor) {
+static double build_rates(work* w, const aps_params* P, int n, double beta, const uint8_t* anchor, const double* flip_tab,
+                          int64_t flip_G) {
     const int L = P->L, K = P->K;
     const int suppress = (P->flags & APS_FLAG_SUPPRESS_FLIP_BOUND) != 0, immob = (P->flags & APS_FLAG_IMMOBILIZE) != 0;
     const double D = P->rate_diffusion, lam = P->rate_active;
@@ -209,7 +210,9 @@ static double build_rates(work* w, const aps_params* P, int n, double beta, cons
         w->r_act[i] = anchored ? 0.0 : ra;                                 /* :340 */
         /* flip_rate_fn default: np.exp(-beta * sigma * m), CLASS.py:60 */
         double arg = ((-beta) * (double)sg) * w->m[p];
-        w->cvec[i] = (suppress && bnd) ? 0.0 : aps_exp(arg);               /* :266-267 */
+        /* custom flip_rate_fn: the caller's callable tabulated on the host, linear interpolation (aps_flip_interp) */
+        const double cv = flip_tab ? aps_flip_interp(flip_tab, flip_G, sg, w->m[p]) : aps_exp(arg);
+        w->cvec[i] = (suppress && bnd) ? 0.0 : cv;                         /* :266-267 */
         int occ_here = w->cp[p] + w->cm[p];
         w->r_bind[i] = (anchor && !bnd && sg == -1 && on_anchor && occ_here < K) ? P->k_on : 0.0;   /* :343-345 */
         w->r_unbind[i] = bnd ? P->k_off : 0.0;                             /* :347-348 */
@@ -280,7 +283,7 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
         if (B->m_field_in) memcpy(w->m, B->m_field_in + (size_t)rep * (size_t)L, 8 * (size_t)L);
         else m_field(w, P, B->weights);                                  /* :512 */
         if (n == 0) { status = APS_RUN_EMPTY; break; }                   /* :256-257 (every particle has exited) */
-        double R = build_rates(w, P, n, beta, anchor);                   /* :259-352 */
+        double R = build_rates(w, P, n, beta, anchor, B->flip_tab, B->flip_G);   /* :259-352 */
         if (!(R > 0)) { status = APS_RUN_EMPTY; break; }                 /* :353-355 */
         double e, u_choice, u_event;
         if (mode == 0) {

@@ -13,6 +13,14 @@ from aps_b200.batch import make_batch, make_params
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+# Named custom flip rates of the `custom_flip_*` fixtures (callables cannot be stored in a fixture): the SAME Python
+# callables are handed to the reference (tools/gen_golden.py) and to the drop-in / tabulated for the oracle.
+FLIP_FNS = {
+    "glauber_1p5": lambda sigma, m: 1.0 - sigma * np.tanh(1.5 * m),
+    "exp_quadratic": lambda sigma, m: np.exp(-0.8 * sigma * m) + 0.25 * m * m,
+}
+
+
 def case_names():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
     return [n for n in names if not n.startswith(("stat_", "pde_", "full_"))]
@@ -41,7 +49,7 @@ class HostRun:
 
     def __init__(self, L, n_max, M, n, pos0, sigma0, beta, times_obs, weights, draws=None, draw_off=None,
                  seeds=None, record=7, trace_cap=0, max_events=0, t_start=None, obs_start=None, ev_start=None,
-                 anchor_mask=None, bound0=None, exit_cap=0, alloc_m_local=True):
+                 anchor_mask=None, bound0=None, exit_cap=0, alloc_m_local=True, flip_tab=None):
         R = len(n)
         self.R, self.L, self.n_max, self.M = R, L, n_max, M
         self.n = np.ascontiguousarray(n, dtype=np.int32)
@@ -80,8 +88,10 @@ class HostRun:
         self.exit_t = np.full((R, max(exit_cap, 1)), np.nan, np.float64)
         self.exit_pos = np.full((R, max(exit_cap, 1)), -1, np.int32)
         self.n_exit = np.zeros(R, np.int32)
+        self.flip_tab = None if flip_tab is None else np.ascontiguousarray(flip_tab, dtype=np.float64).reshape(2, -1)
         self.batch, self._keep = make_batch(
             R, n_max, M, record=record, max_events=max_events, trace_cap=trace_cap, exit_cap=exit_cap,
+            flip_tab=self.flip_tab, flip_G=0 if flip_tab is None else self.flip_tab.shape[1] - 1,
             anchor_mask=self.anchor_mask, bound0=self.bound0, n_end=self.n_end, bound_end=self.bound_end, obs_n=self.obs_n,
             obs_bound=self.obs_bound, exit_t=self.exit_t, exit_pos=self.exit_pos, n_exit=self.n_exit,
             times_obs=self.times_obs, weights=self.weights, beta=self.beta, n=self.n, pos0=self.pos0,
@@ -100,6 +110,9 @@ class HostRun:
 def hostrun_from_case(c, trace=True, **kw):
     m = c["meta"]
     n = m["n"]
+    if m.get("flip"):
+        from aps_b200.engine import tabulate_flip_rate
+        kw.setdefault("flip_tab", tabulate_flip_rate(FLIP_FNS[m["flip"]]))
     return HostRun(m["L"], max(n, 1), len(c["times_obs"]), [n], c["pos0"], c["sigma0"], [m["ps"]["beta"]],
                    c["times_obs"], c["weights"], draws=c["draws"], draw_off=[0, len(c["draws"])],
                    trace_cap=(len(c["trace"]) + 4) if trace else 0,

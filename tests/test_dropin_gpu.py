@@ -29,6 +29,9 @@ def build(c, rng):
     kw = dict(flip_rate_fn=None, minus_anchor=True, periodic=False, immobilize_when_anchored=True,
               anchor_radius=0.003, anchor_positions=None, crowding_suppresses_rates=False, k_on=0, k_off=0, k_exit=0)
     kw.update(m["ps"])
+    if m.get("flip"):
+        from common import FLIP_FNS
+        kw["flip_rate_fn"] = FLIP_FNS[m["flip"]]           # custom flip rate: the same callable the reference was given
     if m.get("profile"):
         p = m["profile"]
         rp, rm = exp_gradient(p["L"], p["N"], p["frac_plus"], p["decay_plus"])

@@ -183,6 +183,13 @@ def cases():
     c["periodic_global"] = dict(ps=dict(L=50, xlim=1, rate_diffusion=0.6, rate_active=2, beta=1.2, init="fixed", N=30,
                                         scale_rates=False, local_kernel_sigma=0.0, site_capacity=1, periodic=True),
                                 run=dict(T=3.0, obs_dt=0.5, record_fft=False, record_var=False), seed=2020)
+    # custom flip_rate_fn (CLASS.py:59-62): named callables of tests/common.py FLIP_FNS
+    c["custom_flip_local"] = dict(ps=dict(L=200, xlim=1, rate_diffusion=0.3, rate_active=3, beta=1.5, init="fixed", N=120,
+                                          scale_rates=False, local_kernel_sigma=0.02, site_capacity=1),
+                                  flip="glauber_1p5", run=dict(T=3.0, obs_dt=0.25, record_fft=False, record_var=False), seed=2121)
+    c["custom_flip_global_k2"] = dict(ps=dict(L=100, xlim=1, rate_diffusion=0.4, rate_active=2, beta=0.8, init="fixed", N=110,
+                                              scale_rates=False, local_kernel_sigma=0.0, site_capacity=2),
+                                      flip="exp_quadratic", run=dict(T=3.0, obs_dt=0.25, record_fft=False, record_var=False), seed=2222)
     c["poisson_k2"] = dict(ps=dict(L=200, xlim=1, rate_diffusion=0.3, rate_active=4, beta=1.8, init="poisson", N=260,
                                    scale_rates=False, local_kernel_sigma=0.01, site_capacity=2),
                            profile=dict(L=200, N=260, frac_plus=0.6, decay_plus=0.5),
@@ -193,6 +200,10 @@ def cases():
 def build_ps(PS, spec, rng):
     kw = dict(BASE)
     kw.update(spec["ps"])
+    if spec.get("flip"):
+        sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+        from common import FLIP_FNS
+        kw["flip_rate_fn"] = FLIP_FNS[spec["flip"]]
     if "profile" in spec:
         p = spec["profile"]
         rp, rm = exp_gradient(p["L"], p["N"], p["frac_plus"], p["decay_plus"])
@@ -276,7 +287,7 @@ def run_case(PS, name, spec):
         sd = float(ps._sigma_grid)
         radius = int(4.0 * sd + 0.5)
         weights = _filters._gaussian_kernel1d(sd, 0, radius)[::-1].copy()
-    meta = dict(name=name, ps=spec["ps"], run=spec["run"], seed=seed, profile=spec.get("profile"),
+    meta = dict(name=name, ps=spec["ps"], run=spec["run"], seed=seed, profile=spec.get("profile"), flip=spec.get("flip"),
                 dx=ps.dx, rate_diffusion=ps.rate_diffusion, rate_active=ps.rate_active, K=ps.K, L=ps.L,
                 radius=radius, n=int(n), n_obs=int(n_obs), n_events=len(trace),
                 periodic=bool(ps.periodic), anchors=bool(ps.is_anchor_site.any()), k_on=float(ps.k_on), k_off=float(ps.k_off), k_exit=float(ps.k_exit),
