@@ -253,8 +253,10 @@ def test_sweep_over_sigmas_and_raw_structure_series(tmp_path):
     ps = dict(PS, init="fixed", N=30)
     res = la.sweep_over_sigmas([0.0, 0.03], [0.5, 2.0], 3, ps, {}, RUN, base_seed=3, save_dir=str(tmp_path))
     assert list(res) == [0.0, 0.03]
-    for sigma in res:
-        one = la.sweep_over_betas([0.5, 2.0], 3, dict(ps, local_kernel_sigma=sigma), {}, RUN, base_seed=3, want_profiles=False)
+    for si, sigma in enumerate(res):
+        # every sigma of a reproducible sweep gets its own streams: base_seed + si * 1_000_003 * max(10 000, runs per beta)
+        one = la.sweep_over_betas([0.5, 2.0], 3, dict(ps, local_kernel_sigma=sigma), {}, RUN, base_seed=3 + si * 1_000_003 * 10_000,
+                                  want_profiles=False)
         assert np.array_equal(res[sigma]["v_mean"], one["means"]) and np.array_equal(res[sigma]["D_se"], one["D_ses"])
         z = np.load(tmp_path / f"v_eff_vs_beta_sigma_{sigma:.4g}.npz", allow_pickle=True)
         assert set(z.files) == {"beta", "v_mean", "v_se", "D_mean", "D_se", "ps_kwargs"}
