@@ -157,6 +157,12 @@ class ApsPdeArgs(C.Structure):          # include/aps_pde.h
                                           "tracer_hist", "v_eff_series", "D_eff_series", "tot_series"]]
 
 
+class ApsK2Multi(C.Structure):         # include/aps.h aps_k2_multi
+    _fields_ = [("n_passes", C.c_int32), ("world", C.c_int32), ("rank", C.c_int32), ("refresh_every", C.c_int32),
+                ("ghost", C.c_int64), ("own_lo", C.c_int64), ("own_hi", C.c_int64), ("buf0", C.c_void_p), ("buf1", C.c_void_p),
+                ("sync", C.c_void_p), ("peer", C.c_void_p * 8)]
+
+
 APS_PDE_BC = {"periodic": 0, "neumann": 1}
 APS_PDE_MODEL = {"bidirectional": 0, "anchored_minus": 1}
 
@@ -183,6 +189,12 @@ SYMBOLS = {
     "aps_k2_flip_table": (C.c_int, [_P(ApsK2Rates), C.c_void_p]),
     "aps_k2_pass_device": (C.c_int, [_P(ApsK2Args), C.c_void_p]),
     "aps_k2_run_device": (C.c_int, [_P(ApsK2Args), C.c_int, C.c_void_p]),
+    "aps_k2_run_persistent_device": (C.c_int, [_P(ApsK2Args), _P(ApsK2Multi), C.c_void_p]),
+    "aps_k2_peer_region_bytes": (C.c_int, []),
+    "aps_k2_peer_alloc": (C.c_int, [_P(C.c_void_p), C.c_void_p]),
+    "aps_k2_peer_open": (C.c_int, [C.c_void_p, _P(C.c_void_p)]),
+    "aps_k2_peer_close": (C.c_int, [C.c_void_p]),
+    "aps_k2_peer_free": (C.c_int, [C.c_void_p]),
     "aps_k2_init_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_double, C.c_double, C.c_void_p]),
     "aps_k2_profile_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "aps_pde_solve_device": (C.c_int, [_P(ApsPdeArgs), C.c_void_p]),

@@ -407,15 +407,95 @@ int aps_k2_pass_device(const aps_k2_args* a, void* stream) {
     if (per_sm < 1) per_sm = 1;
     int grid = n_sm * per_sm;                       // persistent CTAs: a multiple of the SM count
     if (grid > ntiles) grid = ntiles;
+    const aps::K2Multi none{};
     if (a->radius >= 0) {
-        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        aps::k2_pass_kernel<true><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap);
+        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aps::k2_pass_kernel<true, false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap, none);
     } else {
-        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        aps::k2_pass_kernel<false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap);
+        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        aps::k2_pass_kernel<false, false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap, none);
     }
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
+    return APS_OK;
+}
+
+// ---- many passes per launch (grid barriers) + slab exchange over peer memory ----
+int aps_k2_peer_region_bytes(void) { return (int)sizeof(aps::K2PeerRegion); }
+
+int aps_k2_peer_alloc(void** region, void* ipc_handle_out) {
+    if (!region || !ipc_handle_out) return fail(APS_ERR_INVALID, "aps_k2_peer_alloc: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "aps.h promises a 64-byte handle");
+    void* p = nullptr;
+    CU(cudaMalloc(&p, sizeof(aps::K2PeerRegion)));
+    CU(cudaMemset(p, 0, sizeof(aps::K2PeerRegion)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    memcpy(ipc_handle_out, &h, sizeof(h));
+    *region = p;
+    return APS_OK;
+}
+int aps_k2_peer_open(const void* ipc_handle, void** region) {
+    if (!region || !ipc_handle) return fail(APS_ERR_INVALID, "aps_k2_peer_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    CU(cudaIpcOpenMemHandle(region, h, cudaIpcMemLazyEnablePeerAccess));
+    return APS_OK;
+}
+int aps_k2_peer_close(void* region) { if (region) CU(cudaIpcCloseMemHandle(region)); return APS_OK; }
+int aps_k2_peer_free(void* region) { if (region) CU(cudaFree(region)); return APS_OK; }
+
+int aps_k2_run_persistent_device(aps_k2_args* a, const aps_k2_multi* hm, void* stream) {
+    if (!a || !hm || hm->n_passes < 0 || !hm->buf0 || !hm->buf1 || hm->buf0 == hm->buf1 || !hm->sync)
+        return fail(APS_ERR_INVALID, "aps_k2_run_persistent: missing buffers / sync scratch");
+    if (a->L < aps::kK2Tile || a->L % aps::kK2Tile || a->global_offset % aps::kK2Tile)
+        return fail(APS_ERR_INVALID, "aps_k2_run_persistent: L and global_offset must be multiples of 8192");
+    if (a->radius > 1024) return fail(APS_ERR_INVALID, "aps_k2_run_persistent: radius too large");
+    if (a->radius >= 0 && (!a->w16 || !a->flip_tab)) return fail(APS_ERR_INVALID, "aps_k2_run_persistent: local field needs w16 taps and flip_tab");
+    if (a->radius < 0 && a->n_particles < 1) return fail(APS_ERR_INVALID, "aps_k2_run_persistent: global field needs n_particles");
+    if (hm->world < 1 || hm->world > aps::kK2MaxRanks || hm->rank < 0 || hm->rank >= hm->world)
+        return fail(APS_ERR_INVALID, "aps_k2_run_persistent: need 1 <= world <= 8 and 0 <= rank < world");
+    if (hm->world > 1) {
+        if (hm->ghost < 16 || hm->ghost > aps::kK2GhostMax || hm->ghost % 16 || hm->refresh_every < 1)
+            return fail(APS_ERR_INVALID, "aps_k2_run_persistent: ghost must be a multiple of 16 in [16, 65536], refresh_every >= 1");
+        for (int q = 0; q < hm->world; ++q) if (!hm->peer[q]) return fail(APS_ERR_INVALID, "aps_k2_run_persistent: missing peer region");
+    }
+    if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (hm->n_passes == 0) return APS_OK;
+    const int cap = g_k2_stash_cap > 0 ? g_k2_stash_cap : aps::k2_stash_cap(a->rates.mu);
+    const size_t smem = k2_smem(a->radius, cap);
+    if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_k2_run_persistent: radius too large for the shared-memory ring");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, n_sm = 0, coop = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) return fail(APS_ERR_CUDA, "device does not support cooperative launches");
+    const void* fn = a->radius >= 0 ? (const void*)aps::k2_pass_kernel<true, true> : (const void*)aps::k2_pass_kernel<false, true>;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, aps::kK2Threads, smem));
+    if (per_sm > g_k2_ctas_per_sm) per_sm = g_k2_ctas_per_sm;
+    if (per_sm < 1) return fail(APS_ERR_CAPACITY, "aps_k2_run_persistent: kernel does not fit on an SM");
+    const int ntiles = (int)(a->L / aps::kK2Tile);
+    int grid = n_sm * per_sm;                       // all CTAs co-resident (grid barrier): a multiple of the SM count
+    if (grid > ntiles) grid = ntiles;
+    aps::K2Multi m{};
+    m.n_passes = hm->n_passes; m.world = hm->world; m.rank = hm->rank; m.refresh_every = hm->refresh_every > 0 ? hm->refresh_every : 1;
+    m.ghost = hm->ghost; m.own_lo = hm->own_lo; m.own_hi = hm->own_hi;
+    m.buf[0] = hm->buf0; m.buf[1] = hm->buf1;
+    long long* sync = (long long*)hm->sync;         // [0] grid barrier, [1] error flag, [2] acc, [3] msum0, [4] msum_cur
+    m.gbar = (unsigned*)(sync + 0); m.err = (int32_t*)(sync + 1); m.acc = sync + 2; m.msum0 = sync + 3; m.msum_cur = sync + 4;
+    for (int q = 0; q < aps::kK2MaxRanks; ++q) m.peer[q] = q < hm->world ? (aps::K2PeerRegion*)hm->peer[q] : nullptr;
+    CU(cudaMemsetAsync(sync, 0, 8, st));            // barrier counter restarts with every launch
+    aps_k2_args ka = *a;
+    if (hm->world > 1 && a->radius < 0) { ka.count_lo = hm->own_lo; ka.count_hi = hm->own_hi; }   // own flips only
+    int cap_arg = cap;
+    void* params[] = {(void*)&ka, (void*)&cap_arg, (void*)&m};
+    CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(aps::kK2Threads), params, smem, st));
+    g_launches.fetch_add(1);
+    a->pass += (uint64_t)hm->n_passes;
     return APS_OK;
 }
 

@@ -95,6 +95,78 @@ __device__ __forceinline__ void k2_field_scalar(const unsigned char* snap, int c
     }
 }
 
+// ---- many passes per launch + slab decomposition over peer memory (NVLink) ---------------------------------------
+// One cooperative launch runs `n_passes` passes: the persistent CTAs meet at a grid barrier (device-scope atomic
+// counter) between passes instead of returning to the host, so a 2^26-site lattice no longer pays a launch and a
+// pipeline ramp-up per ~20 us pass.  With several ranks (one process per GPU, contiguous slabs with a ghost zone of
+// `ghost` sites per interior side, see sublattice.py) the same kernel does the exchange itself through peer memory
+// mapped with CUDA IPC: system-scope release stores of a tag into the neighbour's flag words, acquire loads on the
+// own ones — no NCCL call and no host round trip inside the time stepping:
+//   * ghost refresh (every `refresh_every` passes): a rank copies its two owned edges into its staging area, the
+//     neighbours pull them over NVLink into their ghost zones (double-buffered staging, tags = absolute pass number);
+//   * global-magnetisation mode: every pass each rank stores its cumulative flip increment into every peer's mailbox
+//     (8 bytes per peer) in the same flag round, so all ranks use the lattice-wide sum(sigma) of the single-slab run.
+// Every spin has a time-out that raises `*err` and makes all CTAs leave the kernel (no hung GPU on a lost peer).
+constexpr int kK2MaxRanks = 8;
+constexpr int kK2GhostMax = 65536;
+struct K2PeerRegion {                          // one per rank, in IPC-shared device memory, zero-initialised
+    unsigned long long mail_tag[2][kK2MaxRanks];   // [pass parity][source rank]   tag = absolute pass number + 1
+    long long mail_val[2][kK2MaxRanks];            // cumulative sum of the source rank's own flip increments
+    unsigned long long ready_tag[2][2];            // [refresh parity][side]: the neighbour's edge for my ghost `side` is staged
+    unsigned long long pad[4];
+    unsigned char edge[2][2][kK2GhostMax];         // staging [refresh parity][0 = my left edge, 1 = my right edge]
+};
+struct K2Multi {
+    int32_t n_passes, world, rank, refresh_every;
+    long long ghost, own_lo, own_hi;           // buffer coordinates of the owned range; ghost sites per interior side
+    uint8_t* buf[2];                           // pass j of this launch reads buf[j & 1] and writes buf[(j + 1) & 1]
+    unsigned* gbar;                            // grid-barrier counter, zero at launch
+    int32_t* err;                              // time-out flag
+    long long* acc;                            // global field: cumulative own flip increments since the lattice was created
+    long long* msum0;                          // global field: lattice-wide sum(sigma) at creation
+    long long* msum_cur;                       // global field: lattice-wide sum(sigma) before the current pass (kept up to date)
+    K2PeerRegion* peer[kK2MaxRanks];           // IPC-mapped regions of all ranks (peer[rank] = own), world > 1 only
+};
+
+__device__ __forceinline__ void k2_st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long k2_ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned k2_ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long kK2SpinLimit = 6000000000LL;   // ~3 s of SM clocks: a peer that far behind is lost
+// one thread spins until cond() or until the error flag is up / the time limit is hit (then it raises the flag)
+template <class F>
+__device__ __forceinline__ bool k2_spin(F cond, int32_t* err) {
+    const long long t0 = clock64();
+    while (!cond()) {
+        if (*reinterpret_cast<volatile int32_t*>(err)) return false;
+        if (clock64() - t0 > kK2SpinLimit) { atomicExch(err, 1); return false; }
+        __nanosleep(64);
+    }
+    return true;
+}
+// grid barrier of the co-resident CTAs (cooperative launch): monotone counter, round r waits for r * gridDim.x arrivals
+__device__ __forceinline__ void k2_grid_sync(const K2Multi& m, unsigned& round) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++round;
+        __threadfence();
+        atomicAdd(m.gbar, 1u);
+        const unsigned target = round * gridDim.x;
+        k2_spin([&] { return k2_ld_acquire_gpu(m.gbar) >= target; }, m.err);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 // One pass, persistent CTAs.  Each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through a
 // kK2Stages-deep ring of shared-memory buffers: TMA bulk loads (mbarrier complete_tx) bring the window
 // (and, for the local field, a second read-only copy with the +-r halo) in, the 128 threads run the
@@ -114,15 +186,16 @@ __device__ __forceinline__ void k2_field_scalar(const unsigned char* snap, int c
 //   C  each lane replays its stashed trials in order against the live tile: no RNG, no taps, a few integer ops.
 // The decisions are the same function of (Philox words, state, frozen field) as in the oracle's serial loop;
 // trials beyond the stash capacity keep their two acceptance bits in register masks (Philox regenerated in C).
-template <bool LOCAL>
-__global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_constant__ aps_k2_args a, const int stash_cap) {
+// MULTI = false: one pass a.in -> a.out (aps_k2_pass_device).  MULTI = true: m.n_passes passes ping-ponging between
+// m.buf[0] and m.buf[1] with grid barriers and, for world > 1, the peer-memory exchanges described above.
+template <bool LOCAL, bool MULTI>
+__global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_constant__ aps_k2_args a, const int stash_cap,
+                                                             const __grid_constant__ K2Multi m) {
     extern __shared__ __align__(128) unsigned char k2_raw[];
     const int tid = threadIdx.x;
     const long long L = a.L;                         // sites held by this call (slab incl. ghosts)
-    const int qpar = (int)(a.pass & 1ULL);           // parity; slabs start on tile boundaries, so it is global
     const int r = LOCAL ? a.radius : 0;
     const int R16 = LOCAL ? ((r + 15) & ~15) : 0;
-    const int sh = qpar * APS_K2_HALF - kK2Margin;
     const int ntiles = (int)(L / kK2Tile);
     constexpr int WB = kK2Tile + 32;                 // largest window
     constexpr int kK2Stages = LOCAL ? kK2StagesLocal : kK2StagesGlobal;
@@ -130,8 +203,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(k2_raw);
     unsigned char* bufs = k2_raw + 128;
     __shared__ uint32_t thr_glob[2];
-    const uint8_t* __restrict__ in = a.in;
-    uint8_t* __restrict__ out = a.out;
+    __shared__ long long mail_sum[kK2MaxRanks];
 
     // local-field scratch behind the ring: taps, then per warp [cap][32] acceptance words, candidate list, trial codes
     const int cap = stash_cap;
@@ -148,11 +220,6 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     if (tid == 0) {
         for (int s2 = 0; s2 < kK2Stages; ++s2) k2_mbar_init(&bars[s2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (!LOCAL) {
-            const double m = APS_DIV((double)(*a.msum_in), (double)a.n_particles);
-            thr_glob[0] = aps_k2_flip_thr(a.rates.beta, +1, m, a.rates.inv_cmax, a.rates.t_active);
-            thr_glob[1] = aps_k2_flip_thr(a.rates.beta, -1, m, a.rates.inv_cmax, a.rates.t_active);
-        }
     }
     if (LOCAL && packed) {
         for (int e = tid; e < nwords * 4; e += kK2Threads) {
@@ -166,6 +233,28 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         }
     }
     __syncthreads();
+
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const uint32_t t_left = a.rates.t_left, t_right = a.rates.t_right, t_active = a.rates.t_active;
+    const int my_first = blockIdx.x, step_t = gridDim.x;
+    int it = 0;                                      // ring iteration counter: runs on across the passes of a launch
+    unsigned bar_round = 0;
+    const int n_passes = MULTI ? m.n_passes : 1;
+  for (int pj = 0; pj < n_passes; ++pj) {
+    const uint64_t pass_abs = a.pass + (uint64_t)pj;
+    const uint8_t* __restrict__ in = MULTI ? m.buf[pj & 1] : a.in;
+    uint8_t* __restrict__ out = MULTI ? m.buf[(pj + 1) & 1] : a.out;
+    const int qpar = (int)(pass_abs & 1ULL);         // parity; slabs start on tile boundaries, so it is global
+    const int sh = qpar * APS_K2_HALF - kK2Margin;
+    if (!LOCAL) {
+        if (tid == 0) {
+            const long long msum = MULTI ? *reinterpret_cast<volatile long long*>(m.msum_cur) : (long long)*a.msum_in;
+            const double mg = APS_DIV((double)msum, (double)a.n_particles);
+            thr_glob[0] = aps_k2_flip_thr(a.rates.beta, +1, mg, a.rates.inv_cmax, a.rates.t_active);
+            thr_glob[1] = aps_k2_flip_thr(a.rates.beta, -1, mg, a.rates.inv_cmax, a.rates.t_active);
+        }
+        __syncthreads();
+    }
 
     auto window = [&](int t, long long& lo, long long& hi) {
         lo = (long long)t * kK2Tile + sh; hi = lo + kK2Tile;
@@ -188,14 +277,10 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         }
     };
 
-    const int my_first = blockIdx.x, step_t = gridDim.x;
     if (tid == 0) {
-        for (int k = 0; k < kK2Stages - 1; ++k) { int t = my_first + k * step_t; if (t < ntiles) issue_load(t, k); }
+        for (int k = 0; k < kK2Stages - 1; ++k) { int t = my_first + k * step_t; if (t < ntiles) issue_load(t, (it + k) % kK2Stages); }
     }
-    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
-    const uint32_t t_left = a.rates.t_left, t_right = a.rates.t_right, t_active = a.rates.t_active;
     int dsig = 0;
-    int it = 0;
     for (int t = my_first; t < ntiles; t += step_t, ++it) {
         const int s2 = it % kK2Stages;
         long long lo, hi; window(t, lo, hi);
@@ -215,7 +300,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         const long long t0 = (long long)t * kK2Tile;
         const long long seg_local = (long long)t * kK2Threads + tid;
         const uint64_t seg_global = (uint64_t)(a.global_offset / APS_K2_SEG) + (uint64_t)seg_local;
-        const uint32_t c0 = (uint32_t)seg_global, c1 = (uint32_t)a.pass;
+        const uint32_t c0 = (uint32_t)seg_global, c1 = (uint32_t)pass_abs;
         const uint32_t chi = (uint32_t)(seg_global >> 32) * 0x9E3779B9u + APS_RNG_SUBLATTICE;
         const long long abase = t0 + (long long)tid * APS_K2_SEG + qpar * APS_K2_HALF;     // first active site (slab index)
         const bool seg_ok = abase + APS_K2_HALF <= L;
@@ -334,10 +419,85 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         }
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (a.msum_out) {   // running sum(sigma) for the global magnetisation of the next pass
+    long long* const sum_target = MULTI ? (LOCAL ? nullptr : m.acc) : reinterpret_cast<long long*>(a.msum_out);
+    if (sum_target) {   // running sum(sigma) for the global magnetisation of the next pass
         for (int o = 16; o > 0; o >>= 1) dsig += __shfl_xor_sync(0xffffffffu, dsig, o);
-        if ((tid & 31) == 0 && dsig != 0) atomicAdd(reinterpret_cast<unsigned long long*>(a.msum_out), (unsigned long long)(long long)dsig);
+        if ((tid & 31) == 0 && dsig != 0) atomicAdd(reinterpret_cast<unsigned long long*>(sum_target), (unsigned long long)(long long)dsig);
     }
+    if (!MULTI) break;
+
+    // ================= between two passes of one launch =================
+    // (A) every CTA has written its tiles (bulk stores complete) and added its flips: the pass is finished on this GPU
+    asm volatile("fence.proxy.async;" ::: "memory");
+    k2_grid_sync(m, bar_round);
+    if (*reinterpret_cast<volatile int32_t*>(m.err)) break;
+    const unsigned long long tag = (unsigned long long)pass_abs + 1ULL;
+    const bool refresh = m.world > 1 && ((pass_abs + 1ULL) % (uint64_t)m.refresh_every) == 0ULL;
+    if (!LOCAL) {
+        // lattice-wide sum(sigma): own cumulative increments + (in the same flag round) those of the peers
+        if (blockIdx.x == 0) {
+            const int par = (int)(pass_abs & 1ULL);
+            if (tid < m.world) {
+                const long long mine = *reinterpret_cast<volatile long long*>(m.acc);
+                if (tid == m.rank) mail_sum[tid] = mine;
+                else {
+                    K2PeerRegion* pr = m.peer[tid];
+                    *reinterpret_cast<volatile long long*>(&pr->mail_val[par][m.rank]) = mine;
+                    k2_st_release_sys(&pr->mail_tag[par][m.rank], tag);
+                    K2PeerRegion* me = m.peer[m.rank];
+                    k2_spin([&] { return k2_ld_acquire_sys(&me->mail_tag[par][tid]) == tag; }, m.err);
+                    mail_sum[tid] = *reinterpret_cast<volatile long long*>(&me->mail_val[par][tid]);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                long long s = *m.msum0;
+                for (int q = 0; q < m.world; ++q) s += mail_sum[q];
+                *reinterpret_cast<volatile long long*>(m.msum_cur) = s;
+                __threadfence();
+            }
+        }
+    }
+    if (refresh) {
+        // (B) stage the two owned edges, tell the neighbours, pull theirs into the ghost zones of the new state
+        const int rpar = (int)(((pass_abs + 1ULL) / (uint64_t)m.refresh_every) & 1ULL);
+        K2PeerRegion* me = m.peer[m.rank];
+        const long long g = m.ghost;
+        const int ncopy = gridDim.x < 16 ? gridDim.x : 16;
+        if ((int)blockIdx.x < ncopy) {
+            const long long nvec = g / 16;
+            for (int side = 0; side < 2; ++side) {
+                if ((side == 0 && m.rank == 0) || (side == 1 && m.rank == m.world - 1)) continue;
+                const uint4* src = reinterpret_cast<const uint4*>(out + (side == 0 ? m.own_lo : m.own_hi - g));
+                uint4* dst = reinterpret_cast<uint4*>(me->edge[rpar][side]);
+                for (long long v = (long long)blockIdx.x * kK2Threads + tid; v < nvec; v += (long long)ncopy * kK2Threads) dst[v] = src[v];
+            }
+            __threadfence_system();
+        }
+        k2_grid_sync(m, bar_round);
+        if (blockIdx.x == 0 && tid < 2) {       // my left edge is the RIGHT ghost of rank-1, my right edge the LEFT ghost of rank+1
+            const int nb = tid == 0 ? m.rank - 1 : m.rank + 1;
+            if (nb >= 0 && nb < m.world) k2_st_release_sys(&m.peer[nb]->ready_tag[rpar][tid == 0 ? 1 : 0], tag);
+        }
+        if ((int)blockIdx.x < ncopy) {
+            const long long nvec = g / 16;
+            for (int side = 0; side < 2; ++side) {
+                const int nb = side == 0 ? m.rank - 1 : m.rank + 1;
+                if (nb < 0 || nb >= m.world) continue;
+                if (tid == 0) k2_spin([&] { return k2_ld_acquire_sys(&me->ready_tag[rpar][side]) == tag; }, m.err);
+                __syncthreads();
+                const uint4* src = reinterpret_cast<const uint4*>(m.peer[nb]->edge[rpar][1 - side]);   // NVLink peer loads
+                uint4* dst = reinterpret_cast<uint4*>(out + (side == 0 ? m.own_lo - g : m.own_hi));
+                for (long long v = (long long)blockIdx.x * kK2Threads + tid; v < nvec; v += (long long)ncopy * kK2Threads) dst[v] = src[v];
+            }
+            __threadfence();
+        }
+    }
+    if (!LOCAL || refresh) {                 // (C) the new sum / the refreshed ghosts are visible to every CTA
+        k2_grid_sync(m, bar_round);
+        if (*reinterpret_cast<volatile int32_t*>(m.err)) break;
+    }
+  }
 }
 
 // Bernoulli initial condition: site occupied with probability `density`, '+' with probability frac_plus.

@@ -3,11 +3,19 @@
 The lattice is a byte array in HBM (0 empty / 1 '+' / 2 '-'), ping-ponged between two buffers.  With
 more than one rank the lattice is cut into contiguous slabs (one per GPU) that carry a ghost zone of
 `ghost` sites on each interior side.  Because the random stream is keyed by the GLOBAL segment index,
-a rank recomputes its ghost zone bit-identically to its neighbour; the ghost data only goes stale from
-its outer end inwards, by (radius + 1) sites per pass, so ghosts are refreshed from the neighbours
-(NVLink point-to-point via torch.distributed send/recv) every `ghost // (radius + 2)` passes instead of
-every pass.  The result is bit-identical to the single-GPU run (tested under gloo on CPU with the
-oracle backend and on the GPU against the oracle).
+a rank recomputes its ghost zone bit-identically to its neighbour; the ghost data goes stale from its
+outer end inwards by at most (radius + 33) sites per pass — the trials of an active half of 32 sites run
+sequentially, so one stale site can change a chain of hops across the whole half, plus the reach of the
+field — so the ghosts are refreshed every `(ghost - radius - 1) // (radius + 33)` passes, not every pass.
+
+CUDA backend: `run_passes(n)` is ONE cooperative launch (`aps_k2_run_persistent_device`): grid barriers
+between the passes, and with several ranks the kernel itself refreshes the ghost zones and (global-field mode)
+exchanges the 8-byte sum(sigma) increments through peer memory mapped with CUDA IPC over NVLink — flag words
+written with system-scope release stores, no NCCL call and no host round trip inside the time stepping
+(csrc/aps_k2.cuh).  torch.distributed is only used once, to hand the 64-byte IPC handles round, and for the
+observables (profile all-reduce).  The oracle backend of the CPU tests keeps the host-driven exchange below.
+The result is bit-identical to the single-slab run (gloo tests on CPU with the oracle backend, pytest -m gpu on
+2 GPUs with the kernels).
 """
 from __future__ import annotations
 
@@ -63,6 +71,38 @@ class CudaK2Backend:
     def run(self, args, n_passes):
         capi.check(self.lib.aps_k2_run_device(args, n_passes, torch.cuda.current_stream().cuda_stream), "aps_k2_run_device")
 
+    persistent = True          # run_passes() = one cooperative multi-pass launch with in-kernel exchange
+
+    def run_persistent(self, args, multi):
+        capi.check(self.lib.aps_k2_run_persistent_device(args, multi, torch.cuda.current_stream().cuda_stream),
+                   "aps_k2_run_persistent_device")
+
+    def peer_setup(self, rank, world):
+        """Allocate this rank's exchange region, hand its CUDA IPC handle round and map the peers' regions."""
+        region, handle = C.c_void_p(), (C.c_char * 64)()
+        capi.check(self.lib.aps_k2_peer_alloc(C.byref(region), handle), "aps_k2_peer_alloc")
+        handles = [None] * world
+        torch.distributed.all_gather_object(handles, bytes(handle.raw))
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(region.value)
+            else:
+                p = C.c_void_p()
+                capi.check(self.lib.aps_k2_peer_open(handles[r], C.byref(p)), "aps_k2_peer_open")
+                ptrs.append(p.value)
+        torch.distributed.barrier()
+        return region.value, ptrs
+
+    def peer_teardown(self, rank, own, ptrs):
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        for r, p in enumerate(ptrs):
+            if r != rank:
+                self.lib.aps_k2_peer_close(p)
+        torch.distributed.barrier()
+        self.lib.aps_k2_peer_free(own)
+
     def init(self, state, L, off, seed, density, frac_plus):
         capi.check(self.lib.aps_k2_init_device(state.data_ptr(), L, off, seed, density, frac_plus,
                                                torch.cuda.current_stream().cuda_stream), "aps_k2_init_device")
@@ -105,11 +145,33 @@ class SublatticeLattice:
         self.flip_tab = self.be.flip_table(self.rates) if self.radius >= 0 else None
         self.buf = [self.be.zeros_u8(self.L), self.be.zeros_u8(self.L)]
         self.cur = 0
-        self.msum = [self.be.zeros_i64(1), self.be.zeros_i64(1)]
+        self.persistent = bool(getattr(self.be, "persistent", False))
+        if self.persistent:
+            # device int64[8]: [0] grid barrier, [1] error flag, [2] cumulative own flips, [3] sum(sigma) at creation, [4] current
+            self.sync = self.be.zeros_i64(8)
+            self.msum = [self.sync[4:5], self.sync[5:6]]
+        else:
+            self.msum = [self.be.zeros_i64(1), self.be.zeros_i64(1)]
         self.n_particles = 0
         self.passes_done = 0
-        self.refresh_every = max(1, (self.ghost // (max(self.radius, 0) + 2)) // 2 * 2) if self.world > 1 else 1 << 30
+        # strict staleness bound: (radius + 33) sites per pass (see the module docstring); even, so that refreshes fall on step borders
+        r0 = max(self.radius, 0)
+        self.refresh_every = max(2, ((self.ghost - r0 - 1) // (r0 + 33)) // 2 * 2) if self.world > 1 else 1 << 30
         self.since_refresh = 0
+        self._peer_own, self._peer_ptrs = None, None
+        if self.persistent and self.world > 1:
+            self._peer_own, self._peer_ptrs = self.be.peer_setup(self.rank, self.world)
+
+    def close(self):
+        """Unmap the peers' exchange regions and free the own one (collective: every rank must call it)."""
+        if self._peer_ptrs is not None:
+            self.be.peer_teardown(self.rank, self._peer_own, self._peer_ptrs)
+            self._peer_own, self._peer_ptrs = None, None
+
+    def check(self):
+        """Raise if a peer time-out made the persistent kernel give up (synchronises)."""
+        if self.persistent and int(self.sync[1].item()) != 0:
+            raise capi.ApsError("K2 persistent kernel: a peer did not arrive at a flag round (time-out); state is undefined")
 
     # ---- state ----
     @property
@@ -138,7 +200,11 @@ class SublatticeLattice:
             torch.distributed.all_reduce(t)
             tot = t.cpu()
         self.n_particles = int(tot[0] + tot[1])
-        if self.radius < 0:
+        if self.persistent:
+            self.sync.zero_()
+            self.sync[3] = int(tot[0] - tot[1])
+            self.sync[4] = int(tot[0] - tot[1])
+        elif self.radius < 0:
             self.msum[0][0] = int(tot[0] - tot[1])
 
     # ---- time stepping ----
@@ -156,6 +222,8 @@ class SublatticeLattice:
         return a
 
     def run_passes(self, n_passes):
+        if self.persistent:
+            return self._run_persistent(n_passes)
         done = 0
         sliced_global = self.world > 1 and self.radius < 0
         while done < n_passes:
@@ -176,6 +244,23 @@ class SublatticeLattice:
             done += k
             if self.world > 1 and self.since_refresh >= self.refresh_every:
                 self.exchange_ghosts()
+        return self
+
+    def _run_persistent(self, n_passes):
+        """All passes in one cooperative launch; ghost refresh / sum(sigma) exchange happen inside the kernel."""
+        a = self._args()
+        m = capi.ApsK2Multi()
+        m.n_passes, m.world, m.rank, m.refresh_every = int(n_passes), self.world, self.rank, int(min(self.refresh_every, 1 << 30))
+        m.ghost, m.own_lo, m.own_hi = self.ghost, self.own_lo - self.lo, self.own_hi - self.lo
+        m.buf0, m.buf1 = self.be.ptr(self.buf[self.cur]), self.be.ptr(self.buf[1 - self.cur])
+        m.sync = self.be.ptr(self.sync)
+        if self.world > 1:
+            for r, p in enumerate(self._peer_ptrs):
+                m.peer[r] = p
+        self.be.run_persistent(a, m)
+        if n_passes % 2:
+            self.cur = 1 - self.cur
+        self.passes_done += n_passes
         return self
 
     def run(self, n_steps):

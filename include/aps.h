@@ -313,6 +313,31 @@ int aps_k2_pass_device(const aps_k2_args* a, void* stream);
 /* n_passes passes ping-ponging between a->in and a->out (a->pass, in/out and msum are advanced in the
  * struct); the final state is in a->in after the call.  msum buffers are handled internally. */
 int aps_k2_run_device(aps_k2_args* a, int n_passes, void* stream);
+/* ---- K2, many passes per launch and slab decomposition over peer memory (NVLink) ----------------------------
+ * One cooperative launch runs n_passes passes (grid barriers between passes instead of kernel boundaries).  With
+ * world > 1 (one process per GPU; contiguous slabs with `ghost` redundant sites per interior side) the kernel itself
+ * exchanges the ghost zones (every refresh_every passes) and, in global-field mode, the 8-byte sum(sigma) increments
+ * (every pass) through peer memory mapped with CUDA IPC: release/acquire flag words, no NCCL call, no host round trip.
+ * The result is bit-identical to the single-slab run.  See csrc/aps_k2.cuh (K2PeerRegion, K2Multi). */
+typedef struct aps_k2_multi {
+    int32_t n_passes, world, rank, refresh_every;   /* refresh_every: passes between ghost refreshes (world > 1)      */
+    int64_t ghost, own_lo, own_hi;                  /* ghost sites per interior side; owned range in buffer indices  */
+    uint8_t* buf0;                                  /* pass j of the launch reads buf[j & 1], writes buf[(j+1) & 1]  */
+    uint8_t* buf1;
+    void* sync;                                     /* device int64[8], zero at creation: [0] grid-barrier counter,   */
+                                                    /* [1] error flag (peer time-out), [2] cumulative own flip sum,  */
+                                                    /* [3] sum(sigma) at creation, [4] current lattice-wide sum(sigma) */
+    void* peer[8];                                  /* exchange regions of all ranks (aps_k2_peer_*), world > 1 only  */
+} aps_k2_multi;
+/* a->pass is advanced by n_passes; the final state is in buf[n_passes & 1].  a->in/out/msum_* are ignored. */
+int aps_k2_run_persistent_device(aps_k2_args* a, const aps_k2_multi* m, void* stream);
+/* exchange region of this rank: device memory + its 64-byte CUDA IPC handle; peers map it with aps_k2_peer_open */
+int aps_k2_peer_region_bytes(void);
+int aps_k2_peer_alloc(void** region, void* ipc_handle_out_64_bytes);
+int aps_k2_peer_open(const void* ipc_handle_64_bytes, void** region);
+int aps_k2_peer_close(void* region);
+int aps_k2_peer_free(void* region);
+
 /* Bernoulli(density) occupancy, '+' with probability frac_plus */
 int aps_k2_init_device(uint8_t* state, int64_t L, int64_t global_offset, uint64_t seed, double density, double frac_plus,
                        void* stream);

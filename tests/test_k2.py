@@ -228,3 +228,78 @@ def test_config5_profiles_against_the_reference_pde():
     h_k2 = np.histogram(xs, bins=nb, range=(0, 1))[0] / len(xs)
     h_pde = pde_tot.reshape(nb, -1).sum(1) / pde_tot.sum()
     assert np.abs(h_k2 - h_pde).sum() < 0.2, np.abs(h_k2 - h_pde).sum()
+
+
+# ---------------------------------------------------------------- persistent launches, multi-GPU ----------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("sigma", [None, 5.0])
+def test_gpu_persistent_launch_equals_per_pass_launches(sigma):
+    """One cooperative launch with grid barriers between the passes == one launch per pass (and == the oracle, by the
+    tests above): same bits for any chunking of the passes, in both field modes."""
+    kw = dict(sigma_sites=sigma, seed=5, **PARAMS)
+    a = SublatticeLattice(5 * TILE, **kw)
+    b = SublatticeLattice(5 * TILE, **kw)
+    assert a.persistent
+    b.persistent = False                                  # host loop over aps_k2_pass_device launches
+    a.init_random(0.5, 0.7); b.init_random(0.5, 0.7)
+    for chunk in [1, 2, 13, 40]:
+        a.run_passes(chunk); b.run_passes(chunk)
+        assert np.array_equal(a.state.cpu().numpy(), b.state.cpu().numpy()), (sigma, chunk)
+        if sigma is None:
+            assert int(a.msum[0][0]) == int(b.msum[0][0])
+    a.check()
+    assert a.passes_done == b.passes_done == 56
+
+
+def _gpu_slab_worker(rank, world, port, q, sigma, passes):
+    try:
+        sys.path.insert(0, HERE); sys.path.insert(0, os.path.dirname(HERE))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+        torch.cuda.set_device(rank)
+        capi.check(capi.load().aps_set_device(rank), "aps_set_device")
+        torch.distributed.init_process_group("nccl", rank=rank, world_size=world)
+        kw = dict(sigma_sites=sigma, seed=11, **PARAMS)
+        lat = SublatticeLattice(4 * world * TILE, **kw)
+        lat.init_random(0.5, 0.6)
+        lat.refresh_every = 6                     # several in-kernel ghost refreshes (the strict bound allows >= 150 passes)
+        for chunk in [7, passes - 7]:
+            lat.run_passes(chunk)
+        lat.check()
+        full = lat.gather_state()
+        rp, rm = lat.profile(32)
+        one = SublatticeLattice(4 * world * TILE, single_rank=True, **kw)
+        one.init_random(0.5, 0.6)
+        one.run_passes(passes)
+        want = one.state.cpu().numpy()
+        rp1, rm1 = one.profile(32)
+        ok = bool(np.array_equal(full, want)) and bool(np.array_equal(rp, rp1)) and bool(np.array_equal(rm, rm1))
+        if sigma is None:
+            ok = ok and int(lat.msum[0][0]) == int(one.msum[0][0]) == int((want == 1).sum()) - int((want == 2).sum())
+        lat.close()
+        q.put((rank, ok, ""))
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    except Exception as exc:                      # report instead of hanging the parent on q.get
+        import traceback
+        q.put((rank, False, traceback.format_exc()[-1500:]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sigma", [5.0, None])
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_in_kernel_exchange_is_bit_identical_to_single_gpu(world, sigma):
+    """Slab decomposition over `world` GPUs of one box (one process per GPU): ghost refresh and, for sigma = None, the per-pass
+    sum(sigma) exchange happen INSIDE the persistent kernel through CUDA-IPC peer memory (NVLink).  The gathered lattice, the
+    coarse profile and the running magnetisation must equal the single-GPU run bit for bit.  Skipped on boxes with fewer GPUs."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs on one box")
+    passes = 45
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 11 * world + (200 if sigma is None else 0)
+    procs = [ctx.Process(target=_gpu_slab_worker, args=(r, world, port, q, sigma, passes)) for r in range(world)]
+    [p.start() for p in procs]
+    got = [q.get(timeout=600) for _ in range(world)]
+    [p.join(120) for p in procs]
+    for rank, ok, err in got:
+        assert ok, f"rank {rank}: slab run differs from the single-GPU run {err}"

@@ -1,35 +1,41 @@
 #!/usr/bin/env python
-"""K2 throughput / HBM-roofline probe (device-resident lattice)."""
+"""K2 pass timing on one GPU: persistent multi-pass launches vs one launch per pass, at the configuration BASELINE
+config 5 names (L = 2^26, local field sigma = 5 sites, dt = 0.005; global field, dt = 0.02) and at L = 2^30.
+Prints one JSON line per case: us per pass, GB/s (2 B per site-visit), fraction of the measured HBM copy peak,
+particle attempts per second, simulated time units per wall second."""
 import argparse, json, os, sys
-import numpy as np, torch
+import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from aps_b200.sublattice import SublatticeLattice
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--logL", type=int, default=30)
-ap.add_argument("--beta", type=float, default=2.0)
-ap.add_argument("--dt", type=float, default=0.02)
-ap.add_argument("--sigma", type=float, default=5.0)
-ap.add_argument("--passes", type=int, default=40)
-ap.add_argument("--D", type=float, default=0.02)
-ap.add_argument("--lam", type=float, default=5.0)
-ap.add_argument("--ctas-per-sm", type=int, default=0, help="persistent CTAs per SM (debug hook; 0 = library default)")
-ap.add_argument("--stash-cap", type=int, default=0, help="local-field stash capacity (debug hook; 0 = automatic)")
+ap.add_argument("--logL", type=int, nargs="+", default=[26, 30])
+ap.add_argument("--passes", type=int, default=200)
+ap.add_argument("--legacy", action="store_true", help="also time one launch per pass")
 a = ap.parse_args()
-if a.ctas_per_sm or a.stash_cap:
-    from aps_b200 import capi
-    if a.ctas_per_sm: capi.load().aps_debug_set_k2_ctas_per_sm(a.ctas_per_sm)
-    if a.stash_cap: capi.load().aps_debug_set_k2_stash_cap(a.stash_cap)
-L = 1 << a.logL
-lat = SublatticeLattice(L, D=a.D, lam=a.lam, beta=a.beta, dt=a.dt, sigma_sites=a.sigma if a.sigma > 0 else None, seed=0)
-lat.init_random(0.5, 0.5)
-lat.run_passes(6)
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); lat.run_passes(a.passes); e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / a.passes
-peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6650.0
-gbs = 2.0 * L / (ms * 1e-3) / 1e9
-print(json.dumps(dict(ctas_per_sm=a.ctas_per_sm, stash_cap=a.stash_cap, L=L, beta=a.beta, dt=a.dt, sigma=a.sigma, mu=lat.rates.mu, ms_per_pass=ms, site_visits_per_s=L / (ms * 1e-3),
-                      particle_attempts_per_s=lat.n_particles / (ms * 1e-3), hbm_gbs=gbs, frac_of_measured_peak=gbs / peak,
-                      trials_per_s=lat.rates.mu * (L / 64) / (ms * 1e-3))))
+peak = 6548.2
+pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+if os.path.exists(pk):
+    peak = json.load(open(pk))["hbm_gbs"]
+CASES = [("local sigma=5 dt=0.005", 5.0, 0.005), ("local sigma=5 dt=0.0025", 5.0, 0.0025), ("global dt=0.02", None, 0.02),
+         ("global dt=0.005", None, 0.005), ("global dt=0.0025", None, 0.0025)]
+for logL in a.logL:
+    L = 1 << logL
+    passes = a.passes if logL <= 28 else max(20, a.passes // 8)
+    for name, sigma, dt in CASES:
+        for persistent in ([True, False] if a.legacy else [True]):
+            lat = SublatticeLattice(L, D=0.02, lam=5.0, beta=2.0, dt=dt, sigma_sites=sigma, seed=0, single_rank=True)
+            lat.persistent = persistent
+            lat.init_random(0.5, 0.5)
+            lat.run_passes(6)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); lat.run_passes(passes); e1.record(); torch.cuda.synchronize()
+            lat.check()
+            us = 1e3 * e0.elapsed_time(e1) / passes
+            gbs = 2.0 * L / (us * 1e-6) / 1e9
+            print(json.dumps(dict(logL=logL, case=name, launch="persistent" if persistent else "per-pass", us_per_pass=round(us, 2),
+                                  GBs=round(gbs, 1), frac_of_hbm_peak=round(gbs / peak, 3), attempts_per_s=lat.n_particles / (us * 1e-6),
+                                  sim_time_per_s=0.5 * dt / (us * 1e-6), trials_per_half=round(lat.rates.mu, 2))), flush=True)
+            del lat
+            torch.cuda.empty_cache()
