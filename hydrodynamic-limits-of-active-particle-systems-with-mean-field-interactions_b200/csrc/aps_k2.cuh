@@ -149,7 +149,6 @@ __device__ __forceinline__ bool k2_spin(F cond, int32_t* err) {
     while (!cond()) {
         if (*reinterpret_cast<volatile int32_t*>(err)) return false;
         if (clock64() - t0 > kK2SpinLimit) { atomicExch(err, 1); return false; }
-        __nanosleep(64);
     }
     return true;
 }
@@ -204,6 +203,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     unsigned char* bufs = k2_raw + 128;
     __shared__ uint32_t thr_glob[2];
     __shared__ long long mail_sum[kK2MaxRanks];
+    __shared__ long long msum_sh;                    // MULTI, global field: lattice-wide sum(sigma) before the current pass
 
     // local-field scratch behind the ring: taps, then per warp [cap][32] acceptance words, candidate list, trial codes
     const int cap = stash_cap;
@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     if (tid == 0) {
         for (int s2 = 0; s2 < kK2Stages; ++s2) k2_mbar_init(&bars[s2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (MULTI && !LOCAL) msum_sh = *m.msum_cur;
     }
     if (LOCAL && packed) {
         for (int e = tid; e < nwords * 4; e += kK2Threads) {
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     const int sh = qpar * APS_K2_HALF - kK2Margin;
     if (!LOCAL) {
         if (tid == 0) {
-            const long long msum = MULTI ? *reinterpret_cast<volatile long long*>(m.msum_cur) : (long long)*a.msum_in;
+            const long long msum = MULTI ? msum_sh : (long long)*a.msum_in;
             const double mg = APS_DIV((double)msum, (double)a.n_particles);
             thr_glob[0] = aps_k2_flip_thr(a.rates.beta, +1, mg, a.rates.inv_cmax, a.rates.t_active);
             thr_glob[1] = aps_k2_flip_thr(a.rates.beta, -1, mg, a.rates.inv_cmax, a.rates.t_active);
@@ -307,37 +308,45 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         // slab decomposition: flips of ghost segments are recomputed by the neighbour rank and must not be counted twice
         const int dsig_on = (a.count_hi <= a.count_lo) || (abase >= a.count_lo && abase < a.count_hi);
         aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
+        // Poisson count n = #{k : w >= cdf32[k]} with a warp-uniform index (constant-bank broadcast, no divergent search)
         int ntr = 0;
-        if (seg_ok) while (ntr < (int)a.rates.n_cdf && w4.v[0] >= a.rates.cdf32[ntr]) ++ntr;
+        for (int k = 0; k < (int)a.rates.n_cdf; ++k) ntr += (int)(w4.v[0] >= a.rates.cdf32[k]);
+        if (!seg_ok) ntr = 0;
+        const uint32_t thr_p_glob = LOCAL ? 0u : thr_glob[0], thr_m_glob = LOCAL ? 0u : thr_glob[1];
         unsigned char* act = work_b + R16 + (abase - lo);
 
-        // one trial against the live tile; `acc` = acceptance of a flip for the particle found at the site
-        auto hop_or_flip = [&](int x, int cat, auto&& accept) {
-            const unsigned char v = act[x];
-            if (v == APS_K2_EMPTY) return;
-            const long long lx = abase + x;
-            if (cat == 0) {
-                if (lx > 0 && act[x - 1] == APS_K2_EMPTY) { act[x - 1] = v; act[x] = APS_K2_EMPTY; }
-            } else if (cat == 1 || (cat == 2 && v == APS_K2_PLUS)) {
-                if (lx < L - 1 && act[x + 1] == APS_K2_EMPTY) { act[x + 1] = v; act[x] = APS_K2_EMPTY; }
-            } else if (cat == 3) {
-                if (accept(v)) { act[x] = (v == APS_K2_PLUS) ? APS_K2_MINUS : APS_K2_PLUS; dsig -= dsig_on * ((v == APS_K2_PLUS) ? 2 : -2); }
-            }
+        // one trial against the live tile, branch-free (the four rate slots used to be four divergent paths: ncu counted
+        // ~125 warp-instructions per trial step): d = hop direction of the slot (0 for a flip), the neighbour byte is read
+        // unconditionally (it lies inside the staged window; at a wall the read is harmless and the move is masked off),
+        // `acc` = bit 0 / bit 1: a flip of a '+' / '-' particle is accepted.
+        // walls in 32-bit tile coordinates: abase == 0 <=> first half of the first segment, abase + 32 == L <=> last half
+        const int x_lo = (t == 0 && tid == 0 && qpar == 0) ? 0 : -1;                                   // a left hop needs x > x_lo
+        const int x_hi = (t == ntiles - 1 && tid == kK2Threads - 1 && qpar == 1) ? APS_K2_HALF - 1 : APS_K2_HALF;   // a right hop needs x < x_hi
+        auto hop_or_flip = [&](int x, int cat, uint32_t acc, bool live = true) {
+            const uint32_t v = live ? (uint32_t)act[x] : (uint32_t)APS_K2_EMPTY;
+            const int d = (cat == 0) ? -1 : (cat == 3 ? 0 : 1);
+            const uint32_t nb = act[x + d];
+            const bool inside = (cat == 0) ? (x > x_lo) : (x < x_hi);
+            const bool mv = (v != APS_K2_EMPTY) && (cat < 2 || (cat == 2 && v == APS_K2_PLUS)) && inside && (nb == APS_K2_EMPTY);
+            const bool fl = (v != APS_K2_EMPTY) && (cat == 3) && (((acc >> (v - 1u)) & 1u) != 0u);
+            if (mv) { act[x + d] = (unsigned char)v; act[x] = APS_K2_EMPTY; }
+            if (fl) { act[x] = (unsigned char)(v ^ 3u); dsig -= dsig_on * (int)(6u - 4u * v); }     // '+': -2, '-': +2
         };
-        auto category = [&](uint32_t slot) { return slot < t_left ? 0 : (slot < t_right ? 1 : (slot < t_active ? 2 : 3)); };
+        auto category = [&](uint32_t slot) { return (int)(slot >= t_left) + (int)(slot >= t_right) + (int)(slot >= t_active); };
 
-        // trial word tr of this segment (one word per trial: call 0 holds the count and trials 0..2, later calls four each);
-        // `w4` is advanced when tr enters a new call, so trials must be visited in order
-        auto trial_word = [&](int tr) {
-            if (tr >= 3 && ((tr - 3) & 3) == 0) w4 = aps_philox4x32_10(c0, c1, aps_k2_trial_call(tr), chi, k0, k1);
-            const int wsel = aps_k2_trial_word(tr);
-            return wsel == 0 ? w4.v[0] : (wsel == 1 ? w4.v[1] : (wsel == 2 ? w4.v[2] : w4.v[3]));
-        };
-        if (!LOCAL) {
-            for (int tr = 0; tr < ntr; ++tr) {
-                const uint32_t wa = trial_word(tr), slot = wa << 5;
-                hop_or_flip((int)(wa >> 27), category(slot),
-                            [&](unsigned char v) { return slot - t_active < thr_glob[v == APS_K2_PLUS ? 0 : 1]; });
+        // Philox words of the trials: call 0 holds the count and trials 0..2, call c >= 1 trials 4c-1 .. 4c+2 (one word per
+        // trial); the loops below walk the calls and address the four words of a call at compile-time positions
+        if constexpr (!LOCAL) {
+            auto do_trial = [&](uint32_t wa, bool live) {
+                const uint32_t slot = wa << 5, wb = slot - t_active;
+                hop_or_flip((int)(wa >> 27), category(slot), (uint32_t)(wb < thr_p_glob) | ((uint32_t)(wb < thr_m_glob) << 1), live);
+            };
+            if (ntr > 0) {
+                do_trial(w4.v[1], true); do_trial(w4.v[2], ntr > 1); do_trial(w4.v[3], ntr > 2);
+            }
+            for (int base = 3; base < ntr; base += 4) {
+                w4 = aps_philox4x32_10(c0, c1, 1u + (uint32_t)((base - 3) >> 2), chi, k0, k1);
+                do_trial(w4.v[0], true); do_trial(w4.v[1], base + 1 < ntr); do_trial(w4.v[2], base + 2 < ntr); do_trial(w4.v[3], base + 3 < ntr);
             }
         } else {
             const int lane = tid & 31;
@@ -353,9 +362,8 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             const int tmax = ntr < cap ? ntr : cap;
             const int it_max = __reduce_max_sync(0xffffffffu, tmax);
             int nl = 0;                                                    // warp-uniform length of the candidate list
-            for (int tr = 0; tr < it_max; ++tr) {
+            auto stash_trial = [&](int tr, uint32_t wa) {                  // warp-uniform call sites (tr < it_max)
                 const bool live = tr < tmax;
-                const uint32_t wa = live ? trial_word(tr) : 0u;
                 const uint32_t wb = (wa << 5) - t_active;                  // position inside the flip slot (flip trials only)
                 const int x = (int)(wa >> 27), cat = category(wa << 5), slot = tr * 32 + lane;
                 const bool cand = live && cat == 3;
@@ -366,6 +374,16 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
                     list[nl + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(cbase + x) | ((uint32_t)slot << 14);
                 }
                 nl += __popc(mask);
+            };
+            if (it_max > 0) stash_trial(0, w4.v[1]);
+            if (it_max > 1) stash_trial(1, w4.v[2]);
+            if (it_max > 2) stash_trial(2, w4.v[3]);
+            for (int base = 3; base < it_max; base += 4) {
+                w4 = aps_philox4x32_10(c0, c1, 1u + (uint32_t)((base - 3) >> 2), chi, k0, k1);
+                stash_trial(base, w4.v[0]);
+                if (base + 1 < it_max) stash_trial(base + 1, w4.v[1]);
+                if (base + 2 < it_max) stash_trial(base + 2, w4.v[2]);
+                if (base + 3 < it_max) stash_trial(base + 3, w4.v[3]);
             }
             __syncwarp();
             // ---- phase B: dense evaluation of the flip candidates, one per lane ----
@@ -396,14 +414,13 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             for (int tr = 0; tr < ntr; ++tr) {
                 if (tr < cap) {
                     const uint32_t code = code16[tr * 32 + lane];
-                    hop_or_flip((int)(code & 31u), (int)((code >> 5) & 3u),
-                                [&](unsigned char v) { return (code >> (v == APS_K2_PLUS ? 7 : 8)) & 1u; });
+                    hop_or_flip((int)(code & 31u), (int)((code >> 5) & 3u), code >> 7);
                 } else {
                     const aps_u32x4 wq = aps_philox4x32_10(c0, c1, aps_k2_trial_call(tr), chi, k0, k1);
                     const int wsel = aps_k2_trial_word(tr);
                     const uint32_t wa = wsel == 0 ? wq.v[0] : (wsel == 1 ? wq.v[1] : (wsel == 2 ? wq.v[2] : wq.v[3]));
                     hop_or_flip((int)(wa >> 27), category(wa << 5),
-                                [&](unsigned char v) { return ((v == APS_K2_PLUS ? ov_p : ov_m) >> (tr - cap)) & 1ULL; });
+                                (uint32_t)((ov_p >> (tr - cap)) & 1ULL) | ((uint32_t)((ov_m >> (tr - cap)) & 1ULL) << 1));
                 }
             }
         }
@@ -434,29 +451,32 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     const unsigned long long tag = (unsigned long long)pass_abs + 1ULL;
     const bool refresh = m.world > 1 && ((pass_abs + 1ULL) % (uint64_t)m.refresh_every) == 0ULL;
     if (!LOCAL) {
-        // lattice-wide sum(sigma): own cumulative increments + (in the same flag round) those of the peers
-        if (blockIdx.x == 0) {
-            const int par = (int)(pass_abs & 1ULL);
-            if (tid < m.world) {
-                const long long mine = *reinterpret_cast<volatile long long*>(m.acc);
-                if (tid == m.rank) mail_sum[tid] = mine;
-                else {
+        // lattice-wide sum(sigma) = value at creation + cumulative flip increments of every rank.  The own increments are
+        // complete (barrier A).  CTA 0 posts them into every peer's mailbox; EVERY CTA then polls the own mailboxes (local
+        // memory, written remotely over NVLink) and forms the sum itself, so no second grid barrier is needed.
+        const int par = (int)(pass_abs & 1ULL);
+        if (tid < m.world) {
+            const long long mine = *reinterpret_cast<volatile long long*>(m.acc);
+            if (tid == m.rank) mail_sum[tid] = mine;
+            else {
+                if (blockIdx.x == 0) {
                     K2PeerRegion* pr = m.peer[tid];
                     *reinterpret_cast<volatile long long*>(&pr->mail_val[par][m.rank]) = mine;
                     k2_st_release_sys(&pr->mail_tag[par][m.rank], tag);
-                    K2PeerRegion* me = m.peer[m.rank];
-                    k2_spin([&] { return k2_ld_acquire_sys(&me->mail_tag[par][tid]) == tag; }, m.err);
-                    mail_sum[tid] = *reinterpret_cast<volatile long long*>(&me->mail_val[par][tid]);
                 }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                long long s = *m.msum0;
-                for (int q = 0; q < m.world; ++q) s += mail_sum[q];
-                *reinterpret_cast<volatile long long*>(m.msum_cur) = s;
-                __threadfence();
+                K2PeerRegion* me = m.peer[m.rank];
+                k2_spin([&] { return k2_ld_acquire_sys(&me->mail_tag[par][tid]) == tag; }, m.err);
+                mail_sum[tid] = *reinterpret_cast<volatile long long*>(&me->mail_val[par][tid]);
             }
         }
+        __syncthreads();
+        if (tid == 0) {
+            long long sg = *m.msum0;
+            for (int q = 0; q < m.world; ++q) sg += mail_sum[q];
+            msum_sh = sg;
+            if (blockIdx.x == 0) *reinterpret_cast<volatile long long*>(m.msum_cur) = sg;     // for the host / the next launch
+        }
+        __syncthreads();
     }
     if (refresh) {
         // (B) stage the two owned edges, tell the neighbours, pull theirs into the ghost zones of the new state
@@ -493,10 +513,10 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             __threadfence();
         }
     }
-    if (!LOCAL || refresh) {                 // (C) the new sum / the refreshed ghosts are visible to every CTA
+    if (refresh) {                           // (C) the refreshed ghosts are visible to every CTA
         k2_grid_sync(m, bar_round);
-        if (*reinterpret_cast<volatile int32_t*>(m.err)) break;
     }
+    if (*reinterpret_cast<volatile int32_t*>(m.err)) break;
   }
 }
 

@@ -118,7 +118,8 @@ class CudaK2Backend:
 
 
 class SublatticeLattice:
-    def __init__(self, L, D, lam, beta, dt, sigma_sites=None, seed=0, backend=None, ghost=TILE, single_rank=False):
+    def __init__(self, L, D, lam, beta, dt, sigma_sites=None, seed=0, backend=None, ghost=TILE, single_rank=False,
+                 persistent=None):
         if L % TILE:
             raise ValueError(f"L must be a multiple of {TILE}")
         self.be = backend or CudaK2Backend()
@@ -145,8 +146,11 @@ class SublatticeLattice:
         self.flip_tab = self.be.flip_table(self.rates) if self.radius >= 0 else None
         self.buf = [self.be.zeros_u8(self.L), self.be.zeros_u8(self.L)]
         self.cur = 0
-        self.persistent = bool(getattr(self.be, "persistent", False))
-        if self.persistent:
+        # persistent = one cooperative multi-pass launch per run_passes() with in-kernel exchange: always with several ranks;
+        # on one GPU a launch per pass measures 5-10 % faster than a grid barrier per pass (profiles/r2_k2.md), so it is opt-in
+        self.can_persist = bool(getattr(self.be, "persistent", False))
+        self.persistent = self.can_persist and (self.world > 1 if persistent is None else bool(persistent))
+        if self.can_persist:
             # device int64[8]: [0] grid barrier, [1] error flag, [2] cumulative own flips, [3] sum(sigma) at creation, [4] current
             self.sync = self.be.zeros_i64(8)
             self.msum = [self.sync[4:5], self.sync[5:6]]
@@ -170,7 +174,7 @@ class SublatticeLattice:
 
     def check(self):
         """Raise if a peer time-out made the persistent kernel give up (synchronises)."""
-        if self.persistent and int(self.sync[1].item()) != 0:
+        if self.can_persist and int(self.sync[1].item()) != 0:
             raise capi.ApsError("K2 persistent kernel: a peer did not arrive at a flag round (time-out); state is undefined")
 
     # ---- state ----
@@ -200,7 +204,7 @@ class SublatticeLattice:
             torch.distributed.all_reduce(t)
             tot = t.cpu()
         self.n_particles = int(tot[0] + tot[1])
-        if self.persistent:
+        if self.can_persist:
             self.sync.zero_()
             self.sync[3] = int(tot[0] - tot[1])
             self.sync[4] = int(tot[0] - tot[1])

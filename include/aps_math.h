@@ -6,9 +6,8 @@
  * a bit-exact statement for every output (including event times), both sides evaluate exp/log
  * through the SAME sequence of IEEE-754 operations written below: only +, -, *, / on doubles
  * (each correctly rounded on x86-64 SSE2 and on sm_100a), no FMA contraction, no libm.
- * The algorithms are the classic fdlibm ones (argument reduction by ln2 hi/lo split plus a
- * degree-5 / degree-7 minimax polynomial); error < 1 ulp, checked against libm in
- * tests/test_math.py.
+ * log: the classic fdlibm algorithm; exp: table-driven and division-free (see aps_exp); error <= 1 ulp,
+ * checked against libm in tests/test_oracle_units.py.
  *
  * Build rules: host code must be compiled with -ffp-contract=off; device code goes through
  * the __d*_rn intrinsics, which the compiler never fuses.
@@ -52,8 +51,9 @@ APS_HD double aps_u2d(uint64_t u) {
 #endif
 }
 
-/* exp(x) for finite x; saturates to 0 / +inf outside the double range. */
-APS_HD double aps_exp(double x) {
+/* exp(x) for finite x; saturates to 0 / +inf outside the double range.  fdlibm formulation (one division); since
+ * round 2 only the out-of-range / NaN path of aps_exp below uses it. */
+APS_HD double aps_exp_fdlibm(double x) {
     const double ln2HI = 6.93147180369123816490e-01; /* 0x3fe62e42fee00000 */
     const double ln2LO = 1.90821492927058770002e-10; /* 0x3dea39ef35793c76 */
     const double invln2 = 1.44269504088896338700e+00;
@@ -94,6 +94,69 @@ APS_HD double aps_exp(double x) {
     uint64_t u = aps_d2u(y);
     u += ((uint64_t)(int64_t)k) << 52;
     return aps_u2d(u);
+}
+
+/* 2^(j/64), j = 0..63, correctly rounded (generated with 60-digit decimal arithmetic) */
+#define APS_EXP_TAB_BODY \
+    0x3ff0000000000000ULL, 0x3ff02c9a3e778061ULL, 0x3ff059b0d3158574ULL, 0x3ff0874518759bc8ULL, \
+    0x3ff0b5586cf9890fULL, 0x3ff0e3ec32d3d1a2ULL, 0x3ff11301d0125b51ULL, 0x3ff1429aaea92de0ULL, \
+    0x3ff172b83c7d517bULL, 0x3ff1a35beb6fcb75ULL, 0x3ff1d4873168b9aaULL, 0x3ff2063b88628cd6ULL, \
+    0x3ff2387a6e756238ULL, 0x3ff26b4565e27cddULL, 0x3ff29e9df51fdee1ULL, 0x3ff2d285a6e4030bULL, \
+    0x3ff306fe0a31b715ULL, 0x3ff33c08b26416ffULL, 0x3ff371a7373aa9cbULL, 0x3ff3a7db34e59ff7ULL, \
+    0x3ff3dea64c123422ULL, 0x3ff4160a21f72e2aULL, 0x3ff44e086061892dULL, 0x3ff486a2b5c13cd0ULL, \
+    0x3ff4bfdad5362a27ULL, 0x3ff4f9b2769d2ca7ULL, 0x3ff5342b569d4f82ULL, 0x3ff56f4736b527daULL, \
+    0x3ff5ab07dd485429ULL, 0x3ff5e76f15ad2148ULL, 0x3ff6247eb03a5585ULL, 0x3ff6623882552225ULL, \
+    0x3ff6a09e667f3bcdULL, 0x3ff6dfb23c651a2fULL, 0x3ff71f75e8ec5f74ULL, 0x3ff75feb564267c9ULL, \
+    0x3ff7a11473eb0187ULL, 0x3ff7e2f336cf4e62ULL, 0x3ff82589994cce13ULL, 0x3ff868d99b4492edULL, \
+    0x3ff8ace5422aa0dbULL, 0x3ff8f1ae99157736ULL, 0x3ff93737b0cdc5e5ULL, 0x3ff97d829fde4e50ULL, \
+    0x3ff9c49182a3f090ULL, 0x3ffa0c667b5de565ULL, 0x3ffa5503b23e255dULL, 0x3ffa9e6b5579fdbfULL, \
+    0x3ffae89f995ad3adULL, 0x3ffb33a2b84f15fbULL, 0x3ffb7f76f2fb5e47ULL, 0x3ffbcc1e904bc1d2ULL, \
+    0x3ffc199bdd85529cULL, 0x3ffc67f12e57d14bULL, 0x3ffcb720dcef9069ULL, 0x3ffd072d4a07897cULL, \
+    0x3ffd5818dcfba487ULL, 0x3ffda9e603db3285ULL, 0x3ffdfc97337b9b5fULL, 0x3ffe502ee78b3ff6ULL, \
+    0x3ffea4afa2a490daULL, 0x3ffefa1bee615a27ULL, 0x3fff50765b6e4540ULL, 0x3fffa7c1819e90d8ULL,
+
+static const unsigned long long aps_exp_tab_h[64] = {
+APS_EXP_TAB_BODY
+};
+#if defined(__CUDACC__)
+static __device__ const unsigned long long aps_exp_tab_d[64] = {
+APS_EXP_TAB_BODY
+};
+#endif
+
+/* exp(x), division-free (round 2: the rate refresh of K1 evaluates one exp per particle in the update window, and
+ * the fdlibm form spends ~40 instructions and ~200 cycles of latency in its division):
+ *   x = (64 m + j) ln2/64 + r,  |r| <= ln2/128,   exp(x) = 2^m * T_j * (1 + r + r^2 (1/2 + r/6 + r^2/24 + r^3/120 + r^4/720))
+ * with k = 64 m + j rounded through the 1.5*2^52 shift, the reduction in two exact-product steps (the high part of
+ * ln2/64 has 24 trailing zero bits), T_j from the table above (read through the L1 on the device) and the scaling
+ * applied to the exponent field.  Only correctly rounded +, -, * — the same operation sequence on the GPU and in the
+ * oracle.  Error <= 1 ulp (truncation r^7/5040 < 3e-20; table and final rounding 0.5 ulp each); checked against libm
+ * in tests/test_oracle_units.py.  |x| > 700 and NaN go through the fdlibm form. */
+APS_HD double aps_exp(double x) {
+    const double INV = 92.33248261689366;               /* 64 / ln2 */
+    const double SHIFT = 6755399441055744.0;            /* 1.5 * 2^52 */
+    const double C_HI = 0.010830424667801708;           /* 0x3f862e42fe000000: ln2/64, 24 trailing zero bits */
+    const double C_LO = 2.8447437476627285e-11;         /* 0x3dbf473de6af278f */
+    if (!(x >= -700.0 && x <= 700.0)) return aps_exp_fdlibm(x);
+    const double t = APS_ADD(APS_MUL(x, INV), SHIFT);
+    const double kd = APS_SUB(t, SHIFT);
+    const int32_t ki = (int32_t)(uint32_t)aps_d2u(t);   /* low word of the shifted value = k (two's complement) */
+    double r = APS_SUB(x, APS_MUL(kd, C_HI));
+    r = APS_SUB(r, APS_MUL(kd, C_LO));
+    const int j = ki & 63, m = ki >> 6;
+#if defined(__CUDA_ARCH__)
+    const double T = __longlong_as_double((long long)__ldg(&aps_exp_tab_d[j]));
+#else
+    const double T = aps_u2d(aps_exp_tab_h[j]);
+#endif
+    const double r2 = APS_MUL(r, r);
+    double q = APS_ADD(8.3333333333333332e-03, APS_MUL(r, 1.3888888888888889e-03));   /* 1/120 + r/720 */
+    q = APS_ADD(4.1666666666666664e-02, APS_MUL(r, q));                                /* 1/24 */
+    q = APS_ADD(1.6666666666666666e-01, APS_MUL(r, q));                                /* 1/6 */
+    q = APS_ADD(0.5, APS_MUL(r, q));
+    const double p = APS_ADD(r, APS_MUL(r2, q));
+    const double y = APS_ADD(T, APS_MUL(T, p));          /* in [0.99, 2.01) */
+    return aps_u2d(aps_d2u(y) + (((uint64_t)(int64_t)m) << 52));
 }
 
 /* log(x) for x > 0 (normal range). Returns -inf for 0, NaN for negatives. */

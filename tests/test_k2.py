@@ -237,10 +237,9 @@ def test_gpu_persistent_launch_equals_per_pass_launches(sigma):
     """One cooperative launch with grid barriers between the passes == one launch per pass (and == the oracle, by the
     tests above): same bits for any chunking of the passes, in both field modes."""
     kw = dict(sigma_sites=sigma, seed=5, **PARAMS)
-    a = SublatticeLattice(5 * TILE, **kw)
-    b = SublatticeLattice(5 * TILE, **kw)
-    assert a.persistent
-    b.persistent = False                                  # host loop over aps_k2_pass_device launches
+    a = SublatticeLattice(5 * TILE, persistent=True, **kw)
+    b = SublatticeLattice(5 * TILE, persistent=False, **kw)         # host loop over aps_k2_pass_device launches
+    assert a.persistent and not b.persistent
     a.init_random(0.5, 0.7); b.init_random(0.5, 0.7)
     for chunk in [1, 2, 13, 40]:
         a.run_passes(chunk); b.run_passes(chunk)
