@@ -20,6 +20,8 @@
 // Limits: single-warp CTAs, n_max <= 512 and n <= 488 per replica (<= 4 leaves in numpy's pairwise tree; larger replicas go to
 // the fast kernel like the unsorted ones), r + 1 <= RCAP, L + 2r <= LPCAP.
 #pragma once
+#include <type_traits>
+
 #include "aps_k1_fast.cuh"
 
 namespace aps {
@@ -181,19 +183,33 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     int status = APS_RUN_DONE;
     const int64_t max_events = B.max_events > 0 ? B.max_events : 0x7fffffffffffffffLL;
 
-    // local magnetisation at site p: scipy's symmetric tap order, products formed as multiplier * w (== the table entries)
-    auto local_m = [&](int p) {
+    // local magnetisation at site p: scipy's symmetric tap order, products formed as multiplier * w (== the table entries).
+    // The multipliers are 0, +-1, +-2 (K = 1: a pair of sites holds at most two particles), so multiplier * w is EXACT and
+    // fma(multiplier, w, acc) rounds once, to the same value as the reference's separate multiply and add — one DFMA per
+    // accumulator and tap instead of DMUL + DADD.  For the radius of the capacity class (r = RCAP - 1, every shipped sweep
+    // with sigma = 0.005) the tap loop has a compile-time trip count: immediate offsets, loads hoisted ahead of the chain.
+    // (`hot` selects the unrolled form: only the rate refresh of the event loop uses it, to keep the loop body in the i-cache)
+    auto local_m = [&](int p, auto hot) {
         const uint8_t* c = code + pad + p;
         const double w0 = F.wtab[r];
         const double2 m0 = F.mst[c[0]];
         double sc = APS_MUL(m0.x, w0), tc = APS_MUL(m0.y, w0);
+        if (decltype(hot)::value && r == RCAP - 1) {
+#pragma unroll
+            for (int jj = -(RCAP - 1); jj < 0; ++jj) {
+                const double2 mm = F.mst[(int)c[jj] + (int)c[-jj]];
+                const double wj = F.wtab[RCAP - 1 + jj];
+                sc = __fma_rn(mm.x, wj, sc);
+                tc = __fma_rn(mm.y, wj, tc);
+            }
+        } else {
 #pragma unroll 4
-        for (int jj = -r; jj < 0; ++jj) {
-            const int idx = (int)c[jj] + (int)c[-jj];
-            const double wj = F.wtab[r + jj];
-            const double2 mm = F.mst[idx];
-            sc = APS_ADD(sc, APS_MUL(mm.x, wj));
-            tc = APS_ADD(tc, APS_MUL(mm.y, wj));
+            for (int jj = -r; jj < 0; ++jj) {
+                const double2 mm = F.mst[(int)c[jj] + (int)c[-jj]];
+                const double wj = F.wtab[r + jj];
+                sc = __fma_rn(mm.x, wj, sc);
+                tc = __fma_rn(mm.y, wj, tc);
+            }
         }
         double m = 0.0;
         if (tc > 0.0) m = APS_DIV(sc, tc);
@@ -218,7 +234,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     auto write_field = [&](int first, int count) {
         if (!((B.record & APS_REC_MLOCAL) && B.obs_m_local)) return;
         for (int l = lane; l < L; l += 32) {
-            const double m = local_m(l);
+            const double m = local_m(l, std::false_type{});
             for (int mm = first; mm < first + count; ++mm)
                 B.obs_m_local[((size_t)rep * (size_t)M + (size_t)mm) * (size_t)L + l] = m;
         }
@@ -228,12 +244,12 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         return (l_free ? 1 : 0) | (r_free ? 2 : 0) | ((cd == 1 && r_free) ? 4 : 0);
     };
     // full rate of particle i (CLASS.py:351)
-    auto refresh = [&](int i) {
+    auto refresh = [&](int i, auto hot) {
         const int p = pos[i];
         const int cd = code[pad + p];
         const double sgd = cd == 1 ? 1.0 : -1.0;
         const double h = F.hop_tab[hop_flags(p, cd)];
-        const double m = local_m(p);
+        const double m = local_m(p, hot);
         rates[i] = APS_ADD(h, aps_exp(APS_MUL(APS_MUL(-beta, sgd), m)));
         F.dirty_c[i >> cs_shift] = 1;
         int lf = (i >= ls1) + (i >= ls2) + (i >= ls3);
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     };
     auto code_put = [&](int x, int delta) { code_add(code, L, pad, x, delta); };
 
-    for (int i = lane; i < n; i += 32) refresh(i);
+    for (int i = lane; i < n; i += 32) refresh(i, std::false_type{});
     if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
     __syncwarp();
     double next_obs = (obs_idx < M) ? B.times_obs[obs_idx] : 0.0;
@@ -471,7 +487,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                 count += __popc(mask);
                 if (count >= 32 || s0 + 32 > whi) {                    // the list holds at most 64 entries
                     __syncwarp();
-                    for (int j0 = 0; j0 < count; j0 += 32) { const int j = j0 + lane; if (j < count) refresh(F.list[j]); }
+                    for (int j0 = 0; j0 < count; j0 += 32) { const int j = j0 + lane; if (j < count) refresh(F.list[j], std::true_type{}); }
                     __syncwarp();
                     count = 0;
                 }
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             for (int i0 = ilo; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
                 const bool in = i < n && (int)pos[i < n ? i : n - 1] <= whi;
-                if (in) refresh(i);
+                if (in) refresh(i, std::true_type{});
                 if (!__all_sync(0xffffffffu, in)) break;
             }
         }
