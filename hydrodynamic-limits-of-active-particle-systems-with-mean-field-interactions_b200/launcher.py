@@ -476,41 +476,61 @@ def sweep_betas_for_structures(beta_values, n_runs_per_beta, ps_kwargs, init_kwa
     sweep_beta_structure_ensemble (:105-165).  `raw` holds one entry per run with the per-run observables and a light
     `out` dict (`times_obs`, `fft_amp_list` restricted to the first `k_keep` modes, `var_list`, `m_global`) — enough
     for the driver's time-series analyses (time_to_pattern, lowk_variance_time, extract_growth_rate; k <= 25 there)
-    without downloading the (M, L) arrays.  Single rank; shard beta values over ranks by calling it with subsets."""
+    without downloading the (M, L) arrays.
+    Multi-GPU: the beta values are dealt to the ranks in strides (rank r takes betas r, r+world, ...: the event rate grows
+    with beta), every rank runs its betas in one launch and analyses them on its device; the per-beta result dicts (a few
+    KB each) are exchanged with one all_gather_object, so every rank returns the full dict."""
     from .capi import APS_REC_MLOCAL
-    spec = build_beta_sweep_spec(beta_values, n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, base_seed=base_seed)
-    spec.record = APS_REC_COUNTS | APS_REC_POS | APS_REC_MLOCAL
-    ens = DeviceEnsemble(spec, 0, len(spec.betas))
-    ens.init_particles()
-    ens.rb.run_philox()
-    amp, total, var = fft_amplitudes(ens.rb)
-    obs = {k: v.cpu().numpy() for k, v in structure_observables(ens.rb, start_fraction, k_max, amp=amp, var=var).items()}
-    nb, nr = len(beta_values), n_runs_per_beta
-    if keep_raw:
-        amp_h = amp[:, :, :k_keep].cpu().numpy()
-        var_h = var.cpu().numpy()
-        n_h = np.maximum(1, ens.n.cpu().numpy()).astype(float)
-        mg_h = ens.rb.obs_sigma_sum.cpu().numpy() / n_h[:, None]
-    results = {}
-    for b, beta in enumerate(beta_values):
-        sl = slice(b * nr, (b + 1) * nr)
-        se = lambda x: x.std(ddof=1) / np.sqrt(nr)
-        results[beta] = {
-            "var_mean": obs["var_mean"][sl].mean(), "var_se": se(obs["var_mean"][sl]),
-            "low_k_power_mean": obs["low_k_power"][sl].mean(), "low_k_power_se": se(obs["low_k_power"][sl]),
-            "dominant_k_mode": int(np.round(obs["dominant_k"][sl].mean())),
-            "m_local_var_mean": obs["m_local_var"][sl].mean(), "m_local_var_se": se(obs["m_local_var"][sl]),
-            "fft_mean_mean": obs["fft_mean"][sl].mean(axis=0),
-            "fft_mean_se": obs["fft_mean"][sl].std(axis=0, ddof=1) / np.sqrt(nr),
-            "lowk_var_mean": obs["lowk_variance"][sl].mean(), "lowk_var_se": se(obs["lowk_variance"][sl]),
-            "n_events": ens.rb.n_events[sl].cpu().numpy(),
-        }
+    rank, world = dist_info()
+    beta_values = list(beta_values)
+    seeds_all = replica_seeds(np.repeat(np.arange(len(beta_values)), n_runs_per_beta),
+                              np.tile(np.arange(n_runs_per_beta), len(beta_values)), base_seed)
+    if world > 1 and base_seed is None:          # fresh entropy must be the same on every rank: rank 0 decides
+        box = [seeds_all]
+        torch.distributed.broadcast_object_list(box, src=0)
+        seeds_all = box[0]
+    mine = list(range(rank, len(beta_values), world))
+    results_local = {}
+    if mine:
+        spec = build_beta_sweep_spec([beta_values[i] for i in mine], n_runs_per_beta, ps_kwargs, init_kwargs, run_kwargs, base_seed=0)
+        spec.seeds = np.concatenate([seeds_all[i * n_runs_per_beta:(i + 1) * n_runs_per_beta] for i in mine])
+        spec.record = APS_REC_COUNTS | APS_REC_POS | APS_REC_MLOCAL
+        ens = DeviceEnsemble(spec, 0, len(spec.betas))
+        ens.init_particles()
+        ens.rb.run_philox()
+        amp, total, var = fft_amplitudes(ens.rb)
+        obs = {k: v.cpu().numpy() for k, v in structure_observables(ens.rb, start_fraction, k_max, amp=amp, var=var).items()}
+        nr = n_runs_per_beta
+        n_events = ens.rb.n_events.cpu().numpy()
         if keep_raw:
-            results[beta]["raw"] = [
-                dict({k: (obs[k][r] if obs[k].ndim > 1 else obs[k][r].item()) for k in obs},
-                     out=dict(times_obs=ens.times_obs, fft_amp_list=amp_h[r], var_list=var_h[r], m_global=mg_h[r]))
-                for r in range(b * nr, (b + 1) * nr)]
-    return results
+            amp_h = amp[:, :, :k_keep].cpu().numpy()
+            var_h = var.cpu().numpy()
+            n_h = np.maximum(1, ens.n.cpu().numpy()).astype(float)
+            mg_h = ens.rb.obs_sigma_sum.cpu().numpy() / n_h[:, None]
+        for b, i in enumerate(mine):
+            sl = slice(b * nr, (b + 1) * nr)
+            se = lambda x: x.std(ddof=1) / np.sqrt(nr)
+            res = {
+                "var_mean": obs["var_mean"][sl].mean(), "var_se": se(obs["var_mean"][sl]),
+                "low_k_power_mean": obs["low_k_power"][sl].mean(), "low_k_power_se": se(obs["low_k_power"][sl]),
+                "dominant_k_mode": int(np.round(obs["dominant_k"][sl].mean())),
+                "m_local_var_mean": obs["m_local_var"][sl].mean(), "m_local_var_se": se(obs["m_local_var"][sl]),
+                "fft_mean_mean": obs["fft_mean"][sl].mean(axis=0),
+                "fft_mean_se": obs["fft_mean"][sl].std(axis=0, ddof=1) / np.sqrt(nr),
+                "lowk_var_mean": obs["lowk_variance"][sl].mean(), "lowk_var_se": se(obs["lowk_variance"][sl]),
+                "n_events": n_events[sl],
+            }
+            if keep_raw:
+                res["raw"] = [
+                    dict({k: (obs[k][r] if obs[k].ndim > 1 else obs[k][r].item()) for k in obs},
+                         out=dict(times_obs=ens.times_obs, fft_amp_list=amp_h[r], var_list=var_h[r], m_global=mg_h[r]))
+                    for r in range(b * nr, (b + 1) * nr)]
+            results_local[i] = res
+    if world > 1:
+        parts = [None] * world
+        torch.distributed.all_gather_object(parts, results_local)
+        results_local = {i: r for part in parts for i, r in part.items()}
+    return {beta_values[i]: results_local[i] for i in range(len(beta_values))}
 
 
 def sweep_over_sigmas(sigma_values, beta_values, n_runs_per_beta=5, ps_kwargs=None, init_kwargs=None, run_kwargs=None,

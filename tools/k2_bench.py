@@ -11,6 +11,7 @@ from aps_b200.sublattice import SublatticeLattice
 ap = argparse.ArgumentParser()
 ap.add_argument("--logL", type=int, nargs="+", default=[26, 30])
 ap.add_argument("--passes", type=int, default=200)
+ap.add_argument("--case", default="", help="substring filter on the case names")
 ap.add_argument("--legacy", action="store_true", help="also time the persistent multi-pass launch (grid barrier per pass)")
 a = ap.parse_args()
 peak = 6548.2
@@ -23,6 +24,8 @@ for logL in a.logL:
     L = 1 << logL
     passes = a.passes if logL <= 28 else max(20, a.passes // 8)
     for name, sigma, dt in CASES:
+        if a.case not in name:
+            continue
         for persistent in ([False, True] if a.legacy else [False]):
             lat = SublatticeLattice(L, D=0.02, lam=5.0, beta=2.0, dt=dt, sigma_sites=sigma, seed=0, single_rank=True,
                                     persistent=persistent)
