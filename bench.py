@@ -184,6 +184,7 @@ class ReferencePool:
         import multiprocessing as mp
         self.cores = cores
         self.pool = mp.get_context("spawn").Pool(cores)
+        self.pool.map(_ref_worker, [("config2", 1.0, 500, i, 0.05) for i in range(2 * cores)], chunksize=1)   # imports, untimed
 
     def step(self, wl, T, seed0):
         pts = sample_points(wl, self.cores)

@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     __shared__ uint32_t thr_glob[2];
     __shared__ long long mail_sum[kK2MaxRanks];
     __shared__ long long msum_sh;                    // MULTI, global field: lattice-wide sum(sigma) before the current pass
+    __shared__ uint32_t cdf_sh[APS_K2_MAX_TRIALS];   // Poisson cdf thresholds for the per-lane binary search of the trial count
 
     // local-field scratch behind the ring: taps, then per warp [cap][32] acceptance words, candidate list, trial codes
     const int cap = stash_cap;
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (MULTI && !LOCAL) msum_sh = *m.msum_cur;
     }
+    if (tid < APS_K2_MAX_TRIALS) cdf_sh[tid] = a.rates.cdf32[tid];
     if (LOCAL && packed) {
         for (int e = tid; e < nwords * 4; e += kK2Threads) {
             const int k = e >> 2, sft = e & 3;
@@ -308,38 +310,49 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         // slab decomposition: flips of ghost segments are recomputed by the neighbour rank and must not be counted twice
         const int dsig_on = (a.count_hi <= a.count_lo) || (abase >= a.count_lo && abase < a.count_hi);
         aps_u32x4 w4 = aps_philox4x32_10(c0, c1, 0u, chi, k0, k1);
-        // Poisson count n = #{k : w >= cdf32[k]} with a warp-uniform index (constant-bank broadcast, no divergent search)
+        // Poisson count n = #{k < n_cdf : w >= cdf32[k]} (cdf32 is non-decreasing): branch-free binary search in shared memory
         int ntr = 0;
-        for (int k = 0; k < (int)a.rates.n_cdf; ++k) ntr += (int)(w4.v[0] >= a.rates.cdf32[k]);
+#pragma unroll
+        for (int stp = APS_K2_MAX_TRIALS / 2; stp >= 1; stp >>= 1) {
+            const int k = ntr + stp;
+            if (k <= (int)a.rates.n_cdf && w4.v[0] >= cdf_sh[k - 1]) ntr = k;
+        }
         if (!seg_ok) ntr = 0;
         const uint32_t thr_p_glob = LOCAL ? 0u : thr_glob[0], thr_m_glob = LOCAL ? 0u : thr_glob[1];
         unsigned char* act = work_b + R16 + (abase - lo);
 
-        // one trial against the live tile, branch-free (the four rate slots used to be four divergent paths: ncu counted
-        // ~125 warp-instructions per trial step): d = hop direction of the slot (0 for a flip), the neighbour byte is read
-        // unconditionally (it lies inside the staged window; at a wall the read is harmless and the move is masked off),
-        // `acc` = bit 0 / bit 1: a flip of a '+' / '-' particle is accepted.
-        // walls in 32-bit tile coordinates: abase == 0 <=> first half of the first segment, abase + 32 == L <=> last half
-        const int x_lo = (t == 0 && tid == 0 && qpar == 0) ? 0 : -1;                                   // a left hop needs x > x_lo
-        const int x_hi = (t == ntiles - 1 && tid == kK2Threads - 1 && qpar == 1) ? APS_K2_HALF - 1 : APS_K2_HALF;   // a right hop needs x < x_hi
-        auto hop_or_flip = [&](int x, int cat, uint32_t acc, bool live = true) {
-            const uint32_t v = live ? (uint32_t)act[x] : (uint32_t)APS_K2_EMPTY;
-            const int d = (cat == 0) ? -1 : (cat == 3 ? 0 : 1);
-            const uint32_t nb = act[x + d];
-            const bool inside = (cat == 0) ? (x > x_lo) : (x < x_hi);
-            const bool mv = (v != APS_K2_EMPTY) && (cat < 2 || (cat == 2 && v == APS_K2_PLUS)) && inside && (nb == APS_K2_EMPTY);
-            const bool fl = (v != APS_K2_EMPTY) && (cat == 3) && (((acc >> (v - 1u)) & 1u) != 0u);
-            if (mv) { act[x + d] = (unsigned char)v; act[x] = APS_K2_EMPTY; }
-            if (fl) { act[x] = (unsigned char)(v ^ 3u); dsig -= dsig_on * (int)(6u - 4u * v); }     // '+': -2, '-': +2
+        // one trial against the live tile, written on predicates (ncu, round 2: the four rate slots as four divergent paths cost
+        // ~125 warp-instructions per trial step, the first branch-free form with an integer slot category still ~70):
+        //   left / flip / active = position of the rate slot; d = hop direction (0 for a flip); the neighbour byte is read
+        //   unconditionally (it lies inside the staged window); acc_p / acc_m = a flip of a '+' / '-' particle is accepted.
+        // Reflecting walls: the byte beyond the first / last lattice site is a non-empty SENTINEL in the staged window, so
+        // "neighbour empty" fails there by itself (no wall test per trial); see set_wall_sentinels below.
+        const int dsig2 = 2 * dsig_on;
+        auto apply = [&](uint32_t x, bool is_left, bool is_flip, bool is_act, bool acc_p, bool acc_m, bool live) {
+            unsigned char* px = act + x;
+            const uint32_t v = *px;
+            const int d = is_left ? -1 : (is_flip ? 0 : 1);
+            const uint32_t nb = px[d];
+            const bool plus = v == APS_K2_PLUS;
+            const bool part = live && v != APS_K2_EMPTY;
+            const bool mv = part && !is_flip && (!is_act || plus) && nb == APS_K2_EMPTY;
+            const bool fl = part && is_flip && (plus ? acc_p : acc_m);
+            if (mv) { px[d] = (unsigned char)v; *px = APS_K2_EMPTY; }
+            if (fl) { *px = (unsigned char)(v ^ 3u); dsig += plus ? -dsig2 : dsig2; }     // '+' -> '-': -2, '-' -> '+': +2
+        };
+        auto set_wall_sentinels = [&]() {        // only the two threads that own the wall segments touch these bytes
+            if (t == 0 && tid == 0 && qpar == 0) act[-1] = 0xFF;
+            if (t == ntiles - 1 && tid == kK2Threads - 1 && qpar == 1) act[APS_K2_HALF] = 0xFF;
         };
         auto category = [&](uint32_t slot) { return (int)(slot >= t_left) + (int)(slot >= t_right) + (int)(slot >= t_active); };
 
         // Philox words of the trials: call 0 holds the count and trials 0..2, call c >= 1 trials 4c-1 .. 4c+2 (one word per
         // trial); the loops below walk the calls and address the four words of a call at compile-time positions
         if constexpr (!LOCAL) {
+            set_wall_sentinels();
             auto do_trial = [&](uint32_t wa, bool live) {
                 const uint32_t slot = wa << 5, wb = slot - t_active;
-                hop_or_flip((int)(wa >> 27), category(slot), (uint32_t)(wb < thr_p_glob) | ((uint32_t)(wb < thr_m_glob) << 1), live);
+                apply(wa >> 27, slot < t_left, slot >= t_active, slot >= t_right && slot < t_active, wb < thr_p_glob, wb < thr_m_glob, live);
             };
             if (ntr > 0) {
                 do_trial(w4.v[1], true); do_trial(w4.v[2], ntr > 1); do_trial(w4.v[3], ntr > 2);
@@ -410,17 +423,20 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
                 }
             }
             __syncthreads();                                               // every field of the tile has been read
+            set_wall_sentinels();                                          // (the reflect padding of phase B is no longer needed)
             // ---- phase C: replay the trials in order against the live tile ----
             for (int tr = 0; tr < ntr; ++tr) {
                 if (tr < cap) {
                     const uint32_t code = code16[tr * 32 + lane];
-                    hop_or_flip((int)(code & 31u), (int)((code >> 5) & 3u), code >> 7);
+                    const uint32_t cat = code & 0x60u;
+                    apply(code & 31u, cat == 0u, cat == 0x60u, cat == 0x40u, (code & 0x80u) != 0u, (code & 0x100u) != 0u, true);
                 } else {
                     const aps_u32x4 wq = aps_philox4x32_10(c0, c1, aps_k2_trial_call(tr), chi, k0, k1);
                     const int wsel = aps_k2_trial_word(tr);
                     const uint32_t wa = wsel == 0 ? wq.v[0] : (wsel == 1 ? wq.v[1] : (wsel == 2 ? wq.v[2] : wq.v[3]));
-                    hop_or_flip((int)(wa >> 27), category(wa << 5),
-                                (uint32_t)((ov_p >> (tr - cap)) & 1ULL) | ((uint32_t)((ov_m >> (tr - cap)) & 1ULL) << 1));
+                    const uint32_t slot = wa << 5;
+                    apply(wa >> 27, slot < t_left, slot >= t_active, slot >= t_right && slot < t_active,
+                          ((ov_p >> (tr - cap)) & 1ULL) != 0ULL, ((ov_m >> (tr - cap)) & 1ULL) != 0ULL, true);
                 }
             }
         }

@@ -196,6 +196,11 @@ class SublatticeLattice:
         self.buf[1 - self.cur] = self.be.zeros_u8(self.L)
         self._recount()
 
+    def set_state_from_host(self, host_state):
+        """Load this rank's slab from a full-lattice uint8 tensor in (pinned) host memory: the H2D leg of the end-to-end path."""
+        self.buf[self.cur].copy_(host_state[self.lo:self.hi], non_blocking=True)
+        self._recount()
+
     def _recount(self):
         npl, nmi = self.be.count(self.owned())
         tot = torch.tensor([npl, nmi], dtype=torch.int64)

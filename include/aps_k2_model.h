@@ -63,7 +63,18 @@ APS_HD int aps_k2_trial_word(int tr) { return tr < 3 ? tr + 1 : ((tr - 3) & 3); 
 APS_HD int aps_k2_mq_index(int sw, int tw) {
     if (tw <= 0) return APS_K2_MQ;
     int num = sw * APS_K2_MQ;                       /* |sw| <= sum of taps ~ 2^16 -> fits in 32 bits */
+#if defined(__CUDA_ARCH__)
+    /* same truncated quotient as the C division below, without the ~50-instruction integer-division sequence: fp32
+     * estimate (|quotient| <= ~1024, so it is within +-1) corrected by the exact remainder */
+    const int an = (num >= 0 ? num : -num) + tw / 2;
+    int q = (int)(__int2float_rz(an) * __frcp_rn(__int2float_rn(tw)));
+    int rem = an - q * tw;
+    if (rem < 0) { --q; rem += tw; }
+    if (rem >= tw) ++q;
+    if (num < 0) q = -q;
+#else
     int q = (num >= 0 ? num + tw / 2 : num - tw / 2) / tw;
+#endif
     if (q < -APS_K2_MQ) q = -APS_K2_MQ;
     if (q > APS_K2_MQ) q = APS_K2_MQ;
     return (int)q + APS_K2_MQ;
