@@ -122,7 +122,8 @@ class ApsProfileArgs(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("reps_per_point", C.c_int32), ("M", C.c_int32), ("L", C.c_int32),
                 ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("dx", C.c_double), ("n", C.c_void_p),
                 ("n_obs", C.c_void_p), ("obs_cp", C.c_void_p), ("obs_cm", C.c_void_p), ("prof", C.c_void_p),
-                ("point_start", C.c_void_p), ("point_reps", C.c_void_p)]
+                ("point_start", C.c_void_p), ("point_reps", C.c_void_p), ("scratch", C.c_void_p),
+                ("n_replicas", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ApsHistArgs(C.Structure):

@@ -347,6 +347,21 @@ int aps_profile_sums_device(const aps_profile_args* a, void* stream) {
         return fail(APS_ERR_INVALID, "aps_profile_sums: bad argument");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
     if (a->n_points == 0) return APS_OK;
+    if (a->point_start && a->scratch) {
+        // replica lists: (1) one CTA row per replica (all replicas in parallel) into the scratch rows, (2) per-point gather-sum
+        const int R = a->n_replicas;
+        if (R < 1) return fail(APS_ERR_INVALID, "aps_profile_sums: n_replicas needed with point lists and scratch");
+        aps_profile_args one = *a;
+        one.n_points = R; one.reps_per_point = 1; one.point_start = nullptr; one.point_reps = nullptr; one.prof = a->scratch;
+        dim3 g1((a->L + 127) / 128, R);
+        aps::profile_kernel<<<g1, 128, 0, (cudaStream_t)stream>>>(one);
+        CU(cudaGetLastError());
+        dim3 g2((a->L + 127) / 128, a->n_points);
+        aps::profile_gather_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(a->scratch, a->point_start, a->point_reps, a->prof, a->L);
+        CU(cudaGetLastError());
+        g_launches.fetch_add(2);
+        return APS_OK;
+    }
     dim3 grid((a->L + 127) / 128, a->n_points);
     aps::profile_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
     CU(cudaGetLastError());

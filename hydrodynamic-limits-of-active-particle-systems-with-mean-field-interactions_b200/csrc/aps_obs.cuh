@@ -311,6 +311,24 @@ __global__ void profile_kernel(aps_profile_args a) {
     o[l] = sp; o[L + l] = sm; o[2 * L + l] = sp2; o[3 * L + l] = sm2;
 }
 
+// Per-point sums from per-replica rows: out[g][q][l] = sum over the replicas of point g (CSR list, ascending: a fixed
+// summation order, so the result does not depend on the launch geometry) of per_rep[rep][q][l].  q = 0,1: time-averaged
+// rho_plus / rho_minus of the replica (profile_kernel with reps_per_point = 1), q = 2,3: their squares are formed here.
+__global__ void profile_gather_kernel(const double* __restrict__ per_rep, const int32_t* __restrict__ point_start,
+                                      const int32_t* __restrict__ point_reps, double* __restrict__ out, int L) {
+    const int g = blockIdx.y;
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= L) return;
+    double sp = 0.0, sm = 0.0, sp2 = 0.0, sm2 = 0.0;
+    for (int j = point_start[g]; j < point_start[g + 1]; ++j) {
+        const double* row = per_rep + (size_t)point_reps[j] * 4 * L;
+        const double mp = row[l], mm = row[L + l];
+        sp += mp; sm += mm; sp2 += mp * mp; sm2 += mm * mm;
+    }
+    double* o = out + (size_t)g * 4 * L;
+    o[l] = sp; o[L + l] = sm; o[2 * L + l] = sp2; o[3 * L + l] = sm2;
+}
+
 // One thread per replica: time-averaged m_global over a row window -> per-grid-point histogram (integer atomics).
 __global__ void hist_kernel(aps_hist_args a) {
     const int rep = blockIdx.x * blockDim.x + threadIdx.x;

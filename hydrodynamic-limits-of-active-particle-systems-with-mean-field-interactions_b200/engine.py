@@ -212,9 +212,11 @@ class ReplicaBatch:
         row_lo = self.M // 2 if row_lo is None else row_lo
         row_hi = self.M if row_hi is None else row_hi
         prof = torch.empty((n_points, 4, self.L), dtype=torch.float64, device=self.dev)
+        if getattr(self, "_prof_scratch", None) is None:
+            self._prof_scratch = torch.empty((self.R, 4, self.L), dtype=torch.float64, device=self.dev)
         a = ApsProfileArgs(n_points, 0, self.M, self.L, row_lo, row_hi, self.dx, self.n.data_ptr(), self.n_obs.data_ptr(),
                            self.obs_cp.data_ptr(), self.obs_cm.data_ptr(), prof.data_ptr(), point_start.data_ptr(),
-                           point_reps.data_ptr())
+                           point_reps.data_ptr(), self._prof_scratch.data_ptr(), self.R, 0)
         capi.check(self.lib.aps_profile_sums_device(a, _stream()), "aps_profile_sums_device")
         return prof
 

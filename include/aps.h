@@ -261,6 +261,8 @@ typedef struct aps_profile_args {
     double* prof;
     const int32_t* point_start; /* [n_points+1] optional                                          */
     const int32_t* point_reps;  /* [point_start[n_points]] replica indices, ascending per point   */
+    double* scratch;            /* optional [n_replicas][4][L]: with point lists, the replicas are reduced in parallel */
+    int32_t n_replicas, reserved; /* into these rows first and then summed per point (same values, more parallelism) */
 } aps_profile_args;
 int aps_profile_sums_device(const aps_profile_args* a, void* stream);
 
