@@ -54,15 +54,19 @@ for dt in [0.02, 0.01, 0.005, 0.0025]:
         mk.append(((st == 1).sum() - (st == 2).sum()) / n[s]); xk.append((x * (st != 0)).sum() / n[s])
     rows.append((f"K2, dt = {dt}", np.array(mk), np.array(xk)))
 se = lambda v: v.std(ddof=1) / np.sqrt(len(v))
-out = ["| method | m(T=1.5) | bias of m | in combined SE | mean position | bias | in combined SE |", "|---|---|---|---|---|---|---|"]
+# paired statistics: lattice s starts from the same state in every method, so the bias estimate is the mean over lattices of
+# the per-lattice difference (the spread of the initial configurations cancels); positions in lattice sites
+out = ["| method | m(T=1.5) | bias of m (paired) | in SE | mean displacement (sites) | bias (paired, sites) | in SE |", "|---|---|---|---|---|---|---|"]
+x0 = np.array([(x * (states[s] != 0)).sum() / n[s] for s in range(R)])
 res = []
 for name, m, xx in rows:
-    bm, bx = m.mean() - m_exact.mean(), xx.mean() - x_exact.mean()
-    sm, sx = np.hypot(se(m), se(m_exact)), np.hypot(se(xx), se(x_exact))
+    dm, dx = m - m_exact, (xx - x_exact) * L
     first = name.startswith("exact")
-    out.append(f"| {name} | {m.mean():.5f} +- {se(m):.5f} | {'' if first else f'{bm:+.5f}'} | {'' if first else f'{bm / sm:+.1f}'} | "
-               f"{xx.mean():.6f} +- {se(xx):.6f} | {'' if first else f'{bx:+.6f}'} | {'' if first else f'{bx / sx:+.1f}'} |")
-    res.append(dict(method=name, m_mean=float(m.mean()), m_se=float(se(m)), x_mean=float(xx.mean()), x_se=float(se(xx))))
+    disp = (xx - x0) * L
+    out.append(f"| {name} | {m.mean():.5f} +- {se(m):.5f} | {'' if first else f'{dm.mean():+.5f} +- {se(dm):.5f}'} | {'' if first else f'{dm.mean() / se(dm):+.1f}'} | "
+               f"{disp.mean():.4f} +- {se(disp):.4f} | {'' if first else f'{dx.mean():+.4f} +- {se(dx):.4f}'} | {'' if first else f'{dx.mean() / se(dx):+.1f}'} |")
+    res.append(dict(method=name, m_mean=float(m.mean()), m_se=float(se(m)), m_bias=float(dm.mean()), m_bias_se=float(se(dm)),
+                    displacement_sites=float(disp.mean()), displacement_bias_sites=float(dx.mean()), displacement_bias_se=float(se(dx))))
 print(f"R = {R} lattices of L = {L}, ~{int(n.mean())} particles each, m(0) = {float(((states == 1).sum(1) - (states == 2).sum(1)).mean() / n.mean()):.3f}\n")
 print("\n".join(out))
 if a.out:
