@@ -1,0 +1,520 @@
+// aps_k1_pair.cuh — K1 with TWO replicas per warp (one per half-warp of 16 lanes), same arithmetic as aps_k1_lean.cuh.
+//
+// Why (round 2): ncu on the lean kernel (profiles/r1_k1_lean.md) counted 1144 warp-instructions per event at 17.6 of 32 active
+// lanes and 72 % issue-slot utilisation with the 28 replica-warps of an SM resident; at half that occupancy the same replicas run
+// 22 % faster per event (bench.py, 2048 replicas per GPU: 67.5 ms instead of 86.6 ms), i.e. the warps queue for issue slots.  The
+// phases of an event never need more than ~16 lanes — the update window holds ~16 particles, a leaf of numpy's pairwise sum uses
+// 8 lanes, <= 16 selection chunks of 32 rates cover n <= 512 — so two replicas can share one warp: every warp instruction then
+// advances two events, the issue pressure per event halves, and the per-replica shared-memory image stays the same.
+// The two halves execute the same code on their own shared-memory image; every warp collective is restricted to the half
+// (`hmask`, shuffle width 16), so the halves only share the instruction stream, never data.  Where their control flow differs
+// (flip vs hop, one or two refresh passes, an observation row, the guard-band slow path, the end of a run) the hardware runs the
+// two sides one after the other and re-converges — correctness never depends on convergence, only the instruction saving does.
+// Limits as aps_k1_lean.cuh: n <= 488 (NCAP 512) / 968 (NCAP 1024), r + 1 <= RCAP, L + 2r <= LPCAP; sorted particles unless WHO.
+#pragma once
+#include <type_traits>
+
+#include "aps_k1_lean.cuh"
+
+namespace aps {
+
+constexpr int kPairLanes = 16;
+
+template <int RCAP, int LPCAP, int NCAP, bool WHO>
+__host__ __device__ inline size_t k1_pair_image_bytes() {   // one replica (16-byte multiple)
+    return (k1_lean_smem_bytes<RCAP, LPCAP, NCAP, WHO>() + 15) & ~(size_t)15;
+}
+
+template <bool PHILOX, int RCAP, int LPCAP, int NCAP, bool WHO>
+__global__ void __launch_bounds__(32, NCAP <= 512 ? 15 : 7) k1_pair_kernel(const __grid_constant__ K1Args A) {
+    constexpr int LPR = kPairLanes;
+    constexpr int kNMax = NCAP <= 512 ? kLeanNMax : 968;
+    constexpr int kLeafRounds = (NCAP <= 512 ? 4 : 8) / (LPR / 8);      // 8-lane groups per half: LPR / 8
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const aps_params& P = A.p;
+    const aps_batch& B = A.b;
+    const int lane32 = threadIdx.x;
+    const int half = lane32 >> 4;
+    const int lane = lane32 & (LPR - 1);
+    const int hshift = half * LPR;
+    const unsigned hmask = 0xffffu << hshift;
+    const int rep = 2 * blockIdx.x + half;
+    if (rep >= B.n_replicas) return;
+    const int L = P.L, r = P.radius, pad = r, n_max = B.n_max, M = B.M;
+    const int n = B.n[rep];
+    const double beta = B.beta[rep], T = P.T, D = P.rate_diffusion, lam = P.rate_active;
+    auto ballot = [&](bool p) { return (__ballot_sync(hmask, p) >> hshift) & 0xffffu; };
+
+    if (A.only_retry == 2 && B.status[rep] != APS_RUN_RETRY_FAST) return;
+    unsigned char* const base = smem_raw + (size_t)half * k1_pair_image_bytes<RCAP, LPCAP, NCAP, WHO>();
+    LeanFixed<RCAP>& F = *reinterpret_cast<LeanFixed<RCAP>*>(base);
+    unsigned char* dyn = base + ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15);
+    double* const rates = reinterpret_cast<double*>(dyn); dyn += (size_t)NCAP * 8;
+    uint16_t* const pos = reinterpret_cast<uint16_t*>(dyn); dyn += (size_t)NCAP * 2;
+    uint16_t* const who = reinterpret_cast<uint16_t*>(dyn); dyn += WHO ? (size_t)LPCAP * 2 : 0;
+    uint8_t* const code = dyn;
+
+    // ---------------- prologue ----------------
+    for (int i = lane; i < L + 2 * pad; i += LPR) code[i] = 0;
+    if (WHO) for (int i = lane; i < L; i += LPR) who[i] = 0xFFFFu;
+    for (int i = lane; i <= r; i += LPR) F.wtab[i] = B.weights[i];
+    if (lane < 9) { const int am = lane / 3, ap = lane - am * 3; F.mst[lane] = make_double2((double)(ap - am), (double)(ap + am)); }
+    F.desc[lane] = 0;
+    F.dirty_c[lane] = 1; F.dirty_c[lane + LPR] = 1;
+    if (lane < 8) F.dirty_leaf[lane] = 1;
+    if (lane < 8) {
+        const double dz = APS_MUL(D, 0.0);
+        F.hop_tab[lane] = APS_ADD(APS_ADD((lane & 1) ? D : dz, (lane & 2) ? D : dz), (lane & 4) ? lam : 0.0);
+    }
+    __syncwarp(hmask);
+    int S = 0;
+    bool unsorted = false;
+    if (n > 0 && n <= kNMax) {
+        const int32_t* gp = B.pos0 + (size_t)rep * n_max;
+        const int8_t* gs = B.sigma0 + (size_t)rep * n_max;
+        int part = 0, bad = 0;
+        for (int i = lane; i < n; i += LPR) {
+            const int p = gp[i], sg = gs[i];
+            pos[i] = (uint16_t)p;
+            part += sg;
+            if (!WHO && i + 1 < n && gp[i + 1] <= p) bad = 1;         // needs strictly increasing positions (K = 1, sorted)
+            code[pad + p] = (uint8_t)(sg == 1 ? 1 : 3);
+            if (WHO) who[p] = (uint16_t)i;
+        }
+        if (WHO) {
+            __syncwarp(hmask);
+            for (int i = lane; i < n; i += LPR) bad |= (who[pos[i]] != (uint16_t)i);
+        }
+        for (int o = LPR / 2; o > 0; o >>= 1) part += __shfl_xor_sync(hmask, part, o, LPR);
+        S = part;
+        unsorted = __any_sync(hmask, bad);
+    }
+    if (unsorted || n > kNMax || n == 0) {
+        if (lane == 0) {
+            if (n == 0) {
+                if (B.n_obs) B.n_obs[rep] = B.obs_start ? B.obs_start[rep] : 0;
+                if (B.n_events) B.n_events[rep] = B.ev_start ? B.ev_start[rep] : 0;
+                if (B.t_end) B.t_end[rep] = B.t_start ? B.t_start[rep] : 0.0;
+                if (B.n_guard) B.n_guard[rep] = 0;
+                if (B.draws_used) B.draws_used[rep] = 0;
+                if (B.n_end) B.n_end[rep] = 0;
+                if (B.n_exit && !B.ev_start) B.n_exit[rep] = 0;
+                B.status[rep] = APS_RUN_EMPTY;
+            } else B.status[rep] = APS_RUN_RETRY_FAST;
+        }
+        return;
+    }
+    __syncwarp(hmask);
+    for (int i = lane; i < n; i += LPR) {                             // reflect images of the halo
+        const int p = pos[i];
+        const uint8_t c = code[pad + p];
+        if (p < pad) code[pad - 1 - p] = c;
+        if (p >= L - pad) code[pad + 2 * L - 1 - p] = c;
+    }
+    if (lane == 0) {
+        int32_t* na = reinterpret_cast<int32_t*>(rates); int32_t* nb = na + 16; int32_t* nk = nb + 16; int32_t* lv = nk + 16;
+        const int nn = build_sum_tree(n, na, nb, nk, 16);
+        int nl = 0;
+        for (int g = 0; g < nn; ++g) {
+            F.node_kind[g] = (int8_t)nk[g];
+            if (nk[g] == 0) { F.leaf_start[nl] = (int16_t)na[g]; F.leaf_len[nl] = (int16_t)nb[g]; F.node_leaf[g] = (int8_t)nl++; F.node_a[g] = 0; F.node_b[g] = 0; }
+            else { F.node_leaf[g] = -1; F.node_a[g] = (int8_t)na[g]; F.node_b[g] = (int8_t)nb[g]; }
+        }
+        lv[nn - 1] = 0;
+        int maxlev = 0;
+        for (int g = nn - 1; g >= 0; --g) if (nk[g] == 1) {
+            const int l2 = lv[g] + 1;
+            lv[na[g]] = l2; lv[nb[g]] = l2;
+            if (l2 > maxlev) maxlev = l2;
+        }
+        for (int g = 0; g < nn; ++g) F.node_level[g] = (int8_t)lv[g];
+        F.desc[D_NNODES] = nn; F.desc[12] = nl; F.desc[13] = maxlev;
+    }
+    __syncwarp(hmask);
+    const int nnodes = F.desc[D_NNODES], nleaf = F.desc[12], maxlev = F.desc[13];     // nnodes <= 15 < LPR
+    const bool have_node = lane < nnodes;
+    const int nd_kind = have_node ? F.node_kind[lane] : 0, nd_lev = have_node ? F.node_level[lane] : -1;
+    const int nd_a = (have_node && nd_kind) ? F.node_a[lane] : 0, nd_b = (have_node && nd_kind) ? F.node_b[lane] : 0;
+    const int nd_leaf = (have_node && !nd_kind) ? F.node_leaf[lane] : 0;
+    const int my_g = lane >> 3;                                       // 8-lane group of this lane inside its half: 0 or 1
+    const int ls1 = nleaf > 1 ? F.leaf_start[1] : 0x7fff, ls2 = nleaf > 2 ? F.leaf_start[2] : 0x7fff, ls3 = nleaf > 3 ? F.leaf_start[3] : 0x7fff;
+    const int ls4 = nleaf > 4 ? F.leaf_start[4] : 0x7fff, ls5 = nleaf > 5 ? F.leaf_start[5] : 0x7fff;
+    const int ls6 = nleaf > 6 ? F.leaf_start[6] : 0x7fff, ls7 = nleaf > 7 ? F.leaf_start[7] : 0x7fff;
+    int cs_shift = 4;
+    while (((n + (1 << cs_shift) - 1) >> cs_shift) > LPR) ++cs_shift;  // at most one selection chunk per lane of the half
+    const int CS = 1 << cs_shift;
+    const int nchunks = (n + CS - 1) >> cs_shift;
+    const int epl_shift = cs_shift > 4 ? cs_shift - 4 : 0;            // elements per lane in the walk of the winning chunk
+    const int EPL = 1 << epl_shift;
+    double my_cs = 0.0;                                               // cached sum of chunk `lane`
+
+    int64_t n_done = 0;
+    const int64_t ev_base = B.ev_start ? B.ev_start[rep] : 0;
+    int64_t cursor = 0, n_guard = 0, rbase = -(int64_t)kLeanRing - 8;
+    const int64_t draws_len = PHILOX ? 0 : (B.draw_off[rep + 1] - B.draw_off[rep]);
+    const double* gdraws = PHILOX ? nullptr : (B.draws + B.draw_off[rep]);
+    const uint32_t k0 = PHILOX ? (uint32_t)B.seeds[rep] : 0u, k1 = PHILOX ? (uint32_t)(B.seeds[rep] >> 32) : 0u;
+    double t = B.t_start ? B.t_start[rep] : 0.0;
+    int obs_idx = B.obs_start ? B.obs_start[rep] : 0;
+    int status = APS_RUN_DONE;
+    const int64_t max_events = B.max_events > 0 ? B.max_events : 0x7fffffffffffffffLL;
+
+    // local magnetisation at site p (see aps_k1_lean.cuh: exact small-integer multipliers -> DFMA, unrolled for r = RCAP - 1)
+    auto local_m = [&](int p, auto hot) {
+        const uint8_t* c = code + pad + p;
+        const double w0 = F.wtab[r];
+        const double2 m0 = F.mst[c[0]];
+        double sc = APS_MUL(m0.x, w0), tc = APS_MUL(m0.y, w0);
+        if (decltype(hot)::value && r == RCAP - 1) {
+#pragma unroll
+            for (int jj = -(RCAP - 1); jj < 0; ++jj) {
+                const double2 mm = F.mst[(int)c[jj] + (int)c[-jj]];
+                const double wj = F.wtab[RCAP - 1 + jj];
+                sc = __fma_rn(mm.x, wj, sc);
+                tc = __fma_rn(mm.y, wj, tc);
+            }
+        } else {
+#pragma unroll 4
+            for (int jj = -r; jj < 0; ++jj) {
+                const double2 mm = F.mst[(int)c[jj] + (int)c[-jj]];
+                const double wj = F.wtab[r + jj];
+                sc = __fma_rn(mm.x, wj, sc);
+                tc = __fma_rn(mm.y, wj, tc);
+            }
+        }
+        double m = 0.0;
+        if (tc > 0.0) m = APS_DIV(sc, tc);
+        return m < -1.0 ? -1.0 : (m > 1.0 ? 1.0 : m);
+    };
+    auto write_rows = [&](int first, int count) {
+        for (int m = first; m < first + count; ++m) {
+            const size_t row = (size_t)rep * (size_t)M + (size_t)m;
+            if ((B.record & APS_REC_COUNTS) && B.obs_cp && B.obs_cm) {
+                int8_t* ocp = B.obs_cp + row * (size_t)L; int8_t* ocm = B.obs_cm + row * (size_t)L;
+                for (int l = lane; l < L; l += LPR) { const uint8_t v = code[pad + l]; ocp[l] = (int8_t)(v == 1); ocm[l] = (int8_t)(v == 3); }
+            }
+            if ((B.record & APS_REC_POS) && B.obs_pos) {
+                int32_t* op = B.obs_pos + row * (size_t)n_max;
+                for (int i = lane; i < n; i += LPR) op[i] = (int32_t)pos[i];
+            }
+            if (B.obs_sigma_sum && lane == 0) B.obs_sigma_sum[row] = S;
+            if (B.obs_n && lane == 0) B.obs_n[row] = n;
+            if (B.obs_bound) { int8_t* ob = B.obs_bound + row * (size_t)n_max; for (int i = lane; i < n; i += LPR) ob[i] = 0; }
+        }
+    };
+    auto write_field = [&](int first, int count) {
+        if (!((B.record & APS_REC_MLOCAL) && B.obs_m_local)) return;
+        for (int l = lane; l < L; l += LPR) {
+            const double m = local_m(l, std::false_type{});
+            for (int mm = first; mm < first + count; ++mm)
+                B.obs_m_local[((size_t)rep * (size_t)M + (size_t)mm) * (size_t)L + l] = m;
+        }
+    };
+    auto hop_flags = [&](int p, int cd) {
+        const bool l_free = (p > 0) && code[pad + p - 1] == 0, r_free = (p < L - 1) && code[pad + p + 1] == 0;
+        return (l_free ? 1 : 0) | (r_free ? 2 : 0) | ((cd == 1 && r_free) ? 4 : 0);
+    };
+    auto refresh = [&](int i, auto hot) {                             // full rate of particle i (CLASS.py:351)
+        const int p = pos[i];
+        const int cd = code[pad + p];
+        const double sgd = cd == 1 ? 1.0 : -1.0;
+        const double h = F.hop_tab[hop_flags(p, cd)];
+        const double m = local_m(p, hot);
+        rates[i] = APS_ADD(h, aps_exp(APS_MUL(APS_MUL(-beta, sgd), m)));
+        F.dirty_c[i >> cs_shift] = 1;
+        int lf = (i >= ls1) + (i >= ls2) + (i >= ls3);
+        if (NCAP > 512) lf += (i >= ls4) + (i >= ls5) + (i >= ls6) + (i >= ls7);
+        F.dirty_leaf[lf] = 1;
+    };
+    auto code_put = [&](int x, int delta) { code_add(code, L, pad, x, delta); };
+
+    for (int i = lane; i < n; i += LPR) refresh(i, std::false_type{});
+    if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
+    __syncwarp(hmask);
+    double next_obs = (obs_idx < M) ? B.times_obs[obs_idx] : 0.0;
+    const double guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
+
+    while (true) {
+        if (!(t < T)) { status = APS_RUN_DONE; break; }
+        if (n_done >= max_events) { status = APS_RUN_MAX_EVENTS; break; }
+        int avail; double e, uc, ue, ud;
+        if (PHILOX) {
+            const int slot = (int)(n_done & 7);
+            if (slot == 0) {
+                if (lane < 8) {
+                    const uint64_t ev = (uint64_t)(ev_base + n_done + lane);
+                    const aps_u32x4 a = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_A, 0u, k0, k1);
+                    const aps_u32x4 b = aps_philox4x32_10((uint32_t)ev, (uint32_t)(ev >> 32), APS_RNG_EVENT_B, 0u, k0, k1);
+                    F.ring[4 * lane + 0] = -aps_log(APS_SUB(1.0, aps_u53(a.v[0], a.v[1])));
+                    F.ring[4 * lane + 1] = aps_u53(a.v[2], a.v[3]);
+                    F.ring[4 * lane + 2] = aps_u53(b.v[0], b.v[1]);
+                    F.ring[4 * lane + 3] = aps_u53(b.v[2], b.v[3]);
+                }
+                __syncwarp(hmask);
+            }
+            avail = 4;
+            e = F.ring[4 * slot]; uc = F.ring[4 * slot + 1]; ue = F.ring[4 * slot + 2]; ud = F.ring[4 * slot + 3];
+        } else {
+            if (cursor + 4 > rbase + kLeanRing) {
+                __syncwarp(hmask);
+                rbase = cursor;
+                for (int q = lane; q < kLeanRing; q += LPR) F.ring[q] = (rbase + q < draws_len) ? __ldg(gdraws + rbase + q) : 0.0;
+                __syncwarp(hmask);
+            }
+            const int64_t left = draws_len - cursor;
+            avail = left >= 4 ? 4 : (int)(left < 0 ? 0 : left);
+            if (B.spec_from >= 0 && cursor >= B.spec_from && avail > 3) avail = 3;
+            const int o = (int)(cursor - rbase);
+            e = F.ring[o]; uc = F.ring[o + 1]; ue = F.ring[o + 2]; ud = F.ring[o + 3];
+        }
+        if (avail < 3) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+        const int seq = (int)(n_done & 0x3fffffff) + 1;
+
+        auto decode_apply = [&](int sel) {
+            const int p = pos[sel];
+            const int cd = code[pad + p], sg = cd == 1 ? 1 : -1;
+            const int hf = hop_flags(p, cd);
+            const double dz = APS_MUL(D, 0.0);
+            const double rl = (hf & 1) ? D : dz, rr = (hf & 2) ? D : dz, ra = (hf & 4) ? lam : 0.0;
+            const double v = APS_MUL(ue, rates[sel]);
+            const double diff_thresh = APS_ADD(rl, rr), act_thresh = APS_ADD(diff_thresh, ra);
+            int kind, newp = p;
+            if (v < diff_thresh) {
+                if (avail < 4) { F.desc[D_STOP] = 1; F.desc[D_SEQ] = seq; return; }
+                if (ud < APS_DIV(rl, APS_ADD(rl, rr))) { kind = APS_EV_DIFF_LEFT; newp = clampi(p - 1, 0, L - 1); }
+                else { kind = APS_EV_DIFF_RIGHT; newp = clampi(p + 1, 0, L - 1); }
+            } else if (v < act_thresh) { kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, L - 1); }
+            else kind = APS_EV_FLIP;
+            if (kind == APS_EV_FLIP) code_put(p, sg == 1 ? 2 : -2);
+            else if (newp != p) {
+                pos[sel] = (uint16_t)newp; code_put(p, -cd); code_put(newp, cd);
+                if (WHO) { who[p] = 0xFFFFu; who[newp] = (uint16_t)sel; }
+            }
+            F.desc[D_PART] = sel; F.desc[D_KIND] = kind; F.desc[D_OLD] = p; F.desc[D_NEW] = newp; F.desc[D_SG] = sg;
+            F.desc[D_STOP] = 0; F.desc[D_SEQ] = seq;
+        };
+
+        // ---- selection: chunk sums (dirty ones re-summed, cached in a register), half-warp scan, walk of the winning chunk ----
+        {
+            if (lane < nchunks && F.dirty_c[lane]) {
+                const int c0 = lane << cs_shift;
+                const int hi_i = (c0 + CS < n) ? c0 + CS : n;
+                double cs = 0.0;
+                for (int i = c0; i < hi_i; ++i) cs = APS_ADD(cs, rates[i]);
+                my_cs = cs; F.dirty_c[lane] = 0;
+            }
+            double incl = lane < nchunks ? my_cs : 0.0;
+            for (int o = 1; o < LPR; o <<= 1) {
+                const double up = __shfl_up_sync(hmask, incl, o, LPR);
+                if (lane >= o) incl = APS_ADD(incl, up);
+            }
+            double prev = __shfl_up_sync(hmask, incl, 1, LPR);
+            if (lane == 0) prev = 0.0;
+            const double atot = __shfl_sync(hmask, incl, LPR - 1, LPR);
+            const double target = APS_MUL(uc, atot);
+            const unsigned wmask = ballot(lane < nchunks && prev <= target && target < incl);
+            bool exact = (__popc(wmask) != 1);
+            if (!exact) {
+                const int wl = __ffs(wmask) - 1;
+                const double prev_w = __shfl_sync(hmask, prev, wl, LPR), inc_w = __shfl_sync(hmask, incl, wl, LPR);
+                // lane l walks elements i0 .. i0 + EPL - 1 of the winning chunk: local running sums, scan of the lane totals
+                const int i0 = (wl << cs_shift) + (lane << epl_shift);
+                const int cend = ((wl << cs_shift) + CS < n) ? (wl << cs_shift) + CS : n;     // one past the chunk's last element
+                double run = 0.0;
+                for (int q = 0; q < EPL; ++q) { const int i = i0 + q; if (i < cend) run = APS_ADD(run, rates[i]); }
+                double inc2 = run;
+                for (int o = 1; o < LPR; o <<= 1) {
+                    const double up = __shfl_up_sync(hmask, inc2, o, LPR);
+                    if (lane >= o) inc2 = APS_ADD(inc2, up);
+                }
+                double exc2 = __shfl_up_sync(hmask, inc2, 1, LPR);
+                if (lane == 0) exc2 = 0.0;
+                // edges: lo of the lane's first element = prev_w + exc2 (the same expression gives the previous lane's last hi);
+                // the chunk's last element is pinned to inc_w so that neighbouring chunks share their boundary exactly
+                int hit = -1; double hlo = 0.0, hhi = 0.0;
+                double lo = lane == 0 ? prev_w : APS_ADD(prev_w, exc2), part = 0.0;
+                for (int q = 0; q < EPL; ++q) {
+                    const int i = i0 + q;
+                    if (i < cend) {
+                        part = APS_ADD(part, rates[i]);
+                        const double hi = (i == cend - 1) ? inc_w : APS_ADD(prev_w, APS_ADD(exc2, part));
+                        if (hit < 0 && lo <= target && target < hi) { hit = i; hlo = lo; hhi = hi; }
+                        lo = hi;
+                    }
+                }
+                const unsigned smask = ballot(hit >= 0);
+                if (__popc(smask) != 1) exact = true;
+                else if (hit >= 0) {
+                    const double band = APS_MUL(guard, atot);
+                    if ((target - hlo) < band || (hhi - target) < band) F.desc[D_EXACT] = 1;
+                    else decode_apply(hit);
+                }
+            }
+            if (exact && lane == 0) F.desc[D_EXACT] = 1;
+        }
+        // ---- clock: numpy's pairwise sum exactly (8 lanes per leaf, two leaves per round), R, tau, observation crossings ----
+        {
+#pragma unroll
+            for (int rnd = 0; rnd < kLeafRounds; ++rnd) {
+                const int gg = my_g + (LPR / 8) * rnd;
+                if (gg < nleaf && F.dirty_leaf[gg]) {                 // uniform within the 8-lane group
+                    const unsigned gmask = 0xffu << (lane32 & 24);
+                    const int k = lane & 7;
+                    const int gs = F.leaf_start[gg], gl = F.leaf_len[gg];
+                    double res;
+                    if (gl < 8) {
+                        res = 0.0;
+                        for (int i = 0; i < gl; ++i) res = APS_ADD(res, rates[gs + i]);
+                    } else {
+                        const int body = gl - (gl & 7);
+                        double acc = rates[gs + k];
+                        for (int i = 8; i < body; i += 8) acc = APS_ADD(acc, rates[gs + i + k]);
+                        acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 1));
+                        acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 2));
+                        acc = APS_ADD(acc, __shfl_xor_sync(gmask, acc, 4));
+                        res = acc;
+                        for (int i = body; i < gl; ++i) res = APS_ADD(res, rates[gs + i]);
+                    }
+                    __syncwarp(gmask);
+                    if (k == 0) { F.leafsum[gg] = res; F.dirty_leaf[gg] = 0; }
+                }
+            }
+            __syncwarp(hmask);
+            double val = (have_node && !nd_kind) ? F.leafsum[nd_leaf] : 0.0;
+            for (int lev = maxlev - 1; lev >= 0; --lev) {
+                const double va = __shfl_sync(hmask, val, nd_a, LPR), vb = __shfl_sync(hmask, val, nd_b, LPR);
+                if (nd_kind && nd_lev == lev) val = APS_ADD(va, vb);
+            }
+            if (lane == nnodes - 1) {
+                const double R = val;
+                const double tau = APS_MUL(APS_DIV(1.0, R), e);
+                const double tn = APS_ADD(t, tau);
+                F.misc[X_R] = R; F.misc[X_TNEW] = tn;
+                F.desc[D_BADR] = !(R > 0.0);
+                F.desc[D_END] = tn > T;
+                int nc = 0;
+                if (!(tn > T) && obs_idx < M && next_obs <= tn) {
+                    nc = 1;
+                    while (obs_idx + nc < M && B.times_obs[obs_idx + nc] <= tn) ++nc;
+                }
+                F.desc[D_NCROSS] = nc;
+            }
+        }
+        __syncwarp(hmask);
+
+        if (F.desc[D_BADR]) { status = APS_RUN_EMPTY; break; }
+        if (F.desc[D_EXACT] || F.desc[D_SEQ] != seq) {
+            __syncwarp(hmask);
+            if (lane == 0) {
+                const double R = F.misc[X_R];
+                double acc = 0.0;
+                for (int i = 0; i < n; ++i) acc = APS_ADD(acc, APS_DIV(rates[i], R));
+                const double last = acc;
+                int sel = n - 1; acc = 0.0;
+                for (int i = 0; i < n; ++i) { acc = APS_ADD(acc, APS_DIV(rates[i], R)); if (APS_DIV(acc, last) > uc) { sel = i; break; } }
+                decode_apply(sel);
+                F.desc[D_EXACT] = 0;
+            }
+            ++n_guard;
+            __syncwarp(hmask);
+        }
+        if (F.desc[D_STOP]) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+        const int kind = F.desc[D_KIND], part = F.desc[D_PART], oldp = F.desc[D_OLD], newp = F.desc[D_NEW];
+        const int ncross = F.desc[D_NCROSS], endflag = F.desc[D_END];
+        const int sg_now = F.desc[D_SG];                             // orientation of the particle BEFORE the event
+        const double tnew = F.misc[X_TNEW];
+        if (B.trace && lane == 0 && n_done < B.trace_cap) {
+            int32_t* tr = B.trace + ((size_t)rep * (size_t)B.trace_cap + (size_t)n_done) * 3;
+            tr[0] = part; tr[1] = kind; tr[2] = (kind == APS_EV_FLIP) ? -1 : newp;
+        }
+        ++n_done;
+        cursor += 3 + (kind < 2 ? 1 : 0);
+        if (kind == APS_EV_FLIP) S -= 2 * sg_now;
+        t = tnew;
+        if (endflag) { status = APS_RUN_DONE; break; }
+        if (ncross > 0) {
+            if ((B.record & APS_REC_MLOCAL) && B.obs_m_local) {
+                const int cd = sg_now == 1 ? 1 : 3;
+                __syncwarp(hmask);
+                if (lane == 0) {   // undo on the code array only: the recorded field is the pre-event one
+                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? -2 : 2);
+                    else if (newp != oldp) { code_put(newp, -cd); code_put(oldp, cd); }
+                }
+                __syncwarp(hmask);
+                write_field(obs_idx, ncross);
+                __syncwarp(hmask);
+                if (lane == 0) {   // redo
+                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? 2 : -2);
+                    else if (newp != oldp) { code_put(newp, cd); code_put(oldp, -cd); }
+                }
+                __syncwarp(hmask);
+            }
+            write_rows(obs_idx, ncross);
+            obs_idx += ncross;
+            if (obs_idx < M) next_obs = B.times_obs[obs_idx];
+        }
+        if (obs_idx >= M) { status = APS_RUN_DONE; break; }
+
+        // ---- refresh the rates inside the window ----
+        if (WHO) {                                                     // any particle order: site->particle map + ballot compaction
+            const int reach = r > 1 ? r : 1;
+            const int mn = oldp < newp ? oldp : newp, mx = oldp < newp ? newp : oldp;
+            int wlo = mn - reach, whi = mx + reach;
+            if (wlo < 0) wlo = 0;
+            if (whi > L - 1) whi = L - 1;
+            int count = 0;
+            for (int s0 = wlo; s0 <= whi; s0 += LPR) {
+                const int site = s0 + lane;
+                const unsigned v = (site <= whi) ? who[site] : 0xFFFFu;
+                const unsigned mask = ballot(v != 0xFFFFu);
+                if (v != 0xFFFFu) F.list[count + __popc(mask & ((1u << lane) - 1u))] = (uint16_t)v;
+                count += __popc(mask);
+                if (count >= LPR || s0 + LPR > whi) {                  // the list holds at most 2 * LPR entries
+                    __syncwarp(hmask);
+                    for (int j0 = 0; j0 < count; j0 += LPR) { const int j = j0 + lane; if (j < count) refresh(F.list[j], std::true_type{}); }
+                    __syncwarp(hmask);
+                    count = 0;
+                }
+            }
+        } else {   // sorted particles: the window is a contiguous index range around `part`
+            const int reach = r > 1 ? r : 1;
+            const int mn = oldp < newp ? oldp : newp, mx = oldp < newp ? newp : oldp;
+            const int wlo = mn - reach, whi = mx + reach;
+            // lowest index inside the window: blocks of LPR candidates to the left of `part` (positions are sorted, so membership is
+            // monotone in the index); a block that lies completely inside sends the search one block further
+            int ilo = part, top = part;
+            while (true) {
+                const int ia = top - (LPR - 1) + lane;
+                const bool in_a = ia >= 0 && (int)pos[ia >= 0 ? ia : 0] >= wlo;
+                const unsigned ma = ballot(in_a);
+                if (ma) ilo = top - (LPR - 1) + (__ffs(ma) - 1);
+                if (ma != 0xffffu || top - (LPR - 1) <= 0) break;
+                top -= LPR;
+            }
+            for (int i0 = ilo; i0 < n; i0 += LPR) {
+                const int i = i0 + lane;
+                const bool in = i < n && (int)pos[i < n ? i : n - 1] <= whi;
+                if (in) refresh(i, std::true_type{});
+                if (!__all_sync(hmask, in)) break;
+            }
+        }
+        __syncwarp(hmask);
+    }
+
+    if (lane == 0) {
+        if (B.n_obs) B.n_obs[rep] = obs_idx;
+        if (B.n_events) B.n_events[rep] = ev_base + n_done;
+        if (B.t_end) B.t_end[rep] = t;
+        B.status[rep] = status;
+        if (B.n_guard) B.n_guard[rep] = n_guard;
+        if (B.draws_used) B.draws_used[rep] = PHILOX ? 0 : cursor;
+        if (B.n_end) B.n_end[rep] = n;
+        if (B.n_exit && !B.ev_start) B.n_exit[rep] = 0;
+    }
+    __syncwarp(hmask);
+    if (B.bound_end) for (int i = lane; i < n; i += LPR) B.bound_end[(size_t)rep * n_max + i] = 0;
+    if (B.pos_end) for (int i = lane; i < n; i += LPR) B.pos_end[(size_t)rep * n_max + i] = (int32_t)pos[i];
+    if (B.sigma_end) for (int i = lane; i < n; i += LPR) B.sigma_end[(size_t)rep * n_max + i] = (int8_t)(code[pad + pos[i]] == 1 ? 1 : -1);
+}
+
+}  // namespace aps
