@@ -452,7 +452,7 @@ def ensemble_main(args, torch, la, capi, rank, world):
         dens, betas = np.linspace(50, 950, 16).astype(int), np.linspace(0, 3, 16)
         call = lambda s: la.double_sweep(dens, betas, 128, w["ps"], w["run"], frac_plus=p["frac_plus"], decay_plus=p["decay_plus"],
                                          decay_minus=p["decay_minus"], base_seed=100 + s)
-        count = lambda out: (int(out["n_events_total"]), out["info"]["h2d_bytes"], out["info"]["d2h_bytes"])
+        count = lambda out: (int(out["info"]["n_events_total"]), out["info"]["h2d_bytes"], out["info"]["d2h_bytes"])
         api = "launcher.double_sweep (host parameters -> host reducers per (density, beta) point)"
     for _ in range(2):
         call(0)

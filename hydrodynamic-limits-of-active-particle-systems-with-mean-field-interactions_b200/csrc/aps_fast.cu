@@ -10,7 +10,10 @@ namespace aps {
 // A/B knobs of include/aps.h, read ONCE when the library is loaded (never on the launch path)
 static const int g_env_extra_smem = [] { const char* e = getenv("APS_K1_EXTRA_SMEM"); return e ? atoi(e) : 0; }();   // occupancy experiments only
 static const bool g_env_no_lean = getenv("APS_K1_NO_LEAN") != nullptr;
-static const bool g_env_no_pair = getenv("APS_K1_NO_PAIR") != nullptr;     // A/B: one replica per warp (aps_k1_lean.cuh) first
+// A/B: two replicas per warp (aps_k1_pair.cuh) instead of one (aps_k1_lean.cuh).  Measured on B200 (profiles/r2_k1.md): 114.4 ms
+// against 88.8 ms for the 4096-replica config-2 launch — the lock-step of two different event streams costs more than the halved
+// issue pressure gains — so the pair kernel is OFF unless APS_K1_PAIR=1 (it stays in the test matrix through that knob).
+static const bool g_env_no_pair = getenv("APS_K1_PAIR") == nullptr;
 
 template <int NT, int RCAP, int NCAP, int LPCAP>
 static cudaError_t launch_nt(const K1Args& a, bool philox, cudaStream_t st) {

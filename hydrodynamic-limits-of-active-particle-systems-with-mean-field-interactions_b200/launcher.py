@@ -462,8 +462,7 @@ def double_sweep(n_part_values, beta_values, n_runs, ps_kwargs, run_kwargs, **kw
             d[stem + "stds"] = np.array([s[1] for s in stats])
             d[stem + "ses"] = np.array([s[2] for s in stats])
         out[int(N)] = d
-    out["info"] = res.info
-    out["n_events_total"] = int(res.n_events.sum())
+    out["info"] = dict(res.info, n_events_total=int(res.n_events.sum()))
     return out
 
 
