@@ -13,7 +13,6 @@ static const bool g_env_no_lean = getenv("APS_K1_NO_LEAN") != nullptr;
 // A/B: two replicas per warp (aps_k1_pair.cuh) instead of one (aps_k1_lean.cuh).  Measured on B200 (profiles/r2_k1.md): 114.4 ms
 // against 88.8 ms for the 4096-replica config-2 launch — the lock-step of two different event streams costs more than the halved
 // issue pressure gains — so the pair kernel is OFF unless APS_K1_PAIR=1 (it stays in the test matrix through that knob).
-static const bool g_env_wide_lean = getenv("APS_K1_WIDE_LEAN") != nullptr;   // A/B: single-warp lean kernel with the site map for r <= 80
 static bool g_env_no_pair = getenv("APS_K1_PAIR") == nullptr;
 void set_k1_pair(int on) { g_env_no_pair = !on; }
 
@@ -111,16 +110,6 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
                 return launch_class<21, 1024, 1056>(b, philox, st, nt);
             }
             return launch_class<21, 1024, 1056>(a, philox, st, nt);
-        }
-        if (g_env_wide_lean && !g_env_no_lean && r1 <= 81 && nm <= 1024 && lp <= 1184) {
-            // wide windows (config 4: r = 80) on the trimmed single-warp image with the site map: no product table (11.6 KB),
-            // twice the replicas per SM of the two-warp full-size kernel; rejects (n > 488 / 968) fall through to it
-            cudaError_t e = nm <= 512 ? launch_lean<81, 1184, 512, true>(a, philox, st) : launch_lean<81, 1184, 1024, true>(a, philox, st);
-            if (e != cudaSuccess) return e;
-            *launched = 2;
-            K1Args b = a;
-            b.only_retry = 2;
-            return nm <= 512 ? launch_class<81, 512, 1184>(b, philox, st, nt) : launch_class<81, 1024, 1184>(b, philox, st, nt);
         }
         if (r1 <= 81 && nm <= 512 && lp <= 1184) return launch_class<81, 512, 1184>(a, philox, st, nt);
         if (r1 <= 81 && nm <= 1024 && lp <= 1184) return launch_class<81, 1024, 1184>(a, philox, st, nt);
