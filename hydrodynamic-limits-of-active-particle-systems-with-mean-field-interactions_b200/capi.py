@@ -204,7 +204,6 @@ SYMBOLS = {
     "aps_debug_set_k1_threads": (None, [C.c_int]),
     "aps_debug_set_use_lut": (None, [C.c_int]),
     "aps_debug_set_use_fast": (None, [C.c_int]),
-    "aps_debug_set_k1_pair": (None, [C.c_int]),
     "aps_debug_set_k2_ctas_per_sm": (None, [C.c_int]),
     "aps_debug_set_k2_stash_cap": (None, [C.c_int]),
     "aps_debug_set_reduce_threads": (None, [C.c_int]),

@@ -19,7 +19,7 @@ namespace aps {
 size_t pde_smem_bytes(int L, int bc, int n_tracers);
 cudaError_t pde_launch(const aps_pde_args& a, cudaStream_t st);
 }
-namespace aps { cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched); void set_k1_pair(int on); }
+namespace aps { cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched); }
 
 namespace {
 
@@ -584,7 +584,6 @@ void aps_debug_set_use_lut(int on) { g_use_lut = on ? 1 : 0; }
 void aps_debug_set_k2_ctas_per_sm(int n) { g_k2_ctas_per_sm = n > 0 ? n : 6; }
 void aps_debug_set_k2_stash_cap(int n) { g_k2_stash_cap = (n == 1 || n == 2 || n == 4 || n == 8 || n == 16 || n == 32) ? n : 0; }
 void aps_debug_set_reduce_threads(int n) { g_reduce_threads = (n >= 32 && n <= 1024 && n % 32 == 0) ? n : 128; }
-void aps_debug_set_k1_pair(int on) { aps::set_k1_pair(on); }   // two replicas per warp (aps_k1_pair.cuh); off by default
 void aps_debug_set_use_fast(int on) { g_use_fast = on; }   // 0 generic only, 1 capacity classes, 2 run-time layout
 
 }  // extern "C"

@@ -3,19 +3,13 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 
-#include "aps_k1_pair.cuh"
+#include "aps_k1_lean.cuh"
 
 namespace aps {
 
 // A/B knobs of include/aps.h, read ONCE when the library is loaded (never on the launch path)
 static const int g_env_extra_smem = [] { const char* e = getenv("APS_K1_EXTRA_SMEM"); return e ? atoi(e) : 0; }();   // occupancy experiments only
 static const bool g_env_no_lean = getenv("APS_K1_NO_LEAN") != nullptr;
-// A/B: two replicas per warp (aps_k1_pair.cuh) instead of one (aps_k1_lean.cuh).  Measured on B200 (profiles/r2_k1.md): 114.4 ms
-// against 88.8 ms for the 4096-replica config-2 launch — the lock-step of two different event streams costs more than the halved
-// issue pressure gains — so the pair kernel is OFF unless APS_K1_PAIR=1 (it stays in the test matrix through that knob).
-static bool g_env_no_pair = getenv("APS_K1_PAIR") == nullptr;
-void set_k1_pair(int on) { g_env_no_pair = !on; }
-
 template <int NT, int RCAP, int NCAP, int LPCAP>
 static cudaError_t launch_nt(const K1Args& a, bool philox, cudaStream_t st) {
     const size_t smem = k1_fast_smem_bytes(a.p.L, a.b.n_max, a.p.radius, RCAP, NCAP, LPCAP) + (size_t)g_env_extra_smem;
@@ -54,25 +48,6 @@ static cudaError_t launch_lean(const K1Args& a, bool philox, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// two replicas per warp (aps_k1_pair.cuh): grid = ceil(replicas / 2) single-warp CTAs, two shared-memory images per CTA
-template <int RCAP, int LPCAP, int NCAP, bool WHO>
-static cudaError_t launch_pair(const K1Args& a, bool philox, cudaStream_t st) {
-    const size_t smem = 2 * k1_pair_image_bytes<RCAP, LPCAP, NCAP, WHO>();
-    const int grid = (a.b.n_replicas + 1) / 2;
-    if (philox) {
-        auto k = k1_pair_kernel<true, RCAP, LPCAP, NCAP, WHO>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<grid, 32, smem, st>>>(a);
-    } else {
-        auto k = k1_pair_kernel<false, RCAP, LPCAP, NCAP, WHO>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<grid, 32, smem, st>>>(a);
-    }
-    return cudaGetLastError();
-}
-
 // Returns cudaSuccess and *launched = number of specialised kernels enqueued; *launched = 0 if the
 // configuration does not qualify (the caller then uses the generic kernel only).
 cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched) {
@@ -86,8 +61,7 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
             if (nt == 32 && !g_env_no_lean) {
                 // half-size shared-memory image: all replicas of an SM resident at once; its rejects (unsorted initial
                 // positions) go through the full-size kernel in a second, otherwise empty launch
-                cudaError_t e = g_env_no_pair ? launch_lean<21, 1056, 512, false>(a, philox, st)
-                                              : launch_pair<21, 1056, 512, false>(a, philox, st);   // two replicas per warp
+                cudaError_t e = launch_lean<21, 1056, 512, false>(a, philox, st);
                 if (e != cudaSuccess) return e;
                 K1Args b = a;
                 b.only_retry = 2;

@@ -549,8 +549,21 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
             double prev = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) prev = 0.0;
             if (lane == 31) s.wtot[wid] = incl;
-            // exact leaves: 8 lanes per leaf == numpy's 8 strided accumulators
-            for (int g = tid >> 3; g < nnodes; g += NT / 8) {
+            if (PHILOX && wid == 0) {
+                // native mode: R is DEFINED as the 32-lane scan total of the chunk sums with the chunking rule of aps_math.h
+                // (aps_native_total) — the quantity the specialised kernels' selection produces anyway; same bits in every kernel
+                const int sh = aps_native_cs_shift(n), c_lo = lane << sh;
+                const int c_hi = (c_lo + (1 << sh) < n) ? c_lo + (1 << sh) : n;
+                double c = 0.0;
+                for (int i = c_lo; i < c_hi; ++i) c = APS_ADD(c, s.rates[i]);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, c, o);
+                    if (lane >= o) c = APS_ADD(c, up);
+                }
+                if (lane == 31) s.misc[2] = c;
+            }
+            // exact leaves (replay mode): 8 lanes per leaf == numpy's 8 strided accumulators
+            for (int g = tid >> 3; !PHILOX && g < nnodes; g += NT / 8) {
                 const unsigned gmask = 0xffu << (lane & 24);
                 if (s.node_kind[g] != 0) continue;   // uniform within the 8-lane group
                 const int k = tid & 7, start = s.node_a[g], len = s.node_b[g];
@@ -597,9 +610,10 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
                 }
             }
             if (tid == NT - 1) {
-                for (int g = 0; g < nnodes; ++g)
-                    if (s.node_kind[g] != 0) s.node_val[g] = APS_ADD(s.node_val[s.node_a[g]], s.node_val[s.node_b[g]]);
-                const double R = s.node_val[nnodes - 1];
+                if (!PHILOX)
+                    for (int g = 0; g < nnodes; ++g)
+                        if (s.node_kind[g] != 0) s.node_val[g] = APS_ADD(s.node_val[s.node_a[g]], s.node_val[s.node_b[g]]);
+                const double R = PHILOX ? s.misc[2] : s.node_val[nnodes - 1];
                 const double tau = APS_MUL(APS_DIV(1.0, R), e);
                 const double tn = APS_ADD(t, tau);
                 s.misc[X_R] = R; s.misc[X_TNEW] = tn;

@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
         accslot[i] = (uint8_t)((lf << 3) | (body ? (j & 7) : 0) | (body ? 0 : 0x80));
     }
     const int nnodes = F.desc[D_NNODES], nleaf = F.desc[12], maxlev = F.desc[13];
-    int cs_shift = STATIC ? (NCAP <= 256 ? 3 : NCAP <= 512 ? 4 : 5) : 3;
-    while (((n + (1 << cs_shift) - 1) >> cs_shift) > 32) ++cs_shift;     // at most one chunk per lane of the selection warp
+    const int cs_shift = aps_native_cs_shift(n);     // chunks of 16 * 2^k rates, at most one per lane of the selection warp; the
+                                                     // same rule in every K1 kernel: the scan total is R in native mode (aps_math.h)
     const int CS = 1 << cs_shift;
     const int nchunks = (n + CS - 1) >> cs_shift;
 
@@ -257,9 +257,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
         const double cv = aps_exp(APS_MUL(APS_MUL(-beta, (double)sg), m));
         rates[i] = APS_ADD(h, cv);
         F.dirty_c[i >> cs_shift] = 1;
-        const int as = accslot[i];
-        F.dirty_leaf[(as >> 3) & 15] = 1;
-        if (!(as & 0x80)) F.dirty_a[as] = 1;
+        if (!PHILOX) {                                  // pairwise accumulators: replay mode only
+            const int as = accslot[i];
+            F.dirty_leaf[(as >> 3) & 15] = 1;
+            if (!(as & 0x80)) F.dirty_a[as] = 1;
+        }
     };
 
     for (int i = tid; i < n; i += NT) refresh(i, true);
@@ -377,10 +379,24 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
                 }
             }
             if (exact && lane == 0) F.desc[D_EXACT] = 1;
+            if (PHILOX && lane == 0) {                  // native mode: R = total of the selection scan (aps_math.h, aps_native_total)
+                const double R = atot;
+                const double tau = APS_MUL(APS_DIV(1.0, R), e);
+                const double tn = APS_ADD(t, tau);
+                F.misc[X_R] = R; F.misc[X_TNEW] = tn;
+                F.desc[D_BADR] = !(R > 0.0);
+                F.desc[D_END] = tn > T;
+                int nc = 0;
+                if (!(tn > T) && obs_idx < M && next_obs <= tn) {
+                    nc = 1;
+                    while (obs_idx + nc < M && B.times_obs[obs_idx + nc] <= tn) ++nc;
+                }
+                F.desc[D_NCROSS] = nc;
+            }
         }
-        // ---- last warp = CLOCK warp: numpy's pairwise sum exactly (dirty accumulators re-summed, 8 lanes per
+        // ---- last warp = CLOCK warp (replay mode): numpy's pairwise sum exactly (dirty accumulators re-summed, 8 lanes per
         //      leaf, level-synchronous tree), R, tau, the event clock and the observation-crossing count ----
-        if (wid == NW - 1) {
+        if (!PHILOX && wid == NW - 1) {
             for (int g = lane >> 3; g < nleaf; g += 4) {
                 if (!F.dirty_leaf[g]) continue;                       // uniform within the 8-lane group
                 const unsigned gmask = 0xffu << (lane & 24);

@@ -252,9 +252,11 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         const double m = local_m(p, hot);
         rates[i] = APS_ADD(h, aps_exp(APS_MUL(APS_MUL(-beta, sgd), m)));
         F.dirty_c[i >> cs_shift] = 1;
-        int lf = (i >= ls1) + (i >= ls2) + (i >= ls3);
-        if (NCAP > 512) lf += (i >= ls4) + (i >= ls5) + (i >= ls6) + (i >= ls7);
-        F.dirty_leaf[lf] = 1;
+        if (!PHILOX) {                                  // the pairwise leaves are only summed in replay mode (see the clock below)
+            int lf = (i >= ls1) + (i >= ls2) + (i >= ls3);
+            if (NCAP > 512) lf += (i >= ls4) + (i >= ls5) + (i >= ls6) + (i >= ls7);
+            F.dirty_leaf[lf] = 1;
+        }
     };
     auto code_put = [&](int x, int delta) { code_add(code, L, pad, x, delta); };
 
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         };
 
         // ---- selection: chunk sums (dirty ones re-summed, cached in a register), warp scan, walk of the winning chunk ----
+        double r_scan;                                  // total of the scan = R in native mode (aps_math.h, aps_native_total)
         {
             if (lane < nchunks && F.dirty_c[lane]) {
                 const int c0 = lane << cs_shift;
@@ -341,6 +344,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             double prev = __shfl_up_sync(0xffffffffu, incl, 1);
             if (lane == 0) prev = 0.0;
             const double atot = __shfl_sync(0xffffffffu, incl, 31);
+            r_scan = atot;
             const double target = APS_MUL(uc, atot);
             const unsigned wmask = __ballot_sync(0xffffffffu, lane < nchunks && prev <= target && target < incl);
             bool exact = (__popc(wmask) != 1);
@@ -368,8 +372,12 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             }
             if (exact && lane == 0) F.desc[D_EXACT] = 1;
         }
-        // ---- clock: numpy's pairwise sum exactly (8 lanes per leaf, <= 4 leaves), R, tau, observation crossings ----
+        // ---- clock.  Replay mode: numpy's pairwise sum exactly (8 lanes per leaf, <= 4 leaves; CLASS.py:352), the clock the reference
+        //      reports.  Native mode: R is the total of the selection scan (defined in aps_math.h; the oracle does the same), so the
+        //      leaf sums, their dirty flags and the tree drop out of the per-event chain (19 % of it, ncu profiles/r2_k1.md). ----
         {
+            double val = r_scan;
+            if (!PHILOX) {
 #pragma unroll
             for (int half = 0; half < (NCAP > 512 ? 2 : 1); ++half) {
                 const int gg = my_g + 4 * half;
@@ -396,10 +404,11 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                 }
             }
             __syncwarp();
-            double val = (have_node && !nd_kind) ? F.leafsum[nd_leaf] : 0.0;
+            val = (have_node && !nd_kind) ? F.leafsum[nd_leaf] : 0.0;
             for (int lev = maxlev - 1; lev >= 0; --lev) {
                 const double va = __shfl_sync(0xffffffffu, val, nd_a), vb = __shfl_sync(0xffffffffu, val, nd_b);
                 if (nd_kind && nd_lev == lev) val = APS_ADD(va, vb);
+            }
             }
             if (lane == nnodes - 1) {
                 const double R = val;

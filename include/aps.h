@@ -352,7 +352,6 @@ int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset
  * Environment knobs read ONCE when the library is loaded, for A/B measurements only (results never depend on them):
  *   APS_K1_THREADS=32|64|128|256   block size of the K1 kernels
  *   APS_K1_NO_LEAN=1               skip the half-image K1 kernel (aps_k1_lean.cuh), use the full-size one
- *   APS_K1_PAIR=1                  two replicas per warp (aps_k1_pair.cuh) as the first kernel of the chain
  *   APS_K1_EXTRA_SMEM=<bytes>      pad the full-size K1 kernel's shared memory (occupancy experiments) */
 void aps_debug_set_guard_scale(double scale);
 void aps_debug_set_k1_threads(int threads);
@@ -360,7 +359,6 @@ void aps_debug_set_use_lut(int on); /* 0: evaluate filter taps arithmetically in
 void aps_debug_set_k2_ctas_per_sm(int n); /* persistent K2 CTAs per SM (default 6) */
 void aps_debug_set_reduce_threads(int n); /* threads per CTA of the reducer kernel (multiple of 32) */
 void aps_debug_set_k2_stash_cap(int n); /* local-field K2: stashed trials per segment (1..32, power of two; 0 = automatic) */
-void aps_debug_set_k1_pair(int on); /* 1: two replicas per warp for the sorted K = 1 class (aps_k1_pair.cuh; measured slower, off by default; also APS_K1_PAIR=1) */
 void aps_debug_set_use_fast(int on); /* 0: always use the generic K1 kernel (no K=1 specialisation) */
 
 #ifdef __cplusplus

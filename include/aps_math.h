@@ -220,6 +220,36 @@ APS_HD double aps_log(double x) {
     return APS_SUB(APS_MUL(dk, ln2_hi), APS_SUB(APS_SUB(APS_MUL(s, APS_SUB(f, R)), APS_MUL(dk, ln2_lo)), f));
 }
 
+/* Total rate R in NATIVE (Philox) mode — round 2.
+ * In replay mode R = rates.sum() has to be numpy's pairwise sum bit for bit (CLASS.py:352): it feeds the event clock, and the clock
+ * decides which observation row a state lands in, which is compared with the reference.  In native mode there is no reference clock to
+ * compare with (different random stream), and the exact pairwise tree was 19 % of the per-event dependency chain of K1 (ncu, profiles/
+ * r2_k1.md) for a quantity that differs from any other summation order by ~1e-16 relative.  Native mode therefore DEFINES R as the total
+ * the particle-selection scan produces anyway:
+ *     chunks of CS(n) = 16 * 2^k rates, k the smallest with at most 32 chunks; c_j = serial sum of chunk j (from 0.0, left to right);
+ *     R = S(31, 32) with S(l, 1) = c_l (0.0 for absent chunks), S(l, 2w) = S(l, w) + S(l - w, w)   [32-lane Hillis-Steele scan, last lane].
+ * Every K1 kernel and the oracle (mode 1) use this definition, so "GPU == oracle" stays bit-exact in native mode, clock included. */
+APS_HD int aps_native_cs_shift(int n) {
+    int s = 4;
+    while (((n + (1 << s) - 1) >> s) > 32) ++s;
+    return s;
+}
+#if !defined(__CUDA_ARCH__)
+static inline double aps_native_total(const double* rates, int n) {
+    const int sh = aps_native_cs_shift(n), cs = 1 << sh;
+    double v[32];
+    for (int j = 0; j < 32; ++j) {
+        double c = 0.0;
+        const int lo = j << sh, hi = (lo + cs < n) ? lo + cs : n;
+        for (int i = lo; i < hi; ++i) c = c + rates[i];
+        v[j] = c;
+    }
+    for (int o = 1; o < 32; o <<= 1)                 /* in-place Hillis-Steele: high lanes first so that v[l - o] is still the old value */
+        for (int l = 31; l >= o; --l) v[l] = v[l] + v[l - o];
+    return v[31];
+}
+#endif
+
 /* Tabulated flip rate (custom `flip_rate_fn`, PARTICLE_solver_CLASS.py:59-62,262): tab[s*(G+1) + k] holds
  * flip_rate_fn(sigma, m_k) evaluated ON THE HOST by the caller's Python callable at m_k = -1 + 2k/G, s = 0 for
  * sigma = +1 and 1 for sigma = -1; between grid points the rate is interpolated linearly (single-rounding operations

@@ -284,6 +284,7 @@ static void run_one(const aps_params* P, const aps_batch* B, int rep, int mode, 
         else m_field(w, P, B->weights);                                  /* :512 */
         if (n == 0) { status = APS_RUN_EMPTY; break; }                   /* :256-257 (every particle has exited) */
         double R = build_rates(w, P, n, beta, anchor, B->flip_tab, B->flip_G);   /* :259-352 */
+        if (mode != 0) R = aps_native_total(w->rates, n);                /* native mode: the selection scan's total (aps_math.h) */
         if (!(R > 0)) { status = APS_RUN_EMPTY; break; }                 /* :353-355 */
         double e, u_choice, u_event;
         if (mode == 0) {

@@ -5,8 +5,12 @@ All 4096 replicas (64 beta x 64 runs) of BASELINE config 2 at its FULL length, r
   2. the replay logs are written from the ORACLE's trajectories (`aps_oracle_philox_log`: the variates in the order
      the reference draws them, the 4th one only for the oracle's diffusive events) — the kernel has no part in them;
   3. the GPU replays all 4096 logs in one launch: every output of every replica (observation rows, positions,
-     sigma sums, event counts, final state and the bit pattern of the event clock) must equal the oracle's;
-  4. the GPU's native Philox run must give the same again (replay == native).
+     sigma sums, event counts, final state) must equal the oracle's; the event clock agrees to 1e-12 here, because
+     replay mode sums R in numpy's pairwise order (the reference's clock) and native mode takes the selection
+     scan's total (aps_math.h, aps_native_total) — 64 replicas are additionally replayed by the ORACLE, and there
+     the GPU's clock must match bit for bit;
+  4. the GPU's native Philox run must equal the oracle's native run in every output INCLUDING the bit pattern of
+     the event clock (same definition of R on both sides).
 Size-independent properties on all 4096: particle conservation, exclusion, single-file order (K = 1 nearest-
 neighbour hops never reorder particles), sigma-sum consistency.
 The oracle needs ~2 minutes on 16 host threads for step 1; set APS_TEST_ENSEMBLE_T to shorten the run."""
@@ -72,11 +76,14 @@ def test_4096_replicas_full_length_replay_and_native_equal_the_oracle():
     nev = ora["n_events"]
     assert nev.sum() > 2.5e6 * T and nev.min() > 500 * T
 
-    def assert_equals_oracle(tag):
+    def assert_equals_oracle(tag, clock_bitwise):
         torch.cuda.synchronize()
         for k in OUT_KEYS:
             got = getattr(rb, k).cpu().numpy()
             want = ora[k]
+            if k == "t_end" and not clock_bitwise:
+                np.testing.assert_allclose(got, want, rtol=1e-12, err_msg=f"{tag}: event clock")
+                continue
             if k in ("obs_pos", "pos_end", "sigma_end"):          # slots beyond n[r] are padding
                 mask = np.arange(ens.n_max)[None, :] < n[:, None]
                 mask = mask[:, None, :] if k == "obs_pos" else mask
@@ -91,18 +98,26 @@ def test_4096_replicas_full_length_replay_and_native_equal_the_oracle():
     draw_off = torch.tensor(off, dtype=torch.int64, device="cuda")
     del logs
     rb.run_replay(draws, draw_off)
-    assert_equals_oracle("replay")
+    assert_equals_oracle("replay", clock_bitwise=False)
     assert torch.equal(rb.draws_used, draw_off[1:] - draw_off[:-1])
     rep = {k: getattr(rb, k).clone() for k in OUT_KEYS}
-    del draws
+    # replay-mode clock, bit for bit: the oracle replays the same logs for one replica per beta
+    idx = np.arange(0, R, 64)
+    d_h, off_h = draws.cpu().numpy(), np.asarray(off)
+    sub = [d_h[off_h[i]:off_h[i + 1]] for i in idx]
+    hr = HostRun(mp["L"], ens.n_max, rb.M, n[idx], pos0[idx], sg0[idx], betas[idx], ens.times_obs, mp["weights"],
+                 draws=np.concatenate(sub), draw_off=np.concatenate([[0], np.cumsum([len(x) for x in sub])]), record=3,
+                 alloc_m_local=False)
+    run_oracle(params, hr, mode=0, threads=threads)
+    assert np.array_equal(hr.t_end.view(np.uint64), rep["t_end"].cpu().numpy()[idx].view(np.uint64))
+    assert np.array_equal(hr.n_events, nev[idx]) and np.array_equal(hr.obs_cp, rep["obs_cp"].cpu().numpy()[idx])
+    del draws, d_h
 
-    # ---- 4: GPU native run: same again ----
+    # ---- 4: GPU native run == oracle native run, clock included ----
     for k in OUT_KEYS:
         getattr(rb, k).zero_()
     rb.run_philox()
-    torch.cuda.synchronize()
-    for k, v in rep.items():
-        assert torch.equal(_bits(getattr(rb, k)), _bits(v)), f"native differs from replay in {k}"
+    assert_equals_oracle("native", clock_bitwise=True)
 
     # ---- size-independent properties on the whole ensemble ----
     tot = rep["obs_cp"].to(torch.int32) + rep["obs_cm"].to(torch.int32)

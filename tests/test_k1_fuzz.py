@@ -122,32 +122,6 @@ def test_half_image_kernel_random_parameters(seed):
     assert (gpu.n_events > 0).any()
 
 
-@pytest.mark.parametrize("seed", range(12))
-def test_two_replicas_per_warp_kernel_random_parameters(seed):
-    """aps_k1_pair.cuh (two replicas per warp, one per half-warp; off by default because it measured slower) on the same random
-    sorted K = 1 cases: every output must equal the oracle's, native and replay mode alternating, ragged / odd replica counts."""
-    lib = capi.load()
-    c = random_case(9100 + seed, sorted_init=True, lean=True)
-    try:
-        lib.aps_debug_set_k1_pair(1)
-        if seed % 2 == 0:
-            seeds = np.array([seed, 2 ** 33 + seed, 7 * seed + 1, 2 ** 63 + seed], np.uint64)
-            gpu = build(c, seeds=seeds)
-            capi.check(lib.aps_run_philox_host(c["params"], gpu.batch), "aps_run_philox_host")
-            ora = run_oracle(c["params"], build(c, seeds=seeds), mode=1, threads=2)
-        else:
-            g = np.random.default_rng(seed)
-            lens = g.integers(200, 3000, len(c["ns"]))
-            off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-            draws = g.random(int(off[-1]))
-            gpu = build(c, draws=draws, draw_off=off)
-            capi.check(lib.aps_run_replay_host(c["params"], gpu.batch), "aps_run_replay_host")
-            ora = run_oracle(c["params"], build(c, draws=draws, draw_off=off), mode=0, threads=2)
-    finally:
-        lib.aps_debug_set_k1_pair(0)
-    assert_same_outputs(gpu, ora)
-
-
 @pytest.mark.parametrize("n", [1, 7, 8, 9, 128, 129, 257, 488, 489, 495, 505, 512, 600, 968, 969, 1000, 1024])
 def test_half_image_kernel_particle_count_edges(n):
     """Sorted K = 1 inputs around the sizes where numpy's pairwise-sum tree changes shape (129: two leaves, 257: three,
