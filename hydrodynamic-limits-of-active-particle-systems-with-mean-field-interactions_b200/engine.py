@@ -75,7 +75,7 @@ class ReplicaBatch:
     def __init__(self, *, L, K, radius, weights, D, lam, T, times_obs, betas, n, pos0, sigma0, seeds=None,
                  record=APS_REC_COUNTS | APS_REC_POS, crowding=False, device=None, dx=None, anchor_mask=None,
                  k_on=0.0, k_off=0.0, k_exit=0.0, suppress_flip_when_bound=True, immobilize_when_anchored=True,
-                 exit_cap=None, periodic=False, flip_tab=None):
+                 exit_cap=None, periodic=False, flip_tab=None, zero_rows=True):
         self.lib = capi.load()
         self.dev = _dev(device)
         self.L, self.K, self.radius = int(L), int(K), int(radius)
@@ -107,10 +107,13 @@ class ReplicaBatch:
         self.flip_G = 0 if flip_tab is None else int(self.flip_tab.shape[1]) - 1
         R, M, Lq, nm, dv = self.R, self.M, self.L, self.n_max, self.dev
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dv)
-        self.obs_cp = z((R, M, Lq), torch.int8) if record & APS_REC_COUNTS else None
-        self.obs_cm = z((R, M, Lq), torch.int8) if record & APS_REC_COUNTS else None
-        self.obs_pos = z((R, M, nm), torch.int32) if record & APS_REC_POS else None
-        self.obs_m_local = z((R, M, Lq), torch.float64) if record & APS_REC_MLOCAL else None
+        # observation rows: zero-filled like the reference's preallocated arrays (rows never reached stay zero, CLASS.py:465-472) unless
+        # the caller only feeds them to the device-side reducers, which never read a row >= n_obs (saves a multi-GB memset per sweep)
+        zr = z if zero_rows else (lambda shape, dt: torch.empty(shape, dtype=dt, device=dv))
+        self.obs_cp = zr((R, M, Lq), torch.int8) if record & APS_REC_COUNTS else None
+        self.obs_cm = zr((R, M, Lq), torch.int8) if record & APS_REC_COUNTS else None
+        self.obs_pos = zr((R, M, nm), torch.int32) if record & APS_REC_POS else None
+        self.obs_m_local = zr((R, M, Lq), torch.float64) if record & APS_REC_MLOCAL else None
         self.obs_sigma_sum = z((R, M), torch.int32)
         self.n_obs = z((R,), torch.int32)
         self.n_events = z((R,), torch.int64)

@@ -125,15 +125,15 @@ def permute_spec(spec: "EnsembleSpec", order: np.ndarray) -> "EnsembleSpec":
 
 def expected_poisson_particles(rho_p, rho_m, K):
     """mean and an upper bound of n for the K-truncated Poisson init (CLASS.py:160-189)."""
-    lam = np.asarray(rho_p) + np.asarray(rho_m)
-    mean = 0.0
-    for l in lam:
-        pk, cdf, e = math.exp(-l), 0.0, 0.0
-        for k in range(K):
-            e += k * pk
-            cdf += pk
-            pk *= l / (k + 1)
-        mean += e + K * (1.0 - cdf)
+    lam = np.asarray(rho_p, dtype=float) + np.asarray(rho_m, dtype=float)
+    pk = np.exp(-lam)                       # P(count = k), k = 0 .. K-1, vectorised over the sites
+    cdf = np.zeros_like(lam)
+    e = np.zeros_like(lam)
+    for k in range(K):
+        e += k * pk
+        cdf += pk
+        pk = pk * lam / (k + 1)
+    mean = float((e + K * (1.0 - cdf)).sum())
     return mean, int(math.ceil(mean + 6.5 * math.sqrt(max(mean, 1.0)) + 8))
 
 
@@ -231,7 +231,8 @@ class DeviceEnsemble:
         self.rb = ReplicaBatch(L=mp["L"], K=mp["K"], radius=mp["radius"], weights=mp["weights"], D=mp["D"], lam=mp["lam"],
                                T=T, times_obs=self.times_obs, betas=self.betas_h, n=self.n, pos0=self.pos0,
                                sigma0=self.sigma0, seeds=self.seeds, record=spec.record, crowding=mp["crowding"],
-                               device=self.dev.index, dx=mp["dx"], periodic=mp["periodic"], flip_tab=mp["flip_tab"])
+                               device=self.dev.index, dx=mp["dx"], periodic=mp["periodic"], flip_tab=mp["flip_tab"],
+                               zero_rows=bool(spec.record & capi.APS_REC_MLOCAL))   # reducer-only ensembles never read a row >= n_obs
         self.h2d_bytes += (self.rb.times_obs.numel() + self.rb.beta.numel() + (self.rb.weights.numel() if self.rb.weights is not None else 0)) * 8
         self.n_points = int(spec.point_of.max()) + 1 if len(spec.point_of) else 0
         # replica lists per grid point (CSR) for the device-side per-point sums: the shard is in schedule order
