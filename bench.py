@@ -587,7 +587,7 @@ def k2_main(args, torch, la, capi, rank, world):
     # ---- end to end: host lattice bytes -> device slabs -> passes -> coarse profile on the host ----
     rng = np.random.default_rng(0)
     host = torch.from_numpy(np.where(rng.random(L) < 0.5, np.where(rng.random(L) < 0.5, 1, 2), 0).astype(np.uint8)).pin_memory()
-    e2e_steps = 20
+    e2e_steps = 100                          # upload once, run 100 time units, read the profile: the shape of a real use
     barrier()
     t0 = time.perf_counter()
     for _ in range(3):

@@ -128,7 +128,8 @@ class ApsProfileArgs(C.Structure):
 
 class ApsHistArgs(C.Structure):
     _fields_ = [("n_replicas", C.c_int32), ("M", C.c_int32), ("n_points", C.c_int32), ("n_bins", C.c_int32),
-                ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("lo", C.c_double), ("hi", C.c_double),
+                ("row_lo", C.c_int32), ("row_hi", C.c_int32), ("accumulate", C.c_int32), ("reserved", C.c_int32),
+                ("lo", C.c_double), ("hi", C.c_double),
                 ("n", C.c_void_p), ("n_obs", C.c_void_p), ("obs_sigma_sum", C.c_void_p), ("obs_n", C.c_void_p),
                 ("point_of", C.c_void_p), ("mbar", C.c_void_p), ("hist", C.c_void_p)]
 

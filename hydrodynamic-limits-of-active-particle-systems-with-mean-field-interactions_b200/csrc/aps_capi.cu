@@ -374,6 +374,7 @@ int aps_m_histogram_device(const aps_hist_args* a, void* stream) {
         a->row_lo < 0 || a->row_hi > a->M || a->row_hi <= a->row_lo || !(a->hi > a->lo))
         return fail(APS_ERR_INVALID, "aps_m_histogram: bad argument");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
+    if (!a->accumulate) CU(cudaMemsetAsync(a->hist, 0, (size_t)a->n_points * (size_t)a->n_bins * 8, (cudaStream_t)stream));
     if (a->n_replicas == 0) return APS_OK;
     aps::hist_kernel<<<(a->n_replicas + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*a);
     CU(cudaGetLastError());

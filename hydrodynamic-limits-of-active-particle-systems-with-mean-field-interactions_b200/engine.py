@@ -187,7 +187,7 @@ class ReplicaBatch:
     def reduce(self, boundary_xmin=0.99, max_boundary_fraction=0.06, min_window_fraction=0.10,
                window_fraction=0.05, want_v_eff=False):
         """Per-run reducers -> tensor [R][APS_RED_N] (see include/aps.h APS_RED_*)."""
-        out = torch.zeros((self.R, APS_RED_N), dtype=torch.float64, device=self.dev)
+        out = torch.empty((self.R, APS_RED_N), dtype=torch.float64, device=self.dev)      # every slot is written by the kernel
         v = torch.zeros((self.R, self.M), dtype=torch.float64, device=self.dev) if want_v_eff else None
         a = ApsReduceArgs(self.R, self.M, self.L, self.n_max, self.dx, boundary_xmin, max_boundary_fraction,
                           min_window_fraction, window_fraction, self.times_obs.data_ptr(), self.n.data_ptr(),
@@ -228,10 +228,10 @@ class ReplicaBatch:
         the per-replica values (f64 [R]); device-side accumulation (`aps_m_histogram_device`)."""
         row_lo = self.M // 2 if row_lo is None else row_lo
         row_hi = self.M if row_hi is None else row_hi
-        hist = torch.zeros((n_points, n_bins), dtype=torch.int64, device=self.dev)
+        hist = torch.empty((n_points, n_bins), dtype=torch.int64, device=self.dev)       # zeroed by the call (accumulate = 0)
         mbar = torch.empty((self.R,), dtype=torch.float64, device=self.dev)
         obs_n = getattr(self, "obs_n", None)
-        a = ApsHistArgs(self.R, self.M, n_points, n_bins, row_lo, row_hi, lo, hi, self.n.data_ptr(), self.n_obs.data_ptr(),
+        a = ApsHistArgs(self.R, self.M, n_points, n_bins, row_lo, row_hi, 0, 0, lo, hi, self.n.data_ptr(), self.n_obs.data_ptr(),
                         self.obs_sigma_sum.data_ptr(), obs_n.data_ptr() if obs_n is not None else None,
                         point_of.data_ptr() if point_of is not None else None, mbar.data_ptr(), hist.data_ptr())
         capi.check(self.lib.aps_m_histogram_device(a, _stream()), "aps_m_histogram_device")

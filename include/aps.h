@@ -274,6 +274,7 @@ int aps_profile_sums_device(const aps_profile_args* a, void* stream);
 typedef struct aps_hist_args {
     int32_t n_replicas, M, n_points, n_bins;
     int32_t row_lo, row_hi;
+    int32_t accumulate, reserved;   /* 0: the call zeroes hist first (cudaMemsetAsync); 1: add to its contents */
     double lo, hi;                  /* histogram range, normally [-1, 1]                           */
     const int32_t* n;               /* [n_replicas]                                               */
     const int32_t* n_obs;           /* [n_replicas]                                               */
@@ -281,7 +282,7 @@ typedef struct aps_hist_args {
     const int32_t* obs_n;           /* [n_replicas][M] optional per-row particle count (exits)    */
     const int32_t* point_of;        /* [n_replicas] optional grid point of every replica (else 0) */
     double* mbar;                   /* [n_replicas] optional                                      */
-    unsigned long long* hist;       /* [n_points][n_bins], accumulated into (caller zeroes)       */
+    unsigned long long* hist;       /* [n_points][n_bins]                                          */
 } aps_hist_args;
 int aps_m_histogram_device(const aps_hist_args* a, void* stream);
 

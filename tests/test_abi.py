@@ -41,7 +41,7 @@ def test_struct_layout_matches_header(lib):
     assert C.sizeof(capi.ApsParams) == 64
     assert C.sizeof(capi.ApsBatch) == 16 + 24 + 36 * 8 + 8 + 16           # + flip_tab, flip_G (ABI 5)
     assert C.sizeof(capi.ApsPdeArgs) == 8 * 4 + 8 + 3 * 8 + 18 * 8      # include/aps_pde.h
-    assert C.sizeof(capi.ApsProfileArgs) == 6 * 4 + 8 + 8 * 8 + 8 and C.sizeof(capi.ApsHistArgs) == 6 * 4 + 2 * 8 + 7 * 8
+    assert C.sizeof(capi.ApsProfileArgs) == 6 * 4 + 8 + 8 * 8 + 8 and C.sizeof(capi.ApsHistArgs) == 8 * 4 + 2 * 8 + 7 * 8
     assert C.sizeof(capi.ApsK2Multi) == 4 * 4 + 3 * 8 + 3 * 8 + 8 * 8 and lib.aps_k2_peer_region_bytes() == 320 + 4 * 65536
 
 
