@@ -388,12 +388,43 @@ int aps_k2_rates_init(double D, double lam, double beta, double dt, aps_k2_rates
     return APS_OK;
 }
 
-static size_t k2_smem(int radius, int cap) {
+static size_t k2_smem(int radius, int cap, int stages = 0) {
     const size_t WB = aps::kK2Tile + 32;
     const size_t R16 = radius >= 0 ? (size_t)((radius + 15) & ~15) : 0;
     const size_t stride = WB + 2 * R16;              // local field: window + halo in one buffer per stage
-    return 128 + (size_t)(radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal) * stride +
-           (radius >= 0 ? aps::k2_scratch_bytes(radius, cap) + 16 : 0);
+    if (stages <= 0) stages = radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal;
+    return 128 + (size_t)stages * stride + (radius >= 0 ? aps::k2_scratch_bytes(radius, cap) + 16 : 0);
+}
+
+// Launch plan of a K2 pass: ring depth, shared memory and grid.  Long tile walks (many tiles per CTA) use the deep ring at
+// g_k2_ctas_per_sm CTAs per SM.  SHORT slabs — a 2^26-site lattice cut over 8 GPUs leaves 1026 tiles per rank against 888
+// persistent CTAs, i.e. two rounds of which the second is 15 % full — take a 2-deep ring instead when that lets enough CTAs be
+// resident (co-resident for the grid barrier) to walk the slab in fewer rounds.
+struct K2Plan { int stages; size_t smem; int grid; };
+static int k2_plan(const void* fn, int radius, int cap, int ntiles, int n_sm, K2Plan* out) {
+    // one-entry cache per thread: a run is thousands of launches with the same plan (the occupancy queries are host-side work)
+    struct Key { const void* fn; int radius, cap, ntiles, per_sm_cap; K2Plan plan; };
+    thread_local Key last{nullptr, 0, 0, 0, 0, {}};
+    if (last.fn == fn && last.radius == radius && last.cap == cap && last.ntiles == ntiles && last.per_sm_cap == g_k2_ctas_per_sm) { *out = last.plan; return 0; }
+    int best_rounds = 1 << 30;
+    for (int pass = 0; pass < 2; ++pass) {
+        const int stages = pass == 0 ? (radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal) : 2;
+        const size_t smem = k2_smem(radius, cap, stages);
+        if (smem > 227 * 1024) continue;
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, aps::kK2Threads, smem) != cudaSuccess) { cudaGetLastError(); continue; }
+        const int cap_sm = pass == 0 ? g_k2_ctas_per_sm : 2 * g_k2_ctas_per_sm;
+        if (per_sm > cap_sm) per_sm = cap_sm;
+        if (per_sm < 1) continue;
+        int grid = n_sm * per_sm;
+        if (grid > ntiles) grid = ntiles;
+        const int rounds = (ntiles + grid - 1) / grid;
+        if (rounds < best_rounds && (pass == 0 || rounds <= 2)) { best_rounds = rounds; out->stages = stages; out->smem = smem; out->grid = grid; }
+    }
+    if (best_rounds == (1 << 30)) return -1;
+    last = Key{fn, radius, cap, ntiles, g_k2_ctas_per_sm, *out};
+    return 0;
 }
 
 int aps_k2_flip_table(const aps_k2_rates* r, uint32_t* out) {
@@ -413,24 +444,17 @@ int aps_k2_pass_device(const aps_k2_args* a, void* stream) {
     if (a->radius < 0 && (!a->msum_in || a->n_particles < 1)) return fail(APS_ERR_INVALID, "aps_k2_pass: global field needs msum_in and n_particles");
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
     const int cap = g_k2_stash_cap > 0 ? g_k2_stash_cap : aps::k2_stash_cap(a->rates.mu);
-    const size_t smem = k2_smem(a->radius, cap);
-    if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_k2_pass: radius too large for the shared-memory ring");
+    if (k2_smem(a->radius, cap) > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_k2_pass: radius too large for the shared-memory ring");
     const int ntiles = (int)(a->L / aps::kK2Tile);
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; CU(cudaGetDevice(&dev)); CU(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
-    int per_sm = (int)((size_t)(220 * 1024) / smem);
-    if (per_sm > g_k2_ctas_per_sm) per_sm = g_k2_ctas_per_sm;
-    if (per_sm < 1) per_sm = 1;
-    int grid = n_sm * per_sm;                       // persistent CTAs: a multiple of the SM count
-    if (grid > ntiles) grid = ntiles;
+    const void* fn = a->radius >= 0 ? (const void*)aps::k2_pass_kernel<true, false> : (const void*)aps::k2_pass_kernel<false, false>;
+    K2Plan plan{};
+    if (k2_plan(fn, a->radius, cap, ntiles, n_sm, &plan)) return fail(APS_ERR_CAPACITY, "aps_k2_pass: kernel does not fit on an SM");
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
     const aps::K2Multi none{};
-    if (a->radius >= 0) {
-        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        aps::k2_pass_kernel<true, false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap, none);
-    } else {
-        CU(cudaFuncSetAttribute(aps::k2_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        aps::k2_pass_kernel<false, false><<<grid, aps::kK2Threads, smem, (cudaStream_t)stream>>>(*a, cap, none);
-    }
+    if (a->radius >= 0) aps::k2_pass_kernel<true, false><<<plan.grid, aps::kK2Threads, plan.smem, (cudaStream_t)stream>>>(*a, cap, none, plan.stages);
+    else aps::k2_pass_kernel<false, false><<<plan.grid, aps::kK2Threads, plan.smem, (cudaStream_t)stream>>>(*a, cap, none, plan.stages);
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return APS_OK;
@@ -480,8 +504,7 @@ int aps_k2_run_persistent_device(aps_k2_args* a, const aps_k2_multi* hm, void* s
     if (count_sm100() == 0) return fail(APS_ERR_NO_DEVICE, "no sm_100 CUDA device visible; this library has no CPU path");
     if (hm->n_passes == 0) return APS_OK;
     const int cap = g_k2_stash_cap > 0 ? g_k2_stash_cap : aps::k2_stash_cap(a->rates.mu);
-    const size_t smem = k2_smem(a->radius, cap);
-    if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_k2_run_persistent: radius too large for the shared-memory ring");
+    if (k2_smem(a->radius, cap) > 227 * 1024) return fail(APS_ERR_CAPACITY, "aps_k2_run_persistent: radius too large for the shared-memory ring");
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, n_sm = 0, coop = 0;
     CU(cudaGetDevice(&dev));
@@ -489,14 +512,12 @@ int aps_k2_run_persistent_device(aps_k2_args* a, const aps_k2_multi* hm, void* s
     CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     if (!coop) return fail(APS_ERR_CUDA, "device does not support cooperative launches");
     const void* fn = a->radius >= 0 ? (const void*)aps::k2_pass_kernel<true, true> : (const void*)aps::k2_pass_kernel<false, true>;
-    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, aps::kK2Threads, smem));
-    if (per_sm > g_k2_ctas_per_sm) per_sm = g_k2_ctas_per_sm;
-    if (per_sm < 1) return fail(APS_ERR_CAPACITY, "aps_k2_run_persistent: kernel does not fit on an SM");
     const int ntiles = (int)(a->L / aps::kK2Tile);
-    int grid = n_sm * per_sm;                       // all CTAs co-resident (grid barrier): a multiple of the SM count
-    if (grid > ntiles) grid = ntiles;
+    K2Plan plan{};                                  // all CTAs co-resident (grid barrier): grid <= SMs x resident CTAs per SM
+    if (k2_plan(fn, a->radius, cap, ntiles, n_sm, &plan)) return fail(APS_ERR_CAPACITY, "aps_k2_run_persistent: kernel does not fit on an SM");
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    const int grid = plan.grid;
+    const size_t smem = plan.smem;
     aps::K2Multi m{};
     m.n_passes = hm->n_passes; m.world = hm->world; m.rank = hm->rank; m.refresh_every = hm->refresh_every > 0 ? hm->refresh_every : 1;
     m.ghost = hm->ghost; m.own_lo = hm->own_lo; m.own_hi = hm->own_hi;
@@ -507,8 +528,8 @@ int aps_k2_run_persistent_device(aps_k2_args* a, const aps_k2_multi* hm, void* s
     CU(cudaMemsetAsync(sync, 0, 8, st));            // barrier counter restarts with every launch
     aps_k2_args ka = *a;
     if (hm->world > 1 && a->radius < 0) { ka.count_lo = hm->own_lo; ka.count_hi = hm->own_hi; }   // own flips only
-    int cap_arg = cap;
-    void* params[] = {(void*)&ka, (void*)&cap_arg, (void*)&m};
+    int cap_arg = cap, stages_arg = plan.stages;
+    void* params[] = {(void*)&ka, (void*)&cap_arg, (void*)&m, (void*)&stages_arg};
     CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(aps::kK2Threads), params, smem, st));
     g_launches.fetch_add(1);
     a->pass += (uint64_t)hm->n_passes;

@@ -189,7 +189,7 @@ __device__ __forceinline__ void k2_grid_sync(const K2Multi& m, unsigned& round) 
 // m.buf[0] and m.buf[1] with grid barriers and, for world > 1, the peer-memory exchanges described above.
 template <bool LOCAL, bool MULTI>
 __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_constant__ aps_k2_args a, const int stash_cap,
-                                                             const __grid_constant__ K2Multi m) {
+                                                             const __grid_constant__ K2Multi m, const int nstages) {
     extern __shared__ __align__(128) unsigned char k2_raw[];
     const int tid = threadIdx.x;
     const long long L = a.L;                         // sites held by this call (slab incl. ghosts)
@@ -197,7 +197,9 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     const int R16 = LOCAL ? ((r + 15) & ~15) : 0;
     const int ntiles = (int)(L / kK2Tile);
     constexpr int WB = kK2Tile + 32;                 // largest window
-    constexpr int kK2Stages = LOCAL ? kK2StagesLocal : kK2StagesGlobal;
+    // ring depth: kK2StagesLocal / kK2StagesGlobal for long tile walks; 2 for short slabs (a tile or two per CTA: more CTAs per SM
+    // beat a deeper ring there, see k2_plan in aps_capi.cu)
+    const int kK2Stages = nstages;
     const int stride = WB + 2 * R16;                 // LOCAL: [lo - R16, hi + R16) in one buffer, the window at offset R16
     uint64_t* bars = reinterpret_cast<uint64_t*>(k2_raw);
     unsigned char* bufs = k2_raw + 128;
