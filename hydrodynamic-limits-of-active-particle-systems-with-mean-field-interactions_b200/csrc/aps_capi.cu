@@ -399,7 +399,7 @@ static size_t k2_smem(int radius, int cap, int stages = 0) {
 // Launch plan of a K2 pass: ring depth, shared memory and grid.  Long tile walks (many tiles per CTA) use the deep ring at
 // g_k2_ctas_per_sm CTAs per SM.  SHORT slabs — a 2^26-site lattice cut over 8 GPUs leaves 1026 tiles per rank against 888
 // persistent CTAs, i.e. two rounds of which the second is 15 % full — take a 2-deep ring instead when that lets enough CTAs be
-// resident (co-resident for the grid barrier) to walk the slab in fewer rounds.
+// resident (co-resident for the grid barrier) to walk the slab in ONE round.
 struct K2Plan { int stages; size_t smem; int grid; };
 const bool g_env_k2_no_short_plan = getenv("APS_K2_NO_SHORT_PLAN") != nullptr;   // A/B knob, read once at load
 static int k2_plan(const void* fn, int radius, int cap, int ntiles, int n_sm, K2Plan* out) {
@@ -421,7 +421,9 @@ static int k2_plan(const void* fn, int radius, int cap, int ntiles, int n_sm, K2
         int grid = n_sm * per_sm;
         if (grid > ntiles) grid = ntiles;
         const int rounds = (ntiles + grid - 1) / grid;
-        if (rounds < best_rounds && (pass == 0 || rounds <= 2)) { best_rounds = rounds; out->stages = stages; out->smem = smem; out->grid = grid; }
+        // the 2-deep ring only pays when it makes the walk a SINGLE round (measured: 1024 tiles 14.3 -> 12.9 us per pass; with two
+        // rounds of 1776 CTAs the grid barrier of the persistent kernel costs more than the saved round: 20.4 -> 29.0 us at 2048 tiles)
+        if (rounds < best_rounds && (pass == 0 || rounds == 1)) { best_rounds = rounds; out->stages = stages; out->smem = smem; out->grid = grid; }
     }
     if (best_rounds == (1 << 30)) return -1;
     last = Key{fn, radius, cap, ntiles, g_k2_ctas_per_sm, *out};
