@@ -43,6 +43,7 @@ _FIELDS = {
     "exit_pos": "int32",
     "n_exit": "int32",
     "flip_tab": "float64",
+    "weights_host": "float64",
 }
 
 

@@ -87,6 +87,7 @@ class ApsBatch(C.Structure):
         ("exit_cap", C.c_int64),
         ("flip_tab", C.c_void_p),
         ("flip_G", C.c_int64),
+        ("weights_host", C.c_void_p),
     ]
 
 

@@ -131,6 +131,12 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "replica does not fit in 227 KB of shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     a.only_retry = 0; a.reserved = 0;
+    a.wt_valid = 0; a.reserved2 = 0;
+    for (int j = 0; j < 24; ++j) a.wt[j] = 0.0;
+    if (b->weights_host && p->radius >= 0 && p->radius <= 23) {      // taps w[0..radius] (outermost first) as kernel parameters
+        for (int j = 0; j <= p->radius; ++j) a.wt[j] = b->weights_host[j];
+        a.wt_valid = 1;
+    }
     // specialised kernel for K = 1 with a local field (every shipped sweep configuration)
     const bool fast_ok = g_use_fast && p->K == 1 && p->radius >= 0 && p->radius < p->L && !(p->flags & (APS_FLAG_CROWDING | APS_FLAG_PERIODIC)) &&
                          !b->m_field_in && !b->anchor_mask && !b->flip_tab && b->n_max <= 1024 && b->status != nullptr;
@@ -201,6 +207,7 @@ int run_host(const aps_params* p, const aps_batch* hb, bool philox) {
     aps_batch d = *hb;
     TRY(s.in(hb->times_obs, M * 8, (const void**)&d.times_obs));
     TRY(s.in(hb->weights, p->radius >= 0 ? (size_t)(2 * p->radius + 1) * 8 : 0, (const void**)&d.weights));
+    d.weights_host = hb->weights;                  // host-buffer entry point: the taps are host memory already
     TRY(s.in(hb->beta, R * 8, (const void**)&d.beta));
     TRY(s.in(hb->n, R * 4, (const void**)&d.n));
     TRY(s.in(hb->pos0, R * NM * 4, (const void**)&d.pos0));

@@ -194,11 +194,11 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         const double w0 = F.wtab[r];
         const double2 m0 = F.mst[c[0]];
         double sc = APS_MUL(m0.x, w0), tc = APS_MUL(m0.y, w0);
-        if (decltype(hot)::value && r == RCAP - 1) {
+        if (decltype(hot)::value && r == RCAP - 1 && RCAP <= 24 && A.wt_valid) {
 #pragma unroll
             for (int jj = -(RCAP - 1); jj < 0; ++jj) {
                 const double2 mm = F.mst[(int)c[jj] + (int)c[-jj]];
-                const double wj = F.wtab[RCAP - 1 + jj];
+                const double wj = A.wt[RCAP <= 24 ? RCAP - 1 + jj : 0];  // kernel parameter: a constant-bank operand of the DFMA, no load
                 sc = __fma_rn(mm.x, wj, sc);
                 tc = __fma_rn(mm.y, wj, tc);
             }
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         };
 
         // ---- selection: chunk sums (dirty ones re-summed, cached in a register), warp scan, walk of the winning chunk ----
-        double r_scan;                                  // total of the scan = R in native mode (aps_math.h, aps_native_total)
+        double r_scan, inv_r_scan = 0.0;                // total of the scan = R in native mode (aps_math.h, aps_native_total), and 1/R
         {
             if (lane < nchunks && F.dirty_c[lane]) {
                 const int c0 = lane << cs_shift;
@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             if (lane == 0) prev = 0.0;
             const double atot = __shfl_sync(0xffffffffu, incl, 31);
             r_scan = atot;
+            if (PHILOX) inv_r_scan = APS_DIV(1.0, atot);    // every lane, straight after the scan: the division's latency hides behind
+                                                            // the chunk walk instead of sitting in the clock lane's serial section
             const double target = APS_MUL(uc, atot);
             const unsigned wmask = __ballot_sync(0xffffffffu, lane < nchunks && prev <= target && target < incl);
             bool exact = (__popc(wmask) != 1);
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             }
             if (lane == nnodes - 1) {
                 const double R = val;
-                const double tau = APS_MUL(APS_DIV(1.0, R), e);
+                const double tau = APS_MUL(PHILOX ? inv_r_scan : APS_DIV(1.0, R), e);
                 const double tn = APS_ADD(t, tau);
                 F.misc[X_R] = R; F.misc[X_TNEW] = tn;
                 F.desc[D_BADR] = !(R > 0.0);

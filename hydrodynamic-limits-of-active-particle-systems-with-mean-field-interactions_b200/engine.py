@@ -91,6 +91,7 @@ class ReplicaBatch:
         self.times_obs = t(times_obs, np.float64)
         self.M = int(self.times_obs.numel())
         self.weights = t(weights, np.float64) if radius >= 0 else None
+        self.weights_host = np.array(weights, dtype=np.float64, order="C", copy=True) if radius >= 0 else None   # constant-bank taps of K1
         self.beta = t(betas, np.float64)
         self.R = int(self.beta.numel())
         self.n = n if isinstance(n, torch.Tensor) else t(n, np.int32)
@@ -145,6 +146,7 @@ class ReplicaBatch:
             spec_from=extra.pop("spec_from", -1), exit_cap=self.exit_cap, n_end=self.n_end, obs_n=self.obs_n,
             anchor_mask=self.anchor_mask, bound0=self.bound0, bound_end=self.bound_end, obs_bound=self.obs_bound,
             exit_t=self.exit_t, exit_pos=self.exit_pos, n_exit=self.n_exit, flip_tab=self.flip_tab, flip_G=self.flip_G,
+            weights_host=self.weights_host,
             times_obs=self.times_obs, weights=self.weights, beta=self.beta, n=self.n, pos0=self.pos0,
             sigma0=self.sigma0, obs_cp=self.obs_cp, obs_cm=self.obs_cm, obs_pos=self.obs_pos,
             obs_sigma_sum=self.obs_sigma_sum, obs_m_local=self.obs_m_local, n_obs=self.n_obs,

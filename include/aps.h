@@ -155,6 +155,10 @@ typedef struct aps_batch {
      * the kernels interpolate linearly (aps_flip_interp, aps_math.h: tolerance stated there).                        */
     const double* flip_tab;
     int64_t flip_G;
+    /* optional HOST copy of `weights` (same 2*radius+1 values) for the `*_device` entry points: the specialised K1 kernel takes
+     * the taps as kernel-parameter (constant-bank) operands of its unrolled filter instead of shared-memory loads.  NULL is
+     * allowed (the taps are then read from shared memory); the `*_host` entry points fill it in themselves.             */
+    const double* weights_host;
 } aps_batch;
 
 int aps_abi_version(void);

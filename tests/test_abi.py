@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
 def test_struct_layout_matches_header(lib):
     # sizes the C compiler gives the two descriptors (x86-64 SysV): 4 int32 + 6 double; 4 int32 + 3 int64 + 36 pointers + exit_cap
     assert C.sizeof(capi.ApsParams) == 64
-    assert C.sizeof(capi.ApsBatch) == 16 + 24 + 36 * 8 + 8 + 16           # + flip_tab, flip_G (ABI 5)
+    assert C.sizeof(capi.ApsBatch) == 16 + 24 + 36 * 8 + 8 + 24           # + flip_tab, flip_G, weights_host (ABI 5)
     assert C.sizeof(capi.ApsPdeArgs) == 8 * 4 + 8 + 3 * 8 + 18 * 8      # include/aps_pde.h
     assert C.sizeof(capi.ApsProfileArgs) == 6 * 4 + 8 + 8 * 8 + 8 and C.sizeof(capi.ApsHistArgs) == 8 * 4 + 2 * 8 + 7 * 8
     assert C.sizeof(capi.ApsK2Multi) == 4 * 4 + 3 * 8 + 3 * 8 + 8 * 8 and lib.aps_k2_peer_region_bytes() == 320 + 4 * 65536
