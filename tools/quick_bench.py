@@ -72,7 +72,8 @@ def main():
              t_end=torch.zeros(R, dtype=torch.float64, device=dev), status=torch.zeros(R, dtype=torch.int32, device=dev),
              n_guard=torch.zeros(R, dtype=torch.int64, device=dev))
     p = make_params(L, 1, radius, a.D, a.lam, a.T)
-    b, keep = make_batch(R, nmax, M, record=a.record, max_events=a.max_events, **d)
+    w_host = np.ascontiguousarray(w, dtype=np.float64)
+    b, keep = make_batch(R, nmax, M, record=a.record, max_events=a.max_events, weights_host=w_host, **d)
     print(f"R={R} nmax={nmax} mean n={ns.mean():.1f} radius={radius} M={M} smem/replica={lib.aps_replica_smem_bytes(p, nmax)}")
     st = torch.cuda.current_stream().cuda_stream
     for rep in range(a.reps):
