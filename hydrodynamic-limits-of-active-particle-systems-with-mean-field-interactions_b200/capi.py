@@ -208,6 +208,7 @@ SYMBOLS = {
     "aps_debug_set_use_fast": (None, [C.c_int]),
     "aps_debug_set_k2_ctas_per_sm": (None, [C.c_int]),
     "aps_debug_set_k2_stash_cap": (None, [C.c_int]),
+    "aps_debug_set_reduce_impl": (None, [C.c_int]),
     "aps_debug_set_reduce_threads": (None, [C.c_int]),
 }
 

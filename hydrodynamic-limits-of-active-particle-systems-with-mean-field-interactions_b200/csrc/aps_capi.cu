@@ -31,6 +31,7 @@ int g_use_lut = 1;
 int g_use_fast = 1;
 int g_k2_ctas_per_sm = 6;
 int g_reduce_threads = 128;
+int g_reduce_impl = 0;          // 0: integer row sums (round 2); 1: the round-1 kernel (A/B reference of the tests)
 int g_k2_stash_cap = 0;        // 0 = from the mean trial count (aps::k2_stash_cap)
 
 int fail(int code, const std::string& msg) {
@@ -341,8 +342,9 @@ int aps_reduce_runs_device(const aps_reduce_args* a, void* stream) {
     if (a->n_replicas == 0) return APS_OK;
     size_t smem = ((size_t)3 * a->M + 32 + 128) * 8;     // row scalars, reduction scratch, density table
     if (smem > 200 * 1024) return fail(APS_ERR_CAPACITY, "too many observation rows for the reducer");
-    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(aps::reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    aps::reduce_kernel<<<a->n_replicas, g_reduce_threads, smem, (cudaStream_t)stream>>>(*a);
+    auto kern = g_reduce_impl == 1 ? aps::reduce_kernel_v1 : aps::reduce_kernel;
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<a->n_replicas, g_reduce_threads, smem, (cudaStream_t)stream>>>(*a);
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return APS_OK;
@@ -615,6 +617,7 @@ void aps_debug_set_k1_threads(int nt) { g_k1_threads = (nt == 32 || nt == 64 || 
 void aps_debug_set_use_lut(int on) { g_use_lut = on ? 1 : 0; }
 void aps_debug_set_k2_ctas_per_sm(int n) { g_k2_ctas_per_sm = n > 0 ? n : 6; }
 void aps_debug_set_k2_stash_cap(int n) { g_k2_stash_cap = (n == 1 || n == 2 || n == 4 || n == 8 || n == 16 || n == 32) ? n : 0; }
+void aps_debug_set_reduce_impl(int v) { g_reduce_impl = v == 1 ? 1 : 0; }
 void aps_debug_set_reduce_threads(int n) { g_reduce_threads = (n >= 32 && n <= 1024 && n % 32 == 0) ? n : 128; }
 void aps_debug_set_use_fast(int on) { g_use_fast = on; }   // 0 generic only, 1 capacity classes, 2 run-time layout
 

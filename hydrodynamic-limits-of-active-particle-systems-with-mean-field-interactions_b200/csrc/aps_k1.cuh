@@ -556,9 +556,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_kernel(const __grid_constant
                 // native mode: R is DEFINED as the 32-lane scan total of the chunk sums with the chunking rule of aps_math.h
                 // (aps_native_total) — the quantity the specialised kernels' selection produces anyway; same bits in every kernel
                 const int sh = aps_native_cs_shift(n), c_lo = lane << sh;
-                const int c_hi = (c_lo + (1 << sh) < n) ? c_lo + (1 << sh) : n;
-                double c = 0.0;
-                for (int i = c_lo; i < c_hi; ++i) c = APS_ADD(c, s.rates[i]);
+                double c = c_lo < n ? aps_native_chunk(s.rates, c_lo, 1 << sh, n) : 0.0;
                 for (int o = 1; o < 32; o <<= 1) {
                     const double up = __shfl_up_sync(0xffffffffu, c, o);
                     if (lane >= o) c = APS_ADD(c, up);

@@ -339,9 +339,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k1_fast_kernel(const __grid_con
             double cs = 0.0;
             if (lane < nchunks) {
                 if (F.dirty_c[lane]) {
-                    const int c0 = lane << cs_shift;
-                    const int hi_i = (c0 + CS < n) ? c0 + CS : n;
-                    for (int i = c0; i < hi_i; ++i) cs = APS_ADD(cs, rates[i]);
+                    cs = aps_native_chunk(rates, lane << cs_shift, CS, n);      // tree of 16 per block (aps_math.h)
                     F.csum[lane] = cs; F.dirty_c[lane] = 0;
                 } else cs = F.csum[lane];
             }

@@ -74,6 +74,10 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     uint16_t* const pos = reinterpret_cast<uint16_t*>(dyn); dyn += (size_t)NCAP * 2;
     uint16_t* const who = reinterpret_cast<uint16_t*>(dyn); dyn += WHO ? (size_t)LPCAP * 2 : 0;
     uint8_t* const code = dyn;
+    // site codes are stored PRE-SCALED by the size of a multiplier-table entry (16 B): the sum of two codes is the byte offset
+    // into F.mst, so a tap costs one 3-input add instead of an add and a scaled-index multiply (ncu round 2: 7.5 -> 6.5 per tap)
+    constexpr int kCP = 16, kCM = 48;                               // '+' particle, '-' particle (1 and 3 entries)
+    auto mst_at = [&](int byte_off) { return *reinterpret_cast<const double2*>(reinterpret_cast<const unsigned char*>(F.mst) + byte_off); };
 
     // ---------------- prologue ----------------
     for (int i = lane; i < L + 2 * pad; i += 32) code[i] = 0;
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             pos[i] = (uint16_t)p;
             part += sg;
             if (!WHO && i + 1 < n && gp[i + 1] <= p) bad = 1;         // needs strictly increasing positions (K = 1, sorted)
-            code[pad + p] = (uint8_t)(sg == 1 ? 1 : 3);               // distinct sites when valid; garbage otherwise (we bail out)
+            code[pad + p] = (uint8_t)(sg == 1 ? kCP : kCM);              // distinct sites when valid; garbage otherwise (we bail out)
             if (WHO) who[p] = (uint16_t)i;
         }
         if (WHO) {                                                    // two particles on one site: only the last writer is in who[]
@@ -192,12 +196,12 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     auto local_m = [&](int p, auto hot) {
         const uint8_t* c = code + pad + p;
         const double w0 = F.wtab[r];
-        const double2 m0 = F.mst[c[0]];
+        const double2 m0 = mst_at(c[0]);
         double sc = APS_MUL(m0.x, w0), tc = APS_MUL(m0.y, w0);
         if (decltype(hot)::value && r == RCAP - 1 && RCAP <= 24 && A.wt_valid) {
 #pragma unroll
             for (int jj = -(RCAP - 1); jj < 0; ++jj) {
-                const double2 mm = F.mst[(int)c[jj] + (int)c[-jj]];
+                const double2 mm = mst_at((int)c[jj] + (int)c[-jj]);
                 const double wj = A.wt[RCAP <= 24 ? RCAP - 1 + jj : 0];  // kernel parameter: a constant-bank operand of the DFMA, no load
                 sc = __fma_rn(mm.x, wj, sc);
                 tc = __fma_rn(mm.y, wj, tc);
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         } else {
 #pragma unroll 4
             for (int jj = -r; jj < 0; ++jj) {
-                const double2 mm = F.mst[(int)c[jj] + (int)c[-jj]];
+                const double2 mm = mst_at((int)c[jj] + (int)c[-jj]);
                 const double wj = F.wtab[r + jj];
                 sc = __fma_rn(mm.x, wj, sc);
                 tc = __fma_rn(mm.y, wj, tc);
@@ -220,7 +224,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             const size_t row = (size_t)rep * (size_t)M + (size_t)m;
             if ((B.record & APS_REC_COUNTS) && B.obs_cp && B.obs_cm) {
                 int8_t* ocp = B.obs_cp + row * (size_t)L; int8_t* ocm = B.obs_cm + row * (size_t)L;
-                for (int l = lane; l < L; l += 32) { const uint8_t v = code[pad + l]; ocp[l] = (int8_t)(v == 1); ocm[l] = (int8_t)(v == 3); }
+                for (int l = lane; l < L; l += 32) { const uint8_t v = code[pad + l]; ocp[l] = (int8_t)(v == kCP); ocm[l] = (int8_t)(v == kCM); }
             }
             if ((B.record & APS_REC_POS) && B.obs_pos) {
                 int32_t* op = B.obs_pos + row * (size_t)n_max;
@@ -241,13 +245,13 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     };
     auto hop_flags = [&](int p, int cd) {
         const bool l_free = (p > 0) && code[pad + p - 1] == 0, r_free = (p < L - 1) && code[pad + p + 1] == 0;
-        return (l_free ? 1 : 0) | (r_free ? 2 : 0) | ((cd == 1 && r_free) ? 4 : 0);
+        return (l_free ? 1 : 0) | (r_free ? 2 : 0) | ((cd == kCP && r_free) ? 4 : 0);
     };
     // full rate of particle i (CLASS.py:351)
     auto refresh = [&](int i, auto hot) {
         const int p = pos[i];
         const int cd = code[pad + p];
-        const double sgd = cd == 1 ? 1.0 : -1.0;
+        const double sgd = cd == kCP ? 1.0 : -1.0;
         const double h = F.hop_tab[hop_flags(p, cd)];
         const double m = local_m(p, hot);
         rates[i] = APS_ADD(h, aps_exp(APS_MUL(APS_MUL(-beta, sgd), m)));
@@ -259,6 +263,14 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         }
     };
     auto code_put = [&](int x, int delta) { code_add(code, L, pad, x, delta); };
+    auto tree16 = [&](const double* q) {                            // aps_tree16 without the i < n tests: rates[n ..] are 0.0
+        const double2* v = reinterpret_cast<const double2*>(q);
+        const double2 v0 = v[0], v1 = v[1], v2 = v[2], v3 = v[3], v4 = v[4], v5 = v[5], v6 = v[6], v7 = v[7];
+        const double a0 = APS_ADD(APS_ADD(v0.x, v0.y), APS_ADD(v1.x, v1.y)), a1 = APS_ADD(APS_ADD(v2.x, v2.y), APS_ADD(v3.x, v3.y));
+        const double a2 = APS_ADD(APS_ADD(v4.x, v4.y), APS_ADD(v5.x, v5.y)), a3 = APS_ADD(APS_ADD(v6.x, v6.y), APS_ADD(v7.x, v7.y));
+        return APS_ADD(APS_ADD(a0, a1), APS_ADD(a2, a3));
+    };
+    for (int i = n + lane; i < NCAP; i += 32) rates[i] = 0.0;      // zero padding of the last chunk (tree16)
 
     for (int i = lane; i < n; i += 32) refresh(i, std::false_type{});
     if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
 
         auto decode_apply = [&](int sel) {
             const int p = pos[sel];
-            const int cd = code[pad + p], sg = cd == 1 ? 1 : -1;
+            const int cd = code[pad + p], sg = cd == kCP ? 1 : -1;
             const int hf = hop_flags(p, cd);
             const double dz = APS_MUL(D, 0.0);
             const double rl = (hf & 1) ? D : dz, rr = (hf & 2) ? D : dz, ra = (hf & 4) ? lam : 0.0;
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                 else { kind = APS_EV_DIFF_RIGHT; newp = clampi(p + 1, 0, L - 1); }
             } else if (v < act_thresh) { kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, L - 1); }
             else kind = APS_EV_FLIP;
-            if (kind == APS_EV_FLIP) code_put(p, sg == 1 ? 2 : -2);
+            if (kind == APS_EV_FLIP) code_put(p, sg == 1 ? kCM - kCP : kCP - kCM);
             else if (newp != p) {
                 pos[sel] = (uint16_t)newp; code_put(p, -cd); code_put(newp, cd);
                 if (WHO) { who[p] = 0xFFFFu; who[newp] = (uint16_t)sel; }
@@ -330,10 +342,10 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         double r_scan, inv_r_scan = 0.0;                // total of the scan = R in native mode (aps_math.h, aps_native_total), and 1/R
         {
             if (lane < nchunks && F.dirty_c[lane]) {
+                // aps_native_chunk (aps_math.h) on the zero-padded image: adjacent pairwise tree of 16 per block, 16-byte loads
                 const int c0 = lane << cs_shift;
-                const int hi_i = (c0 + CS < n) ? c0 + CS : n;
-                double cs = 0.0;
-                for (int i = c0; i < hi_i; ++i) cs = APS_ADD(cs, rates[i]);
+                double cs = tree16(rates + c0);
+                for (int b = c0 + 16; b < c0 + CS && b < n; b += 16) cs = APS_ADD(cs, tree16(rates + b));
                 my_cs = cs; F.dirty_c[lane] = 0;
             }
             double incl = lane < nchunks ? my_cs : 0.0;
@@ -461,17 +473,17 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         if (endflag) { status = APS_RUN_DONE; break; }
         if (ncross > 0) {
             if ((B.record & APS_REC_MLOCAL) && B.obs_m_local) {
-                const int cd = sg_now == 1 ? 1 : 3;
+                const int cd = sg_now == 1 ? kCP : kCM;
                 __syncwarp();
                 if (lane == 0) {   // undo on the code array only: the recorded field is the pre-event one
-                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? -2 : 2);
+                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? kCP - kCM : kCM - kCP);
                     else if (newp != oldp) { code_put(newp, -cd); code_put(oldp, cd); }
                 }
                 __syncwarp();
                 write_field(obs_idx, ncross);
                 __syncwarp();
                 if (lane == 0) {   // redo
-                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? 2 : -2);
+                    if (kind == APS_EV_FLIP) code_put(oldp, sg_now == 1 ? kCM - kCP : kCP - kCM);
                     else if (newp != oldp) { code_put(newp, cd); code_put(oldp, -cd); }
                 }
                 __syncwarp();
@@ -542,7 +554,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     __syncwarp();
     if (B.bound_end) for (int i = lane; i < n; i += 32) B.bound_end[(size_t)rep * n_max + i] = 0;
     if (B.pos_end) for (int i = lane; i < n; i += 32) B.pos_end[(size_t)rep * n_max + i] = (int32_t)pos[i];
-    if (B.sigma_end) for (int i = lane; i < n; i += 32) B.sigma_end[(size_t)rep * n_max + i] = (int8_t)(code[pad + pos[i]] == 1 ? 1 : -1);
+    if (B.sigma_end) for (int i = lane; i < n; i += 32) B.sigma_end[(size_t)rep * n_max + i] = (int8_t)(code[pad + pos[i]] == kCP ? 1 : -1);
 }
 
 }  // namespace aps

@@ -91,9 +91,11 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// v1 of the reducer (round 1): per-site double arithmetic.  Kept as the A/B reference of reduce_kernel below
+// (aps_debug_set_reduce_impl(1), tests/test_dropin_gpu.py); not launched otherwise.
 // One CTA per replica; every warp owns whole observation rows (lane-strided over the lattice, shuffle
 // reductions only), so the row loops run without block barriers.  Shared: per-row scalars [M] x 3.
-__global__ void reduce_kernel(aps_reduce_args a) {
+__global__ void reduce_kernel_v1(aps_reduce_args a) {
     extern __shared__ double sh[];
     const int rep = blockIdx.x, tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
     const int M = a.M, L = a.L, n = a.n[rep], nobs = a.n_obs[rep];
@@ -261,6 +263,223 @@ __global__ void reduce_kernel(aps_reduce_args a) {
             for (int i = lane; i < n; i += 32) { double ri = ((double)pk[i] * a.dx - (double)p0[i] * a.dx) - rbar; s2 += ri * ri; }
             s2 = warp_sum(s2);
             if (lane == 0) aux[k] = s2 / (double)(n - 1);
+        }
+        __syncthreads();
+        const int cnt = wlen - 1;
+        double tb = 0.0, sb2 = 0.0;
+        for (int k = start_idx + 1; k < end_idx; ++k) { tb += t[k] - t[start_idx]; sb2 += aux[k]; }
+        tb /= cnt; sb2 /= cnt;
+        double num = 0.0, den = 0.0;
+        for (int k = start_idx + 1; k < end_idx; ++k) {
+            double dt = (t[k] - t[start_idx]) - tb;
+            num += dt * (aux[k] - sb2); den += dt * dt;
+        }
+        d_eff = num / den;
+    }
+    if (tid == 0) {
+        out[APS_RED_V_EFF] = mean_v; out[APS_RED_D_EFF] = d_eff; out[APS_RED_M_MEAN] = m_mean;
+        out[APS_RED_RHO_EFF] = rho_eff; out[APS_RED_BLOCK] = block;
+        out[APS_RED_START] = (double)start_idx; out[APS_RED_END] = (double)end_idx; out[APS_RED_NOBS] = (double)nobs;
+    }
+}
+
+// ---- reduce_kernel (round 2): the same reducers on INTEGER row sums ---------------------------------------------------
+// The observation rows hold small non-negative counts, so every lattice sum of the drivers' reducers is a sum of integers
+// times one constant: sum_l rho(l) = C / denom, sum_l rho(l) x_l = step * (sum_l c_l l) / denom, the attempts / blocked
+// sums of compute_blocking_probability are counts over 1 / denom, the MSD of compute_D_eff_active is
+// dx^2 (n S2 - S1^2) / (n (n - 1)) with S1 = sum d_i, S2 = sum d_i^2 of the integer displacements.  The sums are formed
+// exactly (dp4a: four sites per instruction; 8-byte row loads) and converted once per row, instead of a table lookup, a
+// grid-point product and three double additions per site (v1: 2.5 ms of the 64 ms bench step, ~10x its HBM time).
+// Against v1 / numpy only the association of the roundings differs (<= 1e-15 relative; tests: 1e-9 against the reference's
+// own functions, 1e-10 against v1 on random rows with counts up to 3).
+template <class F>
+__device__ __forceinline__ void row_words(const int8_t* cp, const int8_t* cm, int L, int lane, F&& f) {
+    if ((L & 7) == 0) {                       // rows start 8-byte aligned
+        const uint2* c2 = reinterpret_cast<const uint2*>(cp);
+        const uint2* m2 = reinterpret_cast<const uint2*>(cm);
+        for (int w = lane; w < (L >> 3); w += 32) {
+            const uint2 x = c2[w], y = m2[w];
+            f(8 * w, x.x, y.x, x.y & 0xffu, y.y & 0xffu, true);
+            f(8 * w + 4, x.y, y.y, 0u, 0u, false);
+        }
+    } else if ((L & 3) == 0) {
+        const uint32_t* c4 = reinterpret_cast<const uint32_t*>(cp);
+        const uint32_t* m4 = reinterpret_cast<const uint32_t*>(cm);
+        for (int w = lane; w < (L >> 2); w += 32) f(4 * w, c4[w], m4[w], 0u, 0u, false);
+    } else {
+        for (int w = lane; w < ((L + 3) >> 2); w += 32) {
+            uint32_t pw = 0, qw = 0;
+            for (int j = 0; j < 4; ++j) if (4 * w + j < L) { pw |= (uint32_t)(uint8_t)cp[4 * w + j] << (8 * j); qw |= (uint32_t)(uint8_t)cm[4 * w + j] << (8 * j); }
+            f(4 * w, pw, qw, 0u, 0u, false);
+        }
+    }
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void reduce_kernel(aps_reduce_args a) {
+    extern __shared__ double sh[];
+    const int rep = blockIdx.x, tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, wid = tid >> 5, NW = NT >> 5;
+    const int M = a.M, L = a.L, n = a.n[rep], nobs = a.n_obs[rep];
+    double* mean_x = sh;            // [M]
+    double* frac_b = sh + M;        // [M]
+    double* aux = sh + 2 * M;       // [M] scratch (S_k of the MSD fit)
+    double* scr = sh + 3 * M;       // [32] reduction scratch
+    double* out = a.out + (size_t)rep * APS_RED_N;
+    const double step = L > 1 ? APS_DIV(1.0, (double)(L - 1)) : 0.0;
+    const double dxg = L > 1 ? APS_SUB(xgrid(1, L, step), xgrid(0, L, step)) : 0.0;
+    const double denom = APS_MUL((double)(n > 1 ? n : 1), a.dx);
+
+    double* dtab = scr + 32;        // [128] density of a site holding c particles of one species: c / (max(1,n)*dx) (CLASS.py:208-213)
+    for (int c = tid; c < 128; c += NT) dtab[c] = APS_DIV((double)c, denom);
+    __syncthreads();
+    auto dens = [&](int c) { return dtab[c & 127]; };
+    // first grid point with x_l >= boundary_xmin (x_l is non-decreasing in l): v1's per-site test, located once
+    int lmin = L;
+    if (a.boundary_xmin == a.boundary_xmin) {
+        double g0 = step > 0.0 ? a.boundary_xmin / step - 2.0 : 0.0;
+        int g = g0 < 0.0 ? 0 : (g0 > (double)L ? L : (int)g0);
+        while (g < L && !(xgrid(g, L, step) >= a.boundary_xmin)) ++g;
+        lmin = g;
+    }
+    // ---- per-row sums over the lattice (rows never reached are all-zero in the reference) ----
+    for (int m = wid; m < M; m += NW) {
+        uint32_t C = 0, CB = 0, CLlo = 0;
+        unsigned long long CW = 0;
+        if (m < nobs) {
+            const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
+            const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
+            row_words(cp, cm, L, lane, [&](int l0, uint32_t pw, uint32_t qw, uint32_t, uint32_t, bool) {
+                const uint32_t tw = pw + qw;                               // counts per site (< 256: no carry between the bytes)
+                const uint32_t cw = __dp4a(tw, 0x01010101u, 0u);
+                C += cw;
+                CLlo = __dp4a(tw, 0x03020100u, CLlo);
+                CW += (unsigned long long)((uint32_t)l0 * cw);             // l0 * cw < 2^32 for L < 4e6
+                if (l0 >= lmin) CB += cw;
+                else if (l0 + 3 >= lmin) CB = __dp4a(tw, 0x01010101u << (8 * (lmin - l0)), CB);
+            });
+        }
+        C = __reduce_add_sync(0xffffffffu, C); CB = __reduce_add_sync(0xffffffffu, CB); CLlo = __reduce_add_sync(0xffffffffu, CLlo);
+        CW = warp_sum_u64(CW);
+        if (lane == 0) {
+            const double st = APS_DIV((double)C, denom), sb = APS_DIV((double)CB, denom);
+            const double sx = APS_DIV(APS_MUL((double)(CW + CLlo), step), denom);
+            const double Nt = st * dxg;
+            frac_b[m] = (sb * dxg) / (Nt + 1e-12);
+            mean_x[m] = sx / (st + 1e-12);
+        }
+    }
+    __syncthreads();
+
+    // ---- window selection, verbatim quirks of compute_v_eff_and_window (:139-154) ----
+    int start_idx = (int)(0.65 * (double)M), end_idx = M;
+    {
+        int unsafe = 0;
+        for (int m = 0; m < M; ++m) unsafe += (frac_b[m] >= a.max_boundary_fraction);
+        if (unsafe > 0 && unsafe > start_idx) {   // `safe[start_idx:]` non-empty -> `~idx` is always truthy
+            end_idx = start_idx;
+            int min_len = (int)(a.min_window_fraction * (double)M);
+            if (min_len < 3) min_len = 3;
+            if (end_idx - start_idx < min_len) end_idx = (start_idx + min_len < M) ? start_idx + min_len : M;
+        }
+    }
+    const int wlen = end_idx - start_idx;
+    // ---- v_eff = np.gradient(mean_x, times) averaged over the window; mean magnetisation ----
+    const double* t = a.times_obs;
+    bool uniform = true;
+    for (int m = 1; m + 1 < M; ++m) if ((t[m + 1] - t[m]) != (t[1] - t[0])) uniform = false;
+    double acc_v = 0.0, acc_m = 0.0;
+    for (int m = start_idx + tid; m < end_idx; m += NT) {
+        double g;
+        if (M < 2) g = 0.0;
+        else if (m == 0) g = (mean_x[1] - mean_x[0]) / (t[1] - t[0]);
+        else if (m == M - 1) g = (mean_x[M - 1] - mean_x[M - 2]) / (t[M - 1] - t[M - 2]);
+        else if (uniform) g = (mean_x[m + 1] - mean_x[m - 1]) / (2.0 * (t[1] - t[0]));
+        else {
+            double hd = t[m + 1] - t[m], hs = t[m] - t[m - 1];
+            double ca = -hd / (hs * (hd + hs)), cb = (hd - hs) / (hd * hs), cc = hs / (hd * (hd + hs));
+            g = ca * mean_x[m - 1] + cb * mean_x[m] + cc * mean_x[m + 1];
+        }
+        if (a.v_eff) a.v_eff[(size_t)rep * M + m] = g;
+        acc_v += g;
+        acc_m += (m < nobs) ? (double)a.obs_sigma_sum[(size_t)rep * M + m] / (double)n : 0.0;
+    }
+    acc_v = block_sum(acc_v, scr); acc_m = block_sum(acc_m, scr);
+    const double mean_v = wlen > 0 ? acc_v / (double)wlen : 0.0;
+    const double m_mean = wlen > 0 ? acc_m / (double)wlen : 0.0;
+
+    // ---- rho_eff (front density) and blocking probability: one warp per window row ----
+    // attempts = sum of rho_plus over the sites with a right neighbour, blocked = those whose neighbour holds total density >= 1
+    // (sweep_beta.py:197-229): both are (integer count) / denom, so the ratio is the ratio of the counts.
+    const bool one_blocks = APS_ADD(dens(1), dens(0)) >= 1.0;
+    double rsum = 0.0, rcnt = 0.0;
+    unsigned long long att_tot = 0, blk_tot = 0;
+    for (int m = start_idx + wid; m < end_idx; m += NW) {
+        if (m >= nobs) continue;
+        const int8_t* cp = a.obs_cp + ((size_t)rep * M + m) * L;
+        const int8_t* cm = a.obs_cm + ((size_t)rep * M + m) * L;
+        int jmax = -1;
+        uint32_t att = 0, blk = 0;
+        row_words(cp, cm, L, lane, [&](int l0, uint32_t pw, uint32_t qw, uint32_t pnx, uint32_t qnx, bool have_next) {
+            const uint32_t tw = pw + qw;
+            if (tw == 0) return;
+            jmax = l0 + ((31 - __clz(tw)) >> 3);                          // words arrive in increasing order per lane
+            if (pw == 0) return;
+            if (!have_next && (pw >> 24) != 0 && l0 + 4 < L) { pnx = (uint32_t)(uint8_t)cp[l0 + 4]; qnx = (uint32_t)(uint8_t)cm[l0 + 4]; }
+            uint32_t pv = pw;                                             // the last site has no right neighbour: not an attempt
+            if (L - 1 - l0 < 4) pv &= ~(0xFFu << (8 * (L - 1 - l0)));
+            const uint32_t pn = (pw >> 8) | (pnx << 24), qn = (qw >> 8) | (qnx << 24);   // counts of the right neighbours
+            if ((((pw | qw | pnx | qnx) & 0xFEFEFEFEu) | (pn & qn)) == 0u) {           // counts 0 / 1, no neighbour with both species
+                att += __popc(pv);
+                if (one_blocks) blk += __popc(pv & (pn | qn));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t pj = (pv >> (8 * j)) & 0xffu;
+                    if (pj) {
+                        att += pj;
+                        if (APS_ADD(dens((int)((pn >> (8 * j)) & 0xffu)), dens((int)((qn >> (8 * j)) & 0xffu))) >= 1.0) blk += pj;
+                    }
+                }
+            }
+        });
+        jmax = __reduce_max_sync(0xffffffffu, jmax);
+        att_tot += __reduce_add_sync(0xffffffffu, att); blk_tot += __reduce_add_sync(0xffffffffu, blk);
+        if (jmax >= 0) {
+            const double xmax = xgrid(jmax, L, step), lo = xmax - a.window_fraction;
+            // only the sites of the front window can pass the test below: start two grid points left of lo
+            int lfirst = step > 0.0 ? (int)(lo / step) - 2 : 0;
+            if (lfirst < 0) lfirst = 0;
+            double s2 = 0.0;
+            for (int l = lfirst + lane; l <= jmax; l += 32) {
+                double x = xgrid(l, L, step);
+                if (x >= lo && x <= xmax) s2 += APS_ADD(dens(cp[l]), dens(cm[l]));
+            }
+            s2 = warp_sum(s2);
+            rsum += s2 * dxg / a.window_fraction; rcnt += 1.0;
+        }
+    }
+    // every lane of a warp holds the same partials: count each warp once (the counts are < 2^53: exact in double)
+    rsum = block_sum(lane == 0 ? rsum : 0.0, scr); rcnt = block_sum(lane == 0 ? rcnt : 0.0, scr);
+    const double attempts = block_sum(lane == 0 ? (double)att_tot : 0.0, scr), blocked = block_sum(lane == 0 ? (double)blk_tot : 0.0, scr);
+    const double rho_eff = rcnt > 0.0 ? rsum / rcnt : nan("");
+    const double block = attempts > 0.0 ? blocked / attempts : 0.0;
+
+    // ---- D_eff: slope of the per-particle MSD against time (np.polyfit degree 1), one warp per row ----
+    double d_eff = nan("");
+    if (a.obs_pos && wlen >= 3 && n >= 2 && nobs >= end_idx) {
+        const int32_t* p0 = a.obs_pos + ((size_t)rep * M + start_idx) * a.n_max;
+        const double dx2 = a.dx * a.dx;
+        for (int k = start_idx + 1 + wid; k < end_idx; k += NW) {
+            const int32_t* pk = a.obs_pos + ((size_t)rep * M + k) * a.n_max;
+            long long s1 = 0;
+            unsigned long long s2 = 0;
+            for (int i = lane; i < n; i += 32) { const long long d = (long long)pk[i] - (long long)p0[i]; s1 += d; s2 += (unsigned long long)(d * d); }
+            s1 = (long long)warp_sum_u64((unsigned long long)s1); s2 = warp_sum_u64(s2);
+            // sample variance of the displacements r_i = d_i dx:  dx^2 (n S2 - S1^2) / (n (n - 1))
+            if (lane == 0) aux[k] = ((double)((long long)n * (long long)s2 - s1 * s1) * dx2) / ((double)n * (double)(n - 1));
         }
         __syncthreads();
         const int cnt = wlen - 1;

@@ -363,6 +363,7 @@ void aps_debug_set_guard_scale(double scale);
 void aps_debug_set_k1_threads(int threads);
 void aps_debug_set_use_lut(int on); /* 0: evaluate filter taps arithmetically instead of by table */
 void aps_debug_set_k2_ctas_per_sm(int n); /* persistent K2 CTAs per SM (default 6) */
+void aps_debug_set_reduce_impl(int v);    /* 0: integer row sums (default); 1: the round-1 per-site double kernel (A/B tests) */
 void aps_debug_set_reduce_threads(int n); /* threads per CTA of the reducer kernel (multiple of 32) */
 void aps_debug_set_k2_stash_cap(int n); /* local-field K2: stashed trials per segment (1..32, power of two; 0 = automatic) */
 void aps_debug_set_use_fast(int on); /* 0: always use the generic K1 kernel (no K=1 specialisation) */

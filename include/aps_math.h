@@ -226,24 +226,44 @@ APS_HD double aps_log(double x) {
  * compare with (different random stream), and the exact pairwise tree was 19 % of the per-event dependency chain of K1 (ncu, profiles/
  * r2_k1.md) for a quantity that differs from any other summation order by ~1e-16 relative.  Native mode therefore DEFINES R as the total
  * the particle-selection scan produces anyway:
- *     chunks of CS(n) = 16 * 2^k rates, k the smallest with at most 32 chunks; c_j = serial sum of chunk j (from 0.0, left to right);
+ *     chunks of CS(n) = 16 * 2^k rates, k the smallest with at most 32 chunks (rates beyond n count as 0.0);
+ *     T16(b) = adjacent pairwise tree over 16 rates: (((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))) + (((r8+r9)+...)+...)  [aps_tree16];
+ *     c_j = T16 of the chunk's first 16 rates, plus, left to right, the T16 of every further block of 16 that starts below n  [aps_native_chunk];
  *     R = S(31, 32) with S(l, 1) = c_l (0.0 for absent chunks), S(l, 2w) = S(l, w) + S(l - w, w)   [32-lane Hillis-Steele scan, last lane].
+ * (The tree replaced a serial left-to-right chunk sum: one lane re-sums a dirty chunk with 4 dependent additions instead of 16.)
  * Every K1 kernel and the oracle (mode 1) use this definition, so "GPU == oracle" stays bit-exact in native mode, clock included. */
 APS_HD int aps_native_cs_shift(int n) {
     int s = 4;
     while (((n + (1 << s) - 1) >> s) > 32) ++s;
     return s;
 }
+APS_HD double aps_tree16(const double* r, int lo, int n) {
+    double a[16];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 16; ++k) a[k] = (lo + k < n) ? r[lo + k] : 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int w = 1; w < 16; w <<= 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int k = 0; k < 16; k += 2 * w) a[k] = APS_ADD(a[k], a[k + w]);
+    }
+    return a[0];
+}
+APS_HD double aps_native_chunk(const double* r, int lo, int cs, int n) {
+    double c = aps_tree16(r, lo, n);
+    for (int b = lo + 16; b < lo + cs && b < n; b += 16) c = APS_ADD(c, aps_tree16(r, b, n));
+    return c;
+}
 #if !defined(__CUDA_ARCH__)
 static inline double aps_native_total(const double* rates, int n) {
     const int sh = aps_native_cs_shift(n), cs = 1 << sh;
     double v[32];
-    for (int j = 0; j < 32; ++j) {
-        double c = 0.0;
-        const int lo = j << sh, hi = (lo + cs < n) ? lo + cs : n;
-        for (int i = lo; i < hi; ++i) c = c + rates[i];
-        v[j] = c;
-    }
+    for (int j = 0; j < 32; ++j) v[j] = ((j << sh) < n) ? aps_native_chunk(rates, j << sh, cs, n) : 0.0;
     for (int o = 1; o < 32; o <<= 1)                 /* in-place Hillis-Steele: high lanes first so that v[l - o] is still the old value */
         for (int l = 31; l >= o; --l) v[l] = v[l] + v[l - o];
     return v[31];

@@ -196,6 +196,56 @@ def test_device_reducers_match_reference_functions():
         np.testing.assert_allclose(prof[2], c["rho_p_list"][si:ei].mean(0) ** 2, rtol=1e-12, atol=1e-15)
 
 
+@pytest.mark.parametrize("L,kmax", [(1000, 1), (1000, 3), (996, 3), (1003, 2), (64, 3)])
+def test_integer_reducers_equal_the_per_site_kernel_on_random_rows(L, kmax):
+    """reduce_kernel (integer row sums, dp4a) against the round-1 per-site double kernel (aps_debug_set_reduce_impl(1)) on
+    synthetic observation rows: counts up to `kmax` per species and site (sites holding both species included), row
+    lengths with 8-, 4- and 1-byte alignment, replicas whose run stopped early (n_obs < M), drifting positions for the MSD.
+    Window indices must be identical; the float reducers agree to 1e-10 (association of the roundings only)."""
+    from aps_b200 import capi
+    from aps_b200.engine import ReplicaBatch
+    import torch
+    g = np.random.default_rng(L * 10 + kmax)
+    R, M, n_max = 24, 41, 96
+    times = np.linspace(0.0, 4.0, M)
+    n = g.integers(40, n_max + 1, R).astype(np.int32)
+    rb = ReplicaBatch(L=L, K=kmax, radius=2, weights=[0.1, 0.2, 0.4], D=0.02, lam=5.0, T=4.0, times_obs=times,
+                      betas=np.zeros(R), n=n, pos0=np.zeros((R, n_max), np.int32), sigma0=np.ones((R, n_max), np.int8), dx=1.0 / L)
+    cp = np.zeros((R, M, L), np.int8); cm = np.zeros((R, M, L), np.int8)
+    pos = np.zeros((R, M, n_max), np.int32)
+    for r in range(R):
+        front = g.integers(L // 3, L)                       # some replicas reach the boundary zone, some do not
+        for m in range(M):
+            hi = min(L, front + (m * (L - front)) // M + 1) if r % 3 else L
+            occ = g.random(hi) < 0.45
+            cp[r, m, :hi] = np.where(occ, g.integers(0, kmax + 1, hi), 0)
+            cm[r, m, :hi] = np.where(g.random(hi) < 0.4, g.integers(0, kmax + 1, hi), 0)
+            if r % 5 == 0:
+                cp[r, m, L - 1] = kmax                       # a '+' particle on the last site: no right neighbour
+        pos[r] = np.cumsum(g.integers(0, 3, (M, n_max)), axis=0) + g.integers(0, L // 2, n_max)[None, :]
+    n_obs = np.full(R, M, np.int32); n_obs[1::4] = g.integers(M // 2, M, len(n_obs[1::4]))
+    for r in range(R):
+        cp[r, n_obs[r]:] = 0; cm[r, n_obs[r]:] = 0
+    rb.obs_cp.copy_(torch.from_numpy(cp)); rb.obs_cm.copy_(torch.from_numpy(cm)); rb.obs_pos.copy_(torch.from_numpy(pos))
+    rb.obs_sigma_sum.copy_(torch.from_numpy((cp.astype(np.int32) - cm).sum(axis=2).astype(np.int32)))
+    rb.n_obs.copy_(torch.from_numpy(n_obs))
+    lib = capi.load()
+    try:
+        lib.aps_debug_set_reduce_impl(1)
+        want, wv = rb.reduce(want_v_eff=True)
+        want, wv = want.cpu().numpy(), wv.cpu().numpy()
+    finally:
+        lib.aps_debug_set_reduce_impl(0)
+    got, gv = rb.reduce(want_v_eff=True)
+    got, gv = got.cpu().numpy(), gv.cpu().numpy()
+    for col in (capi.APS_RED_START, capi.APS_RED_END, capi.APS_RED_NOBS):
+        assert np.array_equal(got[:, col], want[:, col])
+    assert (want[:, capi.APS_RED_BLOCK] > 0).any() and np.isfinite(want[:, capi.APS_RED_RHO_EFF]).any()
+    for col in (capi.APS_RED_V_EFF, capi.APS_RED_D_EFF, capi.APS_RED_M_MEAN, capi.APS_RED_RHO_EFF, capi.APS_RED_BLOCK):
+        np.testing.assert_allclose(got[:, col], want[:, col], rtol=1e-10, atol=1e-13, equal_nan=True, err_msg=f"column {col}")
+    np.testing.assert_allclose(gv, wv, rtol=1e-10, atol=1e-12)
+
+
 def test_periodic_field_matches_the_fft_convolution():
     """periodic=True: compute_local_m_field (truncated direct ring sum) against the reference's formula
     real(ifft(fft(x) * fft(kernel))) (CLASS.py:111-121,224-227), evaluated here with numpy; |diff| <= 1e-13."""
