@@ -362,8 +362,13 @@ int aps_profile_sums_device(const aps_profile_args* a, void* stream) {
         if (R < 1) return fail(APS_ERR_INVALID, "aps_profile_sums: n_replicas needed with point lists and scratch");
         aps_profile_args one = *a;
         one.n_points = R; one.reps_per_point = 1; one.point_start = nullptr; one.point_reps = nullptr; one.prof = a->scratch;
-        dim3 g1((a->L + 127) / 128, R);
-        aps::profile_kernel<<<g1, 128, 0, (cudaStream_t)stream>>>(one);
+        if (a->L % 4 == 0) {
+            dim3 g1((a->L / 4 + 63) / 64, R);
+            aps::profile_kernel_w4<<<g1, 64, 0, (cudaStream_t)stream>>>(one);
+        } else {
+            dim3 g1((a->L + 127) / 128, R);
+            aps::profile_kernel<<<g1, 128, 0, (cudaStream_t)stream>>>(one);
+        }
         CU(cudaGetLastError());
         dim3 g2((a->L + 127) / 128, a->n_points);
         aps::profile_gather_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(a->scratch, a->point_start, a->point_reps, a->prof, a->L);
@@ -371,8 +376,13 @@ int aps_profile_sums_device(const aps_profile_args* a, void* stream) {
         g_launches.fetch_add(2);
         return APS_OK;
     }
-    dim3 grid((a->L + 127) / 128, a->n_points);
-    aps::profile_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
+    if (a->L % 4 == 0) {
+        dim3 grid((a->L / 4 + 63) / 64, a->n_points);
+        aps::profile_kernel_w4<<<grid, 64, 0, (cudaStream_t)stream>>>(*a);
+    } else {
+        dim3 grid((a->L + 127) / 128, a->n_points);
+        aps::profile_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(*a);
+    }
     CU(cudaGetLastError());
     g_launches.fetch_add(1);
     return APS_OK;

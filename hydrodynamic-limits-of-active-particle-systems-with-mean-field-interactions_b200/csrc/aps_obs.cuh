@@ -533,6 +533,50 @@ __global__ void profile_kernel(aps_profile_args a) {
 // Per-point sums from per-replica rows: out[g][q][l] = sum over the replicas of point g (CSR list, ascending: a fixed
 // summation order, so the result does not depend on the launch geometry) of per_rep[rep][q][l].  q = 0,1: time-averaged
 // rho_plus / rho_minus of the replica (profile_kernel with reps_per_point = 1), q = 2,3: their squares are formed here.
+// profile_kernel for L % 4 == 0: four sites per thread (one 32-bit load per row and species), the counts of the even / odd
+// bytes accumulated in 16-bit lanes and flushed every 256 rows (counts <= 127).  Same integers, hence the same doubles, as profile_kernel.
+__global__ void profile_kernel_w4(aps_profile_args a) {
+    const int g = blockIdx.y;
+    const int l4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (l4 >= a.L) return;
+    const int L = a.L, M = a.M;
+    double sp[4] = {0.0, 0.0, 0.0, 0.0}, sm[4] = {0.0, 0.0, 0.0, 0.0}, sp2[4] = {0.0, 0.0, 0.0, 0.0}, sm2[4] = {0.0, 0.0, 0.0, 0.0};
+    const int rows = a.row_hi - a.row_lo;
+    const int j_lo = a.point_start ? a.point_start[g] : 0, j_hi = a.point_start ? a.point_start[g + 1] : a.reps_per_point;
+    for (int j = j_lo; j < j_hi; ++j) {
+        const int rep = a.point_start ? a.point_reps[j] : g * a.reps_per_point + j;
+        const int n = a.n[rep], nobs = a.n_obs[rep];
+        const double denom = (double)(n > 1 ? n : 1) * a.dx;
+        const int m_hi = a.row_hi < nobs ? a.row_hi : nobs;
+        int cp[4] = {0, 0, 0, 0}, cm[4] = {0, 0, 0, 0};
+        uint32_t pe = 0, po = 0, qe = 0, qo = 0;
+        int pending = 0;
+        auto flush = [&]() {
+            cp[0] += pe & 0xffffu; cp[2] += pe >> 16; cp[1] += po & 0xffffu; cp[3] += po >> 16;
+            cm[0] += qe & 0xffffu; cm[2] += qe >> 16; cm[1] += qo & 0xffffu; cm[3] += qo >> 16;
+            pe = po = qe = qo = 0u; pending = 0;
+        };
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(a.obs_cp + ((size_t)rep * M + a.row_lo) * L + l4);
+        const uint32_t* rq = reinterpret_cast<const uint32_t*>(a.obs_cm + ((size_t)rep * M + a.row_lo) * L + l4);
+        const size_t stride = (size_t)L / 4;
+#pragma unroll 4
+        for (int m = a.row_lo; m < m_hi; ++m, rp += stride, rq += stride) {
+            const uint32_t pw = *rp, qw = *rq;
+            pe += pw & 0x00ff00ffu; po += (pw >> 8) & 0x00ff00ffu;
+            qe += qw & 0x00ff00ffu; qo += (qw >> 8) & 0x00ff00ffu;
+            if (++pending == 256) flush();
+        }
+        flush();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double mp = (double)cp[k] / denom / (double)rows, mm = (double)cm[k] / denom / (double)rows;
+            sp[k] += mp; sm[k] += mm; sp2[k] += mp * mp; sm2[k] += mm * mm;
+        }
+    }
+    double* o = a.prof + ((size_t)g * 4) * L + l4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o[k] = sp[k]; o[L + k] = sm[k]; o[2 * L + k] = sp2[k]; o[3 * L + k] = sm2[k]; }
+}
 __global__ void profile_gather_kernel(const double* __restrict__ per_rep, const int32_t* __restrict__ point_start,
                                       const int32_t* __restrict__ point_reps, double* __restrict__ out, int L) {
     const int g = blockIdx.y;
