@@ -58,8 +58,10 @@ __host__ __device__ inline size_t k1_fast_smem_bytes(int L, int n_max, int radiu
 
 __device__ __forceinline__ void code_add(uint8_t* code, int L, int pad, int x, int delta) {
     code[pad + x] = (uint8_t)(code[pad + x] + delta);
-    if (x < pad) code[pad - 1 - x] = (uint8_t)(code[pad - 1 - x] + delta);
-    if (x >= L - pad) code[pad + 2 * L - 1 - x] = (uint8_t)(code[pad + 2 * L - 1 - x] + delta);
+    if (x < pad || x >= L - pad) {                    // within `pad` of a wall (rare): the reflect images of the site
+        if (x < pad) code[pad - 1 - x] = (uint8_t)(code[pad - 1 - x] + delta);
+        if (x >= L - pad) code[pad + 2 * L - 1 - x] = (uint8_t)(code[pad + 2 * L - 1 - x] + delta);
+    }
 }
 
 __device__ __forceinline__ double fast_local_m(const uint8_t* code, const double2* lut, int pad, int r, int p) {

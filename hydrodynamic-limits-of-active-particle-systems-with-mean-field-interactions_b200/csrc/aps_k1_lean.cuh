@@ -90,6 +90,9 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     if (lane < 8) {
         const double dz = APS_MUL(D, 0.0);
         F.hop_tab[lane] = APS_ADD(APS_ADD((lane & 1) ? D : dz, (lane & 2) ? D : dz), (lane & 4) ? lam : 0.0);
+        // P(left | diffusive hop) per pair of free neighbours (CLASS.py:392): rl / (rl + rr); NaN when neither is free (never used:
+        // the diffusive threshold is 0 then)
+        if (lane < 4) F.misc[lane] = APS_DIV((lane & 1) ? D : dz, APS_ADD((lane & 1) ? D : dz, (lane & 2) ? D : dz));
     }
     __syncwarp();
     int S = 0;
@@ -312,20 +315,21 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
             e = F.ring[o]; uc = F.ring[o + 1]; ue = F.ring[o + 2]; ud = F.ring[o + 3];
         }
         if (avail < 3) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
-        const int seq = (int)(n_done & 0x3fffffff) + 1;
 
-        auto decode_apply = [&](int sel) {
+        // The event of particle `sel`, decided and applied by ONE lane; it is handed to the warp in two packed words that the
+        // caller broadcasts with shuffles (round 2: the shared-memory descriptor + __syncwarp round trip cost ~45 instructions per event):
+        //   pa = part | kind << 10 | (sigma == +1) << 12 | stop << 13 | (guard band hit: redo exactly) << 14,  pb = old site | new site << 16
+        auto decode_apply = [&](int sel, int& pa, int& pb) {
             const int p = pos[sel];
             const int cd = code[pad + p], sg = cd == kCP ? 1 : -1;
             const int hf = hop_flags(p, cd);
-            const double dz = APS_MUL(D, 0.0);
-            const double rl = (hf & 1) ? D : dz, rr = (hf & 2) ? D : dz, ra = (hf & 4) ? lam : 0.0;
             const double v = APS_MUL(ue, rates[sel]);
-            const double diff_thresh = APS_ADD(rl, rr), act_thresh = APS_ADD(diff_thresh, ra);
+            // thresholds (rl + rr) and (rl + rr) + ra with rl, rr in {D, D*0}, ra in {lam, 0}: entries of the hop-rate table
+            const double diff_thresh = F.hop_tab[hf & 3], act_thresh = F.hop_tab[hf];
             int kind, newp = p;
             if (v < diff_thresh) {
-                if (avail < 4) { F.desc[D_STOP] = 1; F.desc[D_SEQ] = seq; return; }
-                if (ud < APS_DIV(rl, APS_ADD(rl, rr))) { kind = APS_EV_DIFF_LEFT; newp = clampi(p - 1, 0, L - 1); }
+                if (avail < 4) { pa = 1 << 13; pb = 0; return; }
+                if (ud < F.misc[hf & 3]) { kind = APS_EV_DIFF_LEFT; newp = clampi(p - 1, 0, L - 1); }
                 else { kind = APS_EV_DIFF_RIGHT; newp = clampi(p + 1, 0, L - 1); }
             } else if (v < act_thresh) { kind = APS_EV_ACTIVE; newp = clampi(p + (sg == 1), 0, L - 1); }
             else kind = APS_EV_FLIP;
@@ -334,12 +338,14 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                 pos[sel] = (uint16_t)newp; code_put(p, -cd); code_put(newp, cd);
                 if (WHO) { who[p] = 0xFFFFu; who[newp] = (uint16_t)sel; }
             }
-            F.desc[D_PART] = sel; F.desc[D_KIND] = kind; F.desc[D_OLD] = p; F.desc[D_NEW] = newp; F.desc[D_SG] = sg;
-            F.desc[D_STOP] = 0; F.desc[D_SEQ] = seq;
+            pa = sel | (kind << 10) | ((sg == 1) << 12);
+            pb = p | (newp << 16);
         };
 
         // ---- selection: chunk sums (dirty ones re-summed, cached in a register), warp scan, walk of the winning chunk ----
         double r_scan, inv_r_scan = 0.0;                // total of the scan = R in native mode (aps_math.h, aps_native_total), and 1/R
+        int pa = 0, pb = 0;                             // the packed event (decode_apply)
+        bool exact;                                     // warp-uniform: the scan could not decide, lane 0 redoes the selection serially
         {
             if (lane < nchunks && F.dirty_c[lane]) {
                 // aps_native_chunk (aps_math.h) on the zero-padded image: adjacent pairwise tree of 16 per block, 16-byte loads
@@ -361,7 +367,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                                                             // the chunk walk instead of sitting in the clock lane's serial section
             const double target = APS_MUL(uc, atot);
             const unsigned wmask = __ballot_sync(0xffffffffu, lane < nchunks && prev <= target && target < incl);
-            bool exact = (__popc(wmask) != 1);
+            exact = (__popc(wmask) != 1);
             if (!exact) {
                 const int wl = __ffs(wmask) - 1;
                 const double prev_w = __shfl_sync(0xffffffffu, prev, wl), inc_w = __shfl_sync(0xffffffffu, incl, wl);
@@ -378,17 +384,22 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                 if (lane == 0) lo = prev_w;
                 const unsigned smask = __ballot_sync(0xffffffffu, mine && lo <= target && target < hi);
                 if (__popc(smask) != 1) exact = true;
-                else if (lane == __ffs(smask) - 1) {
-                    const double band = APS_MUL(guard, atot);
-                    if ((target - lo) < band || (hi - target) < band) F.desc[D_EXACT] = 1;
-                    else decode_apply(i);
+                else {
+                    const int src = __ffs(smask) - 1;
+                    if (lane == src) {
+                        const double band = APS_MUL(guard, atot);
+                        if ((target - lo) < band || (hi - target) < band) pa = 1 << 14;
+                        else decode_apply(i, pa, pb);
+                    }
+                    pa = __shfl_sync(0xffffffffu, pa, src); pb = __shfl_sync(0xffffffffu, pb, src);
+                    exact = (pa & (1 << 14)) != 0;
                 }
             }
-            if (exact && lane == 0) F.desc[D_EXACT] = 1;
         }
         // ---- clock.  Replay mode: numpy's pairwise sum exactly (8 lanes per leaf, <= 4 leaves; CLASS.py:352), the clock the reference
         //      reports.  Native mode: R is the total of the selection scan (defined in aps_math.h; the oracle does the same), so the
         //      leaf sums, their dirty flags and the tree drop out of the per-event chain (19 % of it, ncu profiles/r2_k1.md). ----
+        double R;
         {
             double val = r_scan;
             if (!PHILOX) {
@@ -424,44 +435,35 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                 if (nd_kind && nd_lev == lev) val = APS_ADD(va, vb);
             }
             }
-            if (lane == nnodes - 1) {
-                const double R = val;
-                const double tau = APS_MUL(PHILOX ? inv_r_scan : APS_DIV(1.0, R), e);
-                const double tn = APS_ADD(t, tau);
-                F.misc[X_R] = R; F.misc[X_TNEW] = tn;
-                F.desc[D_BADR] = !(R > 0.0);
-                F.desc[D_END] = tn > T;
-                int nc = 0;
-                if (!(tn > T) && obs_idx < M && next_obs <= tn) {
-                    nc = 1;
-                    while (obs_idx + nc < M && B.times_obs[obs_idx + nc] <= tn) ++nc;
-                }
-                F.desc[D_NCROSS] = nc;
-            }
+            if (!PHILOX) val = __shfl_sync(0xffffffffu, val, nnodes - 1);    // the root of the pairwise tree
+            R = val;
         }
-        __syncwarp();
-
-        if (F.desc[D_BADR]) { status = APS_RUN_EMPTY; break; }
-        if (F.desc[D_EXACT] || F.desc[D_SEQ] != seq) {
-            __syncwarp();
+        // every lane advances the clock itself (same operands in all lanes: no broadcast)
+        const double tau = APS_MUL(PHILOX ? inv_r_scan : APS_DIV(1.0, R), e);
+        const double tnew = APS_ADD(t, tau);
+        const bool endflag = tnew > T;
+        int ncross = 0;
+        if (!endflag && obs_idx < M && next_obs <= tnew) {
+            ncross = 1;
+            while (obs_idx + ncross < M && B.times_obs[obs_idx + ncross] <= tnew) ++ncross;
+        }
+        if (!(R > 0.0)) { status = APS_RUN_EMPTY; break; }
+        if (exact) {
             if (lane == 0) {
-                const double R = F.misc[X_R];
                 double acc = 0.0;
                 for (int i = 0; i < n; ++i) acc = APS_ADD(acc, APS_DIV(rates[i], R));
                 const double last = acc;
                 int sel = n - 1; acc = 0.0;
                 for (int i = 0; i < n; ++i) { acc = APS_ADD(acc, APS_DIV(rates[i], R)); if (APS_DIV(acc, last) > uc) { sel = i; break; } }
-                decode_apply(sel);
-                F.desc[D_EXACT] = 0;
+                decode_apply(sel, pa, pb);
             }
+            pa = __shfl_sync(0xffffffffu, pa, 0); pb = __shfl_sync(0xffffffffu, pb, 0);
             ++n_guard;
-            __syncwarp();
         }
-        if (F.desc[D_STOP]) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
-        const int kind = F.desc[D_KIND], part = F.desc[D_PART], oldp = F.desc[D_OLD], newp = F.desc[D_NEW];
-        const int ncross = F.desc[D_NCROSS], endflag = F.desc[D_END];
-        const int sg_now = F.desc[D_SG];                             // orientation of the particle BEFORE the event
-        const double tnew = F.misc[X_TNEW];
+        __syncwarp();                                                        // the event's writes to pos / code are visible to all lanes
+        if (pa & (1 << 13)) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
+        const int kind = (pa >> 10) & 3, part = pa & 1023, oldp = pb & 0xffff, newp = (int)((unsigned)pb >> 16);
+        const int sg_now = (pa & (1 << 12)) ? 1 : -1;                // orientation of the particle BEFORE the event
         if (B.trace && lane == 0 && n_done < B.trace_cap) {
             int32_t* tr = B.trace + ((size_t)rep * (size_t)B.trace_cap + (size_t)n_done) * 3;
             tr[0] = part; tr[1] = kind; tr[2] = (kind == APS_EV_FLIP) ? -1 : newp;
