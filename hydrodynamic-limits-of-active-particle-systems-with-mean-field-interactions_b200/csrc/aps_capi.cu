@@ -122,6 +122,7 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     if (b->n_replicas == 0) return APS_OK;
     aps::K1Args a;
     a.p = *p; a.b = *b;
+    if (!a.b.trace) a.b.trace_cap = 0;        // internal copy: lets the kernels test the capacity alone
     a.guard_scale = g_guard_scale;
     a.max_nodes = max_tree_nodes(b->n_max);
     a.pad = p->radius > 0 ? p->radius : 0;

@@ -38,7 +38,7 @@ struct LeanFixed {
     double2 mst[9];                    // multipliers (a_plus - a_minus, a_plus + a_minus) of a pair code: one 16-byte load
     double wtab[RCAP];
     double leafsum[8];
-    double misc[4];
+    double misc[6];                    // [0..3] P(left | diffusive hop) per free-neighbour pair, [4] guard band factor
     int32_t desc[16];
     int8_t node_a[16], node_b[16], node_kind[16], node_level[16], node_leaf[16];
     int16_t leaf_start[8], leaf_len[8];
@@ -279,7 +279,8 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
     if (obs_idx == 0 && M > 0) { write_field(0, 1); write_rows(0, 1); obs_idx = 1; }
     __syncwarp();
     double next_obs = (obs_idx < M) ? B.times_obs[obs_idx] : 0.0;
-    const double guard = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;
+    if (lane == 0) F.misc[4] = A.guard_scale * 4.0 * (double)(n + 32) * 1.1102230246251565e-16;   // read by the deciding lane only
+    __syncwarp();
 
     while (true) {
         if (!(t < T)) { status = APS_RUN_DONE; break; }
@@ -387,7 +388,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
                 else {
                     const int src = __ffs(smask) - 1;
                     if (lane == src) {
-                        const double band = APS_MUL(guard, atot);
+                        const double band = APS_MUL(F.misc[4], atot);
                         if ((target - lo) < band || (hi - target) < band) pa = 1 << 14;
                         else decode_apply(i, pa, pb);
                     }
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(cons
         if (pa & (1 << 13)) { status = APS_RUN_DRAWS_EXHAUSTED; break; }
         const int kind = (pa >> 10) & 3, part = pa & 1023, oldp = pb & 0xffff, newp = (int)((unsigned)pb >> 16);
         const int sg_now = (pa & (1 << 12)) ? 1 : -1;                // orientation of the particle BEFORE the event
-        if (B.trace && lane == 0 && n_done < B.trace_cap) {
+        if (lane == 0 && n_done < B.trace_cap) {            // trace_cap is 0 without a trace buffer (launch_k1)
             int32_t* tr = B.trace + ((size_t)rep * (size_t)B.trace_cap + (size_t)n_done) * 3;
             tr[0] = part; tr[1] = kind; tr[2] = (kind == APS_EV_FLIP) ? -1 : newp;
         }

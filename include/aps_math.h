@@ -132,11 +132,26 @@ APS_EXP_TAB_BODY
  * applied to the exponent field.  Only correctly rounded +, -, * — the same operation sequence on the GPU and in the
  * oracle.  Error <= 1 ulp (truncation r^7/5040 < 3e-20; table and final rounding 0.5 ulp each); checked against libm
  * in tests/test_oracle_units.py.  |x| > 700 and NaN go through the fdlibm form. */
+#define APS_EXP_INV 92.33248261689366                    /* 64 / ln2 */
+#define APS_EXP_C_HI 0.010830424667801708                /* 0x3f862e42fe000000: ln2/64, 24 trailing zero bits */
+#define APS_EXP_C_LO 2.8447437476627285e-11              /* 0x3dbf473de6af278f */
+#define APS_EXP_P6 1.3888888888888889e-03                /* 1/720 */
+#define APS_EXP_P5 8.3333333333333332e-03                /* 1/120 */
+#define APS_EXP_P4 4.1666666666666664e-02                /* 1/24 */
+#define APS_EXP_P3 1.6666666666666666e-01                /* 1/6 */
+#if defined(__CUDACC__)
+/* the same literals as constant-bank operands of the DMUL / DADD (as immediates each costs two UMOVs per use) */
+static __constant__ double aps_exp_cst_d[8] = {APS_EXP_INV, APS_EXP_C_HI, APS_EXP_C_LO, APS_EXP_P6, APS_EXP_P5, APS_EXP_P4, APS_EXP_P3, 0.0};
+#endif
 APS_HD double aps_exp(double x) {
-    const double INV = 92.33248261689366;               /* 64 / ln2 */
+#if defined(__CUDA_ARCH__)
+    const double INV = aps_exp_cst_d[0], C_HI = aps_exp_cst_d[1], C_LO = aps_exp_cst_d[2];
+    const double P6 = aps_exp_cst_d[3], P5 = aps_exp_cst_d[4], P4 = aps_exp_cst_d[5], P3 = aps_exp_cst_d[6];
+#else
+    const double INV = APS_EXP_INV, C_HI = APS_EXP_C_HI, C_LO = APS_EXP_C_LO;
+    const double P6 = APS_EXP_P6, P5 = APS_EXP_P5, P4 = APS_EXP_P4, P3 = APS_EXP_P3;
+#endif
     const double SHIFT = 6755399441055744.0;            /* 1.5 * 2^52 */
-    const double C_HI = 0.010830424667801708;           /* 0x3f862e42fe000000: ln2/64, 24 trailing zero bits */
-    const double C_LO = 2.8447437476627285e-11;         /* 0x3dbf473de6af278f */
     if (!(x >= -700.0 && x <= 700.0)) return aps_exp_fdlibm(x);
     const double t = APS_ADD(APS_MUL(x, INV), SHIFT);
     const double kd = APS_SUB(t, SHIFT);
@@ -150,9 +165,9 @@ APS_HD double aps_exp(double x) {
     const double T = aps_u2d(aps_exp_tab_h[j]);
 #endif
     const double r2 = APS_MUL(r, r);
-    double q = APS_ADD(8.3333333333333332e-03, APS_MUL(r, 1.3888888888888889e-03));   /* 1/120 + r/720 */
-    q = APS_ADD(4.1666666666666664e-02, APS_MUL(r, q));                                /* 1/24 */
-    q = APS_ADD(1.6666666666666666e-01, APS_MUL(r, q));                                /* 1/6 */
+    double q = APS_ADD(P5, APS_MUL(r, P6));              /* 1/120 + r/720 */
+    q = APS_ADD(P4, APS_MUL(r, q));                      /* 1/24 */
+    q = APS_ADD(P3, APS_MUL(r, q));                      /* 1/6 */
     q = APS_ADD(0.5, APS_MUL(r, q));
     const double p = APS_ADD(r, APS_MUL(r2, q));
     const double y = APS_ADD(T, APS_MUL(T, p));          /* in [0.99, 2.01) */
