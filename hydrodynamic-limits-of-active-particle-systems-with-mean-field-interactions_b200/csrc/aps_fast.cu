@@ -74,13 +74,16 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
         }
         if (r1 <= 21 && nm <= 1024 && lp <= 1056) {
             if (nt == 32 && !g_env_no_lean) {
-                // mid-size replicas (config 3: N = 900): trimmed image WITH the site map (any particle order), 15 instead of
-                // 10 replicas per SM; its rejects (n > 968, K = 1 violated) fall through to the full-size and generic kernels
-                cudaError_t e = launch_lean<21, 1056, 1024, true>(a, philox, st);
+                // mid-size replicas (config 3: N = 900): trimmed image, sorted particles first (17 replicas per SM), then the
+                // variant WITH the site map for unsorted ones (15 per SM; the full-size kernel holds 10); what both reject
+                // (n > 968, K = 1 violated) falls through to the full-size and generic kernels
+                cudaError_t e = launch_lean<21, 1056, 1024, false>(a, philox, st);
                 if (e != cudaSuccess) return e;
-                *launched = 2;
                 K1Args b = a;
                 b.only_retry = 2;
+                e = launch_lean<21, 1056, 1024, true>(b, philox, st);
+                if (e != cudaSuccess) return e;
+                *launched = 3;
                 return launch_class<21, 1024, 1056>(b, philox, st, nt);
             }
             return launch_class<21, 1024, 1056>(a, philox, st, nt);

@@ -49,14 +49,15 @@ struct LeanFixed {
 
 // NCAP = 512, WHO = false: particles must come sorted (no site map), n <= 488, 28 replicas per SM.
 // NCAP = 512, WHO = true: any particle order, n <= 488, 22 replicas per SM (second link of the chain for small replicas).
-// NCAP = 1024 (WHO = true): site->particle map kept (any particle order), n <= 968 (<= 8 leaves), 15 replicas per SM.
+// NCAP = 1024, WHO = false: sorted particles, n <= 968 (<= 8 leaves), 17 replicas per SM (config 3: N = 900).
+// NCAP = 1024, WHO = true: site->particle map kept (any particle order), n <= 968, 15 replicas per SM.
 template <int RCAP, int LPCAP, int NCAP, bool WHO>
 __host__ __device__ inline size_t k1_lean_smem_bytes() {
     return ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15) + (size_t)NCAP * 8 + (size_t)NCAP * 2 + (size_t)LPCAP + (WHO ? (size_t)LPCAP * 2 : 0);
 }
 
 template <bool PHILOX, int RCAP, int LPCAP, int NCAP, bool WHO>
-__global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : 15) k1_lean_kernel(const __grid_constant__ K1Args A) {
+__global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : (WHO ? 15 : 17)) k1_lean_kernel(const __grid_constant__ K1Args A) {
     constexpr int kNMax = NCAP <= 512 ? kLeanNMax : 968;          // largest n with <= 4 (8) leaves in numpy's pairwise tree
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const aps_params& P = A.p;
