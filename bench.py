@@ -380,9 +380,13 @@ def ensemble_main(args, torch, la, capi, rank, world):
     if wl == "config3":
         from aps_b200.structure import fft_amplitudes, structure_observables
 
-        def step(ens):                         # init -> K1 -> density rows, cuFFT amplitudes, per-run structure observables
+        def step(ens, ev=None):                # init -> K1 -> density rows, cuFFT amplitudes, per-run structure observables
             ens.init_particles()
+            if ev is not None:
+                ev[0].record()
             ens.rb.run_philox()
+            if ev is not None:
+                ev[1].record()
             amp, total, var = fft_amplitudes(ens.rb)
             ens.struct = structure_observables(ens.rb, 0.5, None, amp=amp, var=var)
     else:
@@ -406,7 +410,7 @@ def ensemble_main(args, torch, la, capi, rank, world):
     e0.record()
     for s in range(args.steps):                # every step re-runs the same seeded ensemble from its initial conditions
         if wl == "config3":
-            step(ens)
+            step(ens, k_ev[s])
         else:
             ens.init_particles()
             k_ev[s][0].record()
@@ -419,7 +423,7 @@ def ensemble_main(args, torch, la, capi, rank, world):
     e1.record()
     barrier()
     launches = lib.aps_launch_count() - n0
-    k1_ms = sum(a.elapsed_time(b) for a, b in k_ev) if wl != "config3" else None
+    k1_ms = sum(a.elapsed_time(b) for a, b in k_ev)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     evs = (ens.rb.n_events.sum().double() * args.steps).reshape(1)       # read after the timed region (identical steps)
     events_per_launch = float(evs.item()) / args.steps
@@ -513,7 +517,9 @@ def ensemble_main(args, torch, la, capi, rank, world):
             ncu_file = os.path.join(ROOT, "profiles", "k1_ncu_summary.json")
             ncu_k1 = json.load(open(ncu_file)) if os.path.exists(ncu_file) else {}
             smem_traffic = ncu_k1.get("smem_bytes_per_event_at_128B_per_wavefront") if wl == "config2" else None
-            roofline = dict(bound="smem", kernel="aps::k1_lean_kernel<true,21,1056,512,false>" if wl == "config2" else "aps::k1_fast_kernel<64,true,81,...>",
+            kname = {"config2": "aps::k1_lean_kernel<true,21,1056,512,false>", "config3": "aps::k1_lean_kernel<true,21,1056,1024,false>",
+                     "config4": "aps::k1_fast_kernel<64,true,81,...>"}[wl]
+            roofline = dict(bound="smem", kernel=kname,
                             achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                             traffic=(smem_traffic * events_per_launch if smem_traffic else None),
                             traffic_note="shared-memory wavefronts x 128 B per launch from the ncu capture (DRAM traffic of K1 is ~0.1 GB per launch)",
