@@ -244,6 +244,18 @@ def test_integer_reducers_equal_the_per_site_kernel_on_random_rows(L, kmax):
     for col in (capi.APS_RED_V_EFF, capi.APS_RED_D_EFF, capi.APS_RED_M_MEAN, capi.APS_RED_RHO_EFF, capi.APS_RED_BLOCK):
         np.testing.assert_allclose(got[:, col], want[:, col], rtol=1e-10, atol=1e-13, equal_nan=True, err_msg=f"column {col}")
     np.testing.assert_allclose(gv, wv, rtol=1e-10, atol=1e-12)
+    # per-point profile sums (four sites per thread when L % 4 == 0, one otherwise) against numpy on the same rows
+    lo, hi, reps = M // 2, M, 4
+    prof = rb.profile_sums(reps, row_lo=lo, row_hi=hi).cpu().numpy()
+    denom = np.maximum(n, 1)[:, None] * (1.0 / L)
+    mp = np.stack([cp[r, lo:min(hi, n_obs[r])].sum(axis=0) / denom[r] / (hi - lo) for r in range(R)])
+    mm = np.stack([cm[r, lo:min(hi, n_obs[r])].sum(axis=0) / denom[r] / (hi - lo) for r in range(R)])
+    for g in range(R // reps):
+        sl = slice(g * reps, (g + 1) * reps)
+        np.testing.assert_allclose(prof[g, 0], mp[sl].sum(axis=0), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(prof[g, 1], mm[sl].sum(axis=0), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(prof[g, 2], (mp[sl] ** 2).sum(axis=0), rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(prof[g, 3], (mm[sl] ** 2).sum(axis=0), rtol=1e-12, atol=1e-15)
 
 
 def test_periodic_field_matches_the_fft_convolution():

@@ -45,12 +45,14 @@ def main():
     ap.add_argument("--record", type=int, default=3)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--max_events", type=int, default=0)
+    ap.add_argument("--L", type=int, default=1000)        # other lattice sizes take the runtime-layout kernels (no capacity class)
+    ap.add_argument("--N", type=int, default=500)
     a = ap.parse_args()
     lib = capi.load()
     lib.aps_debug_set_k1_threads(a.threads)
-    L, R = 1000, a.replicas
-    rp, rm = exp_gradient(L, 500, 0.75, 0.35)
-    rm = exp_gradient(L, 500, 0.75, 0.2)[1]
+    L, R = a.L, a.replicas
+    rp, rm = exp_gradient(L, a.N, 0.75, 0.35)
+    rm = exp_gradient(L, a.N, 0.75, 0.2)[1]
     rng = np.random.default_rng(0)
     ns, pos0, sg0, nmax = host_init_poisson_k1(rng, R, rp, rm)
     from scipy.ndimage import _filters
