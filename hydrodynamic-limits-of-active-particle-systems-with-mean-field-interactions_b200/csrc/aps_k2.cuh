@@ -207,11 +207,6 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
     __shared__ long long mail_sum[kK2MaxRanks];
     __shared__ long long msum_sh;                    // MULTI, global field: lattice-wide sum(sigma) before the current pass
     __shared__ uint32_t cdf_sh[APS_K2_MAX_TRIALS];   // Poisson cdf thresholds for the per-lane binary search of the trial count
-    // outcome of one trial as a table: index = kind (0 left, 1 right, 2 active, 3 flip) << 5 | accept('+') << 4 | accept('-') << 3 |
-    // site byte << 1 | (neighbour empty); entry = new site byte | moved << 2 | (1 + d sigma / 2) << 3.  Built below from the predicate
-    // form of the update rule (`apply`), so the two cannot drift apart; a trial step is then two byte loads, one table load and
-    // two stores instead of ~30 predicate instructions (ncu, round 2: the replay loop ran 270 of 1120 instructions per warp and tile).
-    __shared__ uint8_t lut_sh[128];
 
     // local-field scratch behind the ring: taps, then per warp [cap][32] acceptance words, candidate list, trial codes
     const int cap = stash_cap;
@@ -231,16 +226,6 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
         if (MULTI && !LOCAL) msum_sh = *m.msum_cur;
     }
     if (tid < APS_K2_MAX_TRIALS) cdf_sh[tid] = a.rates.cdf32[tid];
-    if (tid < 128) {
-        const uint32_t kind = (uint32_t)tid >> 5, v = ((uint32_t)tid >> 1) & 3u;
-        const bool acc_p = (tid >> 4) & 1, acc_m = (tid >> 3) & 1, nb_empty = tid & 1;
-        const bool is_flip = kind == 3u, is_act = kind == 2u, plus = v == APS_K2_PLUS;
-        const bool part = v == APS_K2_PLUS || v == APS_K2_MINUS;
-        const bool mv = part && !is_flip && (!is_act || plus) && nb_empty;
-        const bool fl = part && is_flip && (plus ? acc_p : acc_m);
-        const uint32_t nv = mv ? (uint32_t)APS_K2_EMPTY : (fl ? (v ^ 3u) : v);
-        lut_sh[tid] = (uint8_t)(nv | (mv ? 4u : 0u) | ((fl ? (plus ? 0u : 2u) : 1u) << 3));
-    }
     if (LOCAL && packed) {
         for (int e = tid; e < nwords * 4; e += kK2Threads) {
             const int k = e >> 2, sft = e & 3;
@@ -357,16 +342,6 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             if (mv) { px[d] = (unsigned char)v; *px = APS_K2_EMPTY; }
             if (fl) { *px = (unsigned char)(v ^ 3u); dsig += plus ? -dsig2 : dsig2; }     // '+' -> '-': -2, '-' -> '+': +2
         };
-        // the same step through the table: kd = kind << 5 | acc_p << 4 | acc_m << 3, dp1 = 1 + hop direction
-        auto apply_lut = [&](uint32_t x, uint32_t kd, uint32_t dp1) {
-            unsigned char* px = act + x;
-            unsigned char* pn = px + (int)dp1 - 1;
-            const uint32_t v = *px, nb = *pn;
-            const uint32_t e = lut_sh[kd | (v << 1) | (nb == APS_K2_EMPTY ? 1u : 0u)];
-            if (e & 4u) *pn = (unsigned char)v;                 // hop: the particle arrives next door (before the site itself is cleared)
-            *px = (unsigned char)(e & 3u);
-            dsig += ((int)((e >> 3) & 3u) - 1) * dsig2;
-        };
         auto set_wall_sentinels = [&]() {        // only the two threads that own the wall segments touch these bytes
             if (t == 0 && tid == 0 && qpar == 0) act[-1] = 0xFF;
             if (t == ntiles - 1 && tid == kK2Threads - 1 && qpar == 1) act[APS_K2_HALF] = 0xFF;
@@ -379,8 +354,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             set_wall_sentinels();
             auto do_trial = [&](uint32_t wa, bool live) {
                 const uint32_t slot = wa << 5, wb = slot - t_active;
-                const uint32_t kind = (uint32_t)category(slot);
-                if (live) apply_lut(wa >> 27, (kind << 5) | (wb < thr_p_glob ? 16u : 0u) | (wb < thr_m_glob ? 8u : 0u), (0x68u >> (2u * kind)) & 3u);
+                apply(wa >> 27, slot < t_left, slot >= t_active, slot >= t_right && slot < t_active, wb < thr_p_glob, wb < thr_m_glob, live);
             };
             if (ntr > 0) {
                 do_trial(w4.v[1], true); do_trial(w4.v[2], ntr > 1); do_trial(w4.v[3], ntr > 2);
@@ -409,7 +383,7 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
                 const int x = (int)(wa >> 27), cat = category(wa << 5), slot = tr * 32 + lane;
                 const bool cand = live && cat == 3;
                 const unsigned mask = __ballot_sync(0xffffffffu, cand);
-                if (live) code16[slot] = (uint16_t)((uint32_t)x | ((uint32_t)cat << 5) | (((0x68u >> (2 * cat)) & 3u) << 9));   // site, kind, 1 + direction
+                if (live) code16[slot] = (uint16_t)((uint32_t)x | ((uint32_t)cat << 5));
                 if (cand) {
                     wb32[slot] = wb;
                     list[nl + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(cbase + x) | ((uint32_t)slot << 14);
@@ -455,9 +429,9 @@ __global__ void __launch_bounds__(kK2Threads) k2_pass_kernel(const __grid_consta
             // ---- phase C: replay the trials in order against the live tile ----
             for (int tr = 0; tr < ntr; ++tr) {
                 if (tr < cap) {
-                    const uint32_t code = code16[tr * 32 + lane];       // site | kind << 5 | acc_p << 7 | acc_m << 8 | (1 + direction) << 9
-                    // table index bits: kind -> 5-6 (in place), acc_p -> 4, acc_m -> 3
-                    apply_lut(code & 31u, (code & 0x60u) | ((code >> 3) & 16u) | ((code >> 5) & 8u), (code >> 9) & 3u);
+                    const uint32_t code = code16[tr * 32 + lane];
+                    const uint32_t cat = code & 0x60u;
+                    apply(code & 31u, cat == 0u, cat == 0x60u, cat == 0x40u, (code & 0x80u) != 0u, (code & 0x100u) != 0u, true);
                 } else {
                     const aps_u32x4 wq = aps_philox4x32_10(c0, c1, aps_k2_trial_call(tr), chi, k0, k1);
                     const int wsel = aps_k2_trial_word(tr);
