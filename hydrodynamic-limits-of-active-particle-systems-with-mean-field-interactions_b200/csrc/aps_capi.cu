@@ -422,6 +422,7 @@ static size_t k2_smem(int radius, int cap, int stages = 0) {
 // resident (co-resident for the grid barrier) to walk the slab in ONE round.
 struct K2Plan { int stages; size_t smem; int grid; };
 const bool g_env_k2_no_short_plan = getenv("APS_K2_NO_SHORT_PLAN") != nullptr;   // A/B knob, read once at load
+const int g_env_k2_stages = [] { const char* e = getenv("APS_K2_STAGES"); return e ? atoi(e) : 0; }();   // A/B knob: ring depth of the first plan
 static int k2_plan(const void* fn, int radius, int cap, int ntiles, int n_sm, K2Plan* out) {
     // one-entry cache per thread: a run is thousands of launches with the same plan (the occupancy queries are host-side work)
     struct Key { const void* fn; int radius, cap, ntiles, per_sm_cap; K2Plan plan; };
@@ -429,7 +430,7 @@ static int k2_plan(const void* fn, int radius, int cap, int ntiles, int n_sm, K2
     if (last.fn == fn && last.radius == radius && last.cap == cap && last.ntiles == ntiles && last.per_sm_cap == g_k2_ctas_per_sm) { *out = last.plan; return 0; }
     int best_rounds = 1 << 30;
     for (int pass = 0; pass < (g_env_k2_no_short_plan ? 1 : 2); ++pass) {
-        const int stages = pass == 0 ? (radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal) : 2;
+        const int stages = pass == 0 ? (g_env_k2_stages >= 2 ? g_env_k2_stages : (radius >= 0 ? aps::kK2StagesLocal : aps::kK2StagesGlobal)) : 2;
         const size_t smem = k2_smem(radius, cap, stages);
         if (smem > 227 * 1024) continue;
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); continue; }

@@ -358,7 +358,8 @@ int aps_k2_profile_device(const uint8_t* state, int64_t L, int64_t global_offset
  *   APS_K1_THREADS=32|64|128|256   block size of the K1 kernels
  *   APS_K1_NO_LEAN=1               skip the half-image K1 kernel (aps_k1_lean.cuh), use the full-size one
  *   APS_K1_EXTRA_SMEM=<bytes>      pad the full-size K1 kernel's shared memory (occupancy experiments)
- *   APS_K2_NO_SHORT_PLAN=1         K2: always the deep TMA ring at 6 CTAs per SM (no 2-deep ring for short slabs) */
+ *   APS_K2_NO_SHORT_PLAN=1         K2: always the deep TMA ring at 6 CTAs per SM (no 2-deep ring for short slabs)
+ *   APS_K2_STAGES=<n>              K2: ring depth of the first launch plan (default 3 local / 4 global field) */
 void aps_debug_set_guard_scale(double scale);
 void aps_debug_set_k1_threads(int threads);
 void aps_debug_set_use_lut(int on); /* 0: evaluate filter taps arithmetically instead of by table */

@@ -13,7 +13,11 @@ ap.add_argument("--logL", type=int, nargs="+", default=[26, 30])
 ap.add_argument("--passes", type=int, default=200)
 ap.add_argument("--case", default="", help="substring filter on the case names")
 ap.add_argument("--legacy", action="store_true", help="also time the persistent multi-pass launch (grid barrier per pass)")
+ap.add_argument("--ctas", type=int, default=0, help="A/B: persistent CTAs per SM (aps_debug_set_k2_ctas_per_sm); ring depth via APS_K2_STAGES")
 a = ap.parse_args()
+if a.ctas:
+    from aps_b200 import capi
+    capi.load().aps_debug_set_k2_ctas_per_sm(a.ctas)
 peak = 6548.2
 pk = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 if os.path.exists(pk):
