@@ -4,6 +4,7 @@ lattices); it is the discrete-time sublattice version of the same model, so pari
   * bit-exact multi-slab (ghost zones, world_size 2/3, gloo) == single slab,
   * statistical agreement with the exact Gillespie chain (oracle K1) in the dt -> 0 regime,
   * conservation / exclusion invariants at any size."""
+import json
 import os
 import sys
 
@@ -182,6 +183,33 @@ def test_gpu_large_lattice_invariants():
     assert int((s != 0).sum()) == n0 and int(s.max()) <= 2
     rp, rm = lat.profile(64)
     assert np.allclose((rp + rm)[4:-4], 0.5, atol=0.01)
+
+
+@pytest.mark.gpu
+def test_config5_size_lattice_against_the_exact_chain():
+    """Size-independent property at BASELINE config 5's FULL size (2^26 sites, 3.4e7 particles): the relaxation of the
+    magnetisation and the mean drift per particle are local quantities, so one huge K2 lattice must reproduce what the EXACT
+    Gillespie chain (K1, reference-pinned) gives on an ensemble of 192 lattices of 8192 sites with the same parameters
+    (tools/k2_dt_bias.py -> tests/golden/k2_dt_bias.json: global field, D = 0.2, lambda = 2, beta = 0.6, 90 % '+', T = 1.5).
+    Tolerance: 3 standard errors of the exact-chain ensemble + the largest paired dt-bias estimate of the table (0.002)."""
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "k2_dt_bias.json")))
+    exact = gold["rows"][0]
+    assert exact["method"].startswith("exact")
+    L, dt = 1 << 26, 0.005
+    lat = SublatticeLattice(L, D=gold["D"], lam=gold["lam"], beta=gold["beta"], dt=dt, sigma_sites=None, seed=11, single_rank=True)
+    lat.init_random(0.5, 0.9)
+    n0 = lat.n_particles
+    idx = torch.arange(L, device="cuda", dtype=torch.int64)
+    x0 = int((idx * (lat.state != 0)).sum()) / n0
+    lat.run(int(round(gold["T"] / dt)))
+    lat.check()
+    s = lat.state
+    assert int((s != 0).sum()) == n0 and int(s.max()) <= 2
+    m = (int((s == 1).sum()) - int((s == 2).sum())) / n0
+    disp = int((idx * (s != 0)).sum()) / n0 - x0
+    assert abs(m - exact["m_mean"]) <= 3 * exact["m_se"] + 0.002, (m, exact["m_mean"])
+    se_d = max(r["displacement_bias_se"] for r in gold["rows"])
+    assert abs(disp - exact["displacement_sites"]) <= 3 * se_d + 0.002, (disp, exact["displacement_sites"])
 
 
 @pytest.mark.gpu
