@@ -19,7 +19,7 @@ namespace aps {
 size_t pde_smem_bytes(int L, int bc, int n_tracers);
 cudaError_t pde_launch(const aps_pde_args& a, cudaStream_t st);
 }
-namespace aps { cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched); }
+namespace aps { cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int auto_threads, int* launched); }
 
 namespace {
 
@@ -134,8 +134,8 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     cudaStream_t st = (cudaStream_t)stream;
     a.only_retry = 0; a.reserved = 0;
     a.wt_valid = 0; a.reserved2 = 0;
-    for (int j = 0; j < 24; ++j) a.wt[j] = 0.0;
-    if (b->weights_host && p->radius >= 0 && p->radius <= 23) {      // taps w[0..radius] (outermost first) as kernel parameters
+    for (int j = 0; j < 84; ++j) a.wt[j] = 0.0;
+    if (b->weights_host && p->radius >= 0 && p->radius <= 83) {      // taps w[0..radius] (outermost first) as kernel parameters
         for (int j = 0; j <= p->radius; ++j) a.wt[j] = b->weights_host[j];
         a.wt_valid = 1;
     }
@@ -145,8 +145,9 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     if (fast_ok) {
         int launched = 0;
         // single-warp CTAs (no block barriers) win for narrow update windows; wide windows (r > 30) use two warps
-        const int fnt = (g_k1_threads || g_env_k1_threads) ? nt : (p->radius <= 30 ? 32 : 64);
-        CU(aps::launch_fast(a, philox, st, g_use_fast == 1, fnt, &launched));
+        const bool forced = g_k1_threads || g_env_k1_threads;
+        const int fnt = forced ? nt : (p->radius <= 30 ? 32 : 64);
+        CU(aps::launch_fast(a, philox, st, g_use_fast == 1, fnt, forced ? 0 : 1, &launched));
         if (launched) { g_launches.fetch_add(launched); a.only_retry = 1; }   // last launch: replicas violating K = 1 only
     }
     switch (nt) {

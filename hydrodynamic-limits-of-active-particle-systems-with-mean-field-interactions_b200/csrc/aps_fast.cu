@@ -50,7 +50,7 @@ static cudaError_t launch_lean(const K1Args& a, bool philox, cudaStream_t st) {
 
 // Returns cudaSuccess and *launched = number of specialised kernels enqueued; *launched = 0 if the
 // configuration does not qualify (the caller then uses the generic kernel only).
-cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int* launched) {
+cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow_static, int nt, int auto_threads, int* launched) {
     *launched = 0;
     nt = nt == 32 ? 32 : 64;
     const int r1 = a.p.radius + 1, nm = a.b.n_max, lp = a.p.L + 2 * a.p.radius;
@@ -88,8 +88,24 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
             }
             return launch_class<21, 1024, 1056>(a, philox, st, nt);
         }
-        if (r1 <= 81 && nm <= 512 && lp <= 1184) return launch_class<81, 512, 1184>(a, philox, st, nt);
-        if (r1 <= 81 && nm <= 1024 && lp <= 1184) return launch_class<81, 1024, 1184>(a, philox, st, nt);
+        if (r1 <= 81 && nm <= 1024 && lp <= 1184) {
+            if (auto_threads && !g_env_no_lean) {            // (a forced thread count selects the two-warp kernel: A/B and its tests)
+                // wide filters (config 4: r = 80, 30 .. 700 particles per replica in one batch): the trimmed one-warp image by
+                // particle count — n <= 488 sorted (26 replicas per SM), then n <= 968 sorted (16 per SM), then the site-map variant
+                // for unsorted replicas; the full-size two-warp kernel (an 11.6 KB pre-multiplied tap table per replica) takes the rest
+                cudaError_t e = launch_lean<81, 1184, 512, false>(a, philox, st);
+                if (e != cudaSuccess) return e;
+                K1Args b = a;
+                b.only_retry = 2;
+                e = launch_lean<81, 1184, 1024, false>(b, philox, st);
+                if (e != cudaSuccess) return e;
+                e = launch_lean<81, 1184, 1024, true>(b, philox, st);
+                if (e != cudaSuccess) return e;
+                *launched = 4;
+                return nm <= 512 ? launch_class<81, 512, 1184>(b, philox, st, nt) : launch_class<81, 1024, 1184>(b, philox, st, nt);
+            }
+            return nm <= 512 ? launch_class<81, 512, 1184>(a, philox, st, nt) : launch_class<81, 1024, 1184>(a, philox, st, nt);
+        }
     }
     return launch_class<0, 0, 0>(a, philox, st, nt);
 }

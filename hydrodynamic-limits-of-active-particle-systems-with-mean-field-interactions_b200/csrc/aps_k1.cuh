@@ -46,9 +46,9 @@ struct K1Args {
     int32_t only_retry;   // 1: run only the replicas the fast kernel flagged (status == 100)
     int32_t reserved;
     int32_t bcode;        // 2K+1: radix of the per-site code c_plus + bcode*c_minus
-    int32_t wt_valid;     // 1: wt[] holds the taps w[0..radius] (radius <= 23): kernel-parameter = constant-bank operands
+    int32_t wt_valid;     // 1: wt[] holds the taps w[0..radius] (radius <= 83): kernel-parameter = constant-bank operands
     int32_t reserved2;
-    double wt[24];
+    double wt[84];
 };
 
 constexpr int kRing = 128;      // doubles of variate look-ahead kept in shared memory

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : (WHO ? 15 : 17)) k1_lea
     // ---------------- prologue ----------------
     for (int i = lane; i < L + 2 * pad; i += 32) code[i] = 0;
     if (WHO) for (int i = lane; i < L; i += 32) who[i] = 0xFFFFu;
-    if (lane <= r) F.wtab[lane] = B.weights[lane];
+    for (int j = lane; j <= r; j += 32) F.wtab[j] = B.weights[j];
     if (lane < 9) { const int am = lane / 3, ap = lane - am * 3; F.mst[lane] = make_double2((double)(ap - am), (double)(ap + am)); }
     if (lane < 16) F.desc[lane] = 0;
     F.dirty_c[lane] = 1;
@@ -202,11 +202,11 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : (WHO ? 15 : 17)) k1_lea
         const double w0 = F.wtab[r];
         const double2 m0 = mst_at(c[0]);
         double sc = APS_MUL(m0.x, w0), tc = APS_MUL(m0.y, w0);
-        if (decltype(hot)::value && r == RCAP - 1 && RCAP <= 24 && A.wt_valid) {
+        if (decltype(hot)::value && r == RCAP - 1 && RCAP <= 84 && A.wt_valid) {
 #pragma unroll
             for (int jj = -(RCAP - 1); jj < 0; ++jj) {
                 const double2 mm = mst_at((int)c[jj] + (int)c[-jj]);
-                const double wj = A.wt[RCAP <= 24 ? RCAP - 1 + jj : 0];  // kernel parameter: a constant-bank operand of the DFMA, no load
+                const double wj = A.wt[RCAP <= 84 ? RCAP - 1 + jj : 0];  // kernel parameter: a constant-bank operand of the DFMA, no load
                 sc = __fma_rn(mm.x, wj, sc);
                 tc = __fma_rn(mm.y, wj, tc);
             }
@@ -523,17 +523,16 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : (WHO ? 15 : 17)) k1_lea
             const int reach = r > 1 ? r : 1;
             const int mn = oldp < newp ? oldp : newp, mx = oldp < newp ? newp : oldp;
             const int wlo = mn - reach, whi = mx + reach;
-            const int ia = part - 31 + lane;                           // candidates part-31 .. part
-            const bool in_a = ia >= 0 && (int)pos[ia >= 0 ? ia : 0] >= wlo;
-            const unsigned ma = __ballot_sync(0xffffffffu, in_a);
-            // in_a is monotone in the lane (sorted positions): the first set lane is the lowest index in the window
-            int ilo = ma ? part - 31 + (__ffs(ma) - 1) : part;
-            if (ma == 0xffffffffu && part - 31 > 0) {
-                // more than 32 particles to the left inside the window: extend the search one more block
-                const int ib = part - 63 + lane;
-                const bool in_b = ib >= 0 && (int)pos[ib >= 0 ? ib : 0] >= wlo;
-                const unsigned mb = __ballot_sync(0xffffffffu, in_b);
-                if (mb) ilo = part - 63 + (__ffs(mb) - 1);
+            // lowest particle index inside the window: blocks of 32 candidates part-31 .. part, part-63 .. part-32, ... (the test is
+            // monotone in the lane because the positions are sorted, so the first set lane of the last non-empty block is the answer;
+            // one block for r = 20, up to three for r = 80)
+            int ilo = part;
+            for (int base = part - 31;; base -= 32) {
+                const int ia = base + lane;
+                const bool in_a = ia >= 0 && (int)pos[ia >= 0 ? ia : 0] >= wlo;
+                const unsigned ma = __ballot_sync(0xffffffffu, in_a);
+                if (ma) ilo = base + (__ffs(ma) - 1);
+                if (ma != 0xffffffffu || base <= 0) break;
             }
             for (int i0 = ilo; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
