@@ -518,7 +518,7 @@ def ensemble_main(args, torch, la, capi, rank, world):
             ncu_k1 = json.load(open(ncu_file)) if os.path.exists(ncu_file) else {}
             smem_traffic = ncu_k1.get("smem_bytes_per_event_at_128B_per_wavefront") if wl == "config2" else None
             kname = {"config2": "aps::k1_lean_kernel<true,21,1056,512,false>", "config3": "aps::k1_lean_kernel<true,21,1056,1024,false>",
-                     "config4": "aps::k1_fast_kernel<64,true,81,...>"}[wl]
+                     "config4": "aps::k1_lean_kernel<true,81,1184,{512,1024},false>"}[wl]
             roofline = dict(bound="smem", kernel=kname,
                             achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                             traffic=(smem_traffic * events_per_launch if smem_traffic else None),
