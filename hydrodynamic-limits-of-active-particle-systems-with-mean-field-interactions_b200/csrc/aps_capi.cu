@@ -132,8 +132,8 @@ int run_device(const aps_params* p, const aps_batch* b, void* stream, bool philo
     const size_t smem = aps::k1_smem_bytes(p->L, b->n_max, p->radius, a.max_nodes, nt / 32, a.use_lut, p->K);
     if (smem > 227 * 1024) return fail(APS_ERR_CAPACITY, "replica does not fit in 227 KB of shared memory");
     cudaStream_t st = (cudaStream_t)stream;
-    a.only_retry = 0; a.reserved = 0;
-    a.wt_valid = 0; a.reserved2 = 0;
+    a.only_retry = 0; a.n_lo = -1;
+    a.wt_valid = 0; a.n_hi = 0x7fffffff;
     for (int j = 0; j < 84; ++j) a.wt[j] = 0.0;
     if (b->weights_host && p->radius >= 0 && p->radius <= 83) {      // taps w[0..radius] (outermost first) as kernel parameters
         for (int j = 0; j <= p->radius; ++j) a.wt[j] = b->weights_host[j];

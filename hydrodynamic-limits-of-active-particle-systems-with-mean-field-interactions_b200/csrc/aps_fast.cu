@@ -31,6 +31,21 @@ static cudaError_t launch_class(const K1Args& a, bool philox, cudaStream_t st, i
     return nt == 32 ? launch_nt<32, RCAP, NCAP, LPCAP>(a, philox, st) : launch_nt<64, RCAP, NCAP, LPCAP>(a, philox, st);
 }
 
+// side stream for size classes of one batch that run concurrently (one per host thread and device, created on first use)
+struct SideStream { int dev; cudaStream_t stream; cudaEvent_t fork, join; };
+static SideStream* side_stream() {
+    thread_local SideStream s{-1, nullptr, nullptr, nullptr};
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    if (s.dev == dev && s.stream) return &s;
+    SideStream n{dev, nullptr, nullptr, nullptr};
+    if (cudaStreamCreateWithFlags(&n.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n.join, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    s = n;                                              // (a thread that changes device leaks one stream and two events: by design rare)
+    return &s;
+}
+
 template <int RCAP, int LPCAP, int NCAP, bool WHO>
 static cudaError_t launch_lean(const K1Args& a, bool philox, cudaStream_t st) {
     const size_t smem = k1_lean_smem_bytes<RCAP, LPCAP, NCAP, WHO>();
@@ -93,12 +108,25 @@ cudaError_t launch_fast(const K1Args& a, bool philox, cudaStream_t st, int allow
                 // wide filters (config 4: r = 80, 30 .. 700 particles per replica in one batch): the trimmed one-warp image by
                 // particle count — n <= 488 sorted (26 replicas per SM), then n <= 968 sorted (16 per SM), then the site-map variant
                 // for unsorted replicas; the full-size two-warp kernel (an 11.6 KB pre-multiplied tap table per replica) takes the rest
-                cudaError_t e = launch_lean<81, 1184, 512, false>(a, philox, st);
+                // The two sorted classes own disjoint replicas (by n), so they run CONCURRENTLY (fork / join on a side stream):
+                // a launch lasts as long as its longest replica chain, and with few replicas per GPU (strong scaling) two partial
+                // waves in sequence would double the step.
+                SideStream* ss = side_stream();
+                K1Args a1 = a, a2 = a;
+                a1.n_hi = kLeanNMax;
+                a2.n_lo = kLeanNMax;
+                cudaError_t e = ss ? cudaEventRecord(ss->fork, st) : cudaSuccess;
                 if (e != cudaSuccess) return e;
+                e = launch_lean<81, 1184, 512, false>(a1, philox, st);
+                if (e != cudaSuccess) return e;
+                if (ss) {
+                    if ((e = cudaStreamWaitEvent(ss->stream, ss->fork, 0)) != cudaSuccess) return e;
+                    if ((e = launch_lean<81, 1184, 1024, false>(a2, philox, ss->stream)) != cudaSuccess) return e;
+                    if ((e = cudaEventRecord(ss->join, ss->stream)) != cudaSuccess) return e;
+                    if ((e = cudaStreamWaitEvent(st, ss->join, 0)) != cudaSuccess) return e;
+                } else if ((e = launch_lean<81, 1184, 1024, false>(a2, philox, st)) != cudaSuccess) return e;
                 K1Args b = a;
                 b.only_retry = 2;
-                e = launch_lean<81, 1184, 1024, false>(b, philox, st);
-                if (e != cudaSuccess) return e;
                 e = launch_lean<81, 1184, 1024, true>(b, philox, st);
                 if (e != cudaSuccess) return e;
                 *launched = 4;

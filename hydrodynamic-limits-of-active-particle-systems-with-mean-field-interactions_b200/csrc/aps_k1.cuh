@@ -44,10 +44,10 @@ struct K1Args {
     int32_t pad;          // halo width = max(radius, 0)
     int32_t use_lut;      // 1: filter taps come from the product table (see local_m_lut)
     int32_t only_retry;   // 1: run only the replicas the fast kernel flagged (status == 100)
-    int32_t reserved;
+    int32_t n_lo;         // lean kernels: a launch owns the replicas with n_lo < n <= n_hi and leaves the others untouched (size classes
     int32_t bcode;        // 2K+1: radix of the per-site code c_plus + bcode*c_minus
     int32_t wt_valid;     // 1: wt[] holds the taps w[0..radius] (radius <= 83): kernel-parameter = constant-bank operands
-    int32_t reserved2;
+    int32_t n_hi;         // of one batch run as independent, concurrent launches); -1 / INT_MAX = all replicas
     double wt[84];
 };
 

@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(32, NCAP <= 512 ? 28 : (WHO ? 15 : 17)) k1_lea
     const double beta = B.beta[rep], T = P.T, D = P.rate_diffusion, lam = P.rate_active;
 
     if (A.only_retry == 2 && B.status[rep] != APS_RUN_RETRY_FAST) return;   // later launch of the chain: earlier rejects only
+    if (n <= A.n_lo || n > A.n_hi) return;                                   // another size class of this batch owns the replica
     LeanFixed<RCAP>& F = *reinterpret_cast<LeanFixed<RCAP>*>(smem_raw);
     unsigned char* dyn = smem_raw + ((sizeof(LeanFixed<RCAP>) + 15) & ~(size_t)15);
     double* const rates = reinterpret_cast<double*>(dyn); dyn += (size_t)NCAP * 8;
