@@ -13,5 +13,5 @@ APS_BENCH_NO_SAMPLER=1 ncu --metrics gpu__time_duration.sum --clock-control none
 ncu --set full --clock-control none --import-source on -k regex:k1_lean -c 1 -o gpurun_out/r2_k1_lean python tools/quick_bench.py --replicas 4144 --T 2 --reps 1 > gpurun_out/r2_ncu_k1.log 2>&1; echo "ncu k1 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:k2_pass -s 12 -c 1 -o gpurun_out/r2_k2_local_final python tools/k2_bench.py --logL 26 --case "local sigma=5 dt=0.005" --passes 20 > gpurun_out/r2_ncu_k2l.log 2>&1; echo "ncu k2 local rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:k2_pass -s 12 -c 1 -o gpurun_out/r2_k2_global_final python tools/k2_bench.py --logL 26 --case "global dt=0.02" --passes 20 > gpurun_out/r2_ncu_k2g.log 2>&1; echo "ncu k2 global rc=$?"
-python tools/k2_dt_bias.py --replicas 192 --out gpurun_out/r2_k2_dt_bias.json > gpurun_out/r2_k2_dt_bias.md 2> gpurun_out/r2_k2_dt_bias.err; cat gpurun_out/r2_k2_dt_bias.md
+python tools/k2_dt_bias.py --replicas 768 --out gpurun_out/r2_k2_dt_bias.json > gpurun_out/r2_k2_dt_bias.md 2> gpurun_out/r2_k2_dt_bias.err; cat gpurun_out/r2_k2_dt_bias.md
 ls -la gpurun_out/*.ncu-rep
