@@ -55,6 +55,7 @@ static double pairwise_sum(const double* a, int64_t n) {
 }
 double aps_oracle_pairwise_sum(const double* a, int64_t n) { return pairwise_sum(a, n); }
 
+double aps_oracle_native_total(const double* rates, int n) { return aps_native_total(rates, n); }   /* native-mode R (aps_math.h) */
 double aps_oracle_exp(double x) { return aps_exp(x); }
 double aps_oracle_log(double x) { return aps_log(x); }
 void aps_oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {

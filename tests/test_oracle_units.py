@@ -51,6 +51,56 @@ def test_philox_known_answers():
         assert o.tolist() == want
 
 
+def test_native_total_follows_its_written_definition():
+    """Native-mode total rate (include/aps_math.h): chunks of CS = 16 * 2^k rates (k smallest with <= 32 chunks, rates beyond n are
+    0.0), chunk sum = T16 of the first 16 rates plus, left to right, T16 of every further block of 16 starting below n, T16 = adjacent
+    pairwise tree; R = last lane of a 32-lane Hillis-Steele scan of the chunk sums.  Restated here with numpy float64 scalars and
+    compared bit for bit; the kernels are compared with the oracle in the GPU tests."""
+    import ctypes
+    lib = oracle.load()
+    lib.aps_oracle_native_total.restype = ctypes.c_double
+    lib.aps_oracle_native_total.argtypes = [ctypes.c_void_p, ctypes.c_int]
+
+    def t16(r, lo, n):
+        a = [np.float64(r[lo + k]) if lo + k < n else np.float64(0.0) for k in range(16)]
+        w = 1
+        while w < 16:
+            for k in range(0, 16, 2 * w):
+                a[k] = a[k] + a[k + w]
+            w *= 2
+        return a[0]
+
+    def total(r):
+        n = len(r)
+        sh = 4
+        while ((n + (1 << sh) - 1) >> sh) > 32:
+            sh += 1
+        cs = 1 << sh
+        v = []
+        for j in range(32):
+            lo = j << sh
+            if lo >= n:
+                v.append(np.float64(0.0)); continue
+            c = t16(r, lo, n)
+            b = lo + 16
+            while b < lo + cs and b < n:
+                c = c + t16(r, b, n); b += 16
+            v.append(c)
+        o = 1
+        while o < 32:
+            v = [v[l] + v[l - o] if l >= o else v[l] for l in range(32)]
+            o *= 2
+        return v[31]
+
+    g = np.random.default_rng(5)
+    for n in [1, 2, 15, 16, 17, 31, 33, 369, 488, 511, 512, 513, 700, 968, 1024, 1500, 2048, 3000]:
+        r = np.ascontiguousarray(g.random(n) * 7.0 + 0.01)
+        got = lib.aps_oracle_native_total(r.ctypes.data, n)
+        want = total(r)
+        assert np.float64(got).view(np.uint64) == np.float64(want).view(np.uint64), n
+        assert abs(got - r.sum()) <= 1e-12 * r.sum()
+
+
 def test_pairwise_sum_equals_numpy_sum():
     """R = rates.sum() (CLASS.py:352) is numpy's pairwise summation."""
     lib = oracle.load()
