@@ -513,6 +513,15 @@ def ensemble_main(args, torch, la, capi, rank, world):
             k1_avg_ms = k1_ms / args.steps
             sm_mhz = (clocks.get("sm_max_mhz") or 1965)
             peak = 148 * 128 * sm_mhz * 1e6 / 1e9
+            peak_source = ("computed 148 SM x 128 B/clk x clocks.max.sm (shared-memory bandwidth is not in MEASURED_PEAKS.json); "
+                           "HBM traffic of K1 is only the observation rows")
+            sp_file = os.path.join(ROOT, "profiles", "smem_peak.json")
+            if os.path.exists(sp_file):        # measured on a B200 of this pool with tools/smem_peak.py (LDS.128 microbenchmark): 99.8 % of the formula
+                sp = json.load(open(sp_file))
+                peak = float(sp["smem_read_gbs"])
+                peak_source = ("MEASURED shared-memory read bandwidth, tools/smem_peak.py -> profiles/smem_peak.json (%.1f B/clk/SM at the max clock; "
+                               "MEASURED_PEAKS.json has no shared-memory figure; formula 148 x 128 B/clk x 1965 MHz = 37 225 GB/s); "
+                               "HBM traffic of K1 is only the observation rows" % sp["bytes_per_clk_per_sm_at_max_clock"])
             achieved = bytes_per_event * events_per_launch / (k1_avg_ms * 1e-3) / 1e9
             ncu_file = os.path.join(ROOT, "profiles", "k1_ncu_summary.json")
             ncu_k1 = json.load(open(ncu_file)) if os.path.exists(ncu_file) else {}
@@ -523,8 +532,7 @@ def ensemble_main(args, torch, la, capi, rank, world):
                             achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                             traffic=(smem_traffic * events_per_launch if smem_traffic else None),
                             traffic_note="shared-memory wavefronts x 128 B per launch from the ncu capture (DRAM traffic of K1 is ~0.1 GB per launch)",
-                            peak_source="computed 148 SM x 128 B/clk x clocks.max.sm (shared-memory bandwidth is not in MEASURED_PEAKS.json); "
-                                        "HBM traffic of K1 is only the observation rows",
+                            peak_source=peak_source,
                             algorithmic_bytes_per_event=bytes_per_event, events_per_launch=events_per_launch, kernel_ms=k1_avg_ms,
                             kernel_share_of_step=k1_avg_ms * args.steps / total_ms, ncu=ncu_k1 if wl == "config2" else None)
         cpu_baseline = None if args.no_cpu_baseline else cpu_arm(wl, 12.0)
