@@ -15,10 +15,13 @@
 //     hop flags are two neighbour reads, the accumulator slot is recomputed from the index;
 //   * cached pairwise accumulators and chunk sums in shared memory: the 8 accumulators of a dirty leaf are re-summed
 //     by 8 lanes in lock-step anyway, the chunk sum of lane c lives in a register of lane c.
-// Two instantiations: <NCAP = 512, WHO = false> as described (sorted inputs, 28 replicas per SM) and <NCAP = 1024, WHO = true>,
-// which keeps the site map and therefore takes any particle order (n <= 968, 15 replicas per SM instead of the fast kernel's 10).
-// Limits: single-warp CTAs, n_max <= 512 and n <= 488 per replica (<= 4 leaves in numpy's pairwise tree; larger replicas go to
-// the fast kernel like the unsorted ones), r + 1 <= RCAP, L + 2r <= LPCAP.
+// Instantiations (aps_fast.cu): RCAP = 21 (r <= 20) and RCAP = 81 (r <= 80, config 4) x
+//   <NCAP = 512, WHO = false> as described (sorted inputs, n <= 488: <= 4 leaves in numpy's pairwise tree; 28 / 26 replicas per SM),
+//   <NCAP = 1024, WHO = false> sorted inputs up to n = 968 (<= 8 leaves; 17 / 16 per SM; config 3),
+//   <NCAP = 512 | 1024, WHO = true> which keep the site map and therefore take any particle order (22 / 15 per SM; the fast kernel: 10).
+// Round 2 (profiles/r2_k1.md): native-mode R from the selection scan, site codes pre-scaled to table offsets, taps as kernel
+// parameters, tree-of-16 chunk sums, the decided event broadcast by shuffles, size classes of one batch launched concurrently.
+// Limits: single-warp CTAs, r + 1 <= RCAP, L + 2r <= LPCAP, n within the class; anything else falls through to the fast kernel.
 #pragma once
 #include <type_traits>
 
